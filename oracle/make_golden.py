@@ -1,0 +1,289 @@
+"""Pin the oracle against the reference itself and mint the golden fixtures.  Test infrastructure only.
+
+Run in the BUILD container only (needs /root/reference and torchaudio):
+    python -m oracle.make_golden
+It (1) imports the reference's own modules, (2) asserts every oracle restatement equals the reference
+on seeded inputs, (3) writes small fixtures to tests/golden/*.npz which the CPU and GPU tests compare
+against (the GPU box has no /root/reference).
+"""
+import importlib.util
+import os
+import re
+import random
+import sys
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _load(path, name):
+    s = importlib.util.spec_from_file_location(name, path)
+    m = importlib.util.module_from_spec(s)
+    s.loader.exec_module(m)
+    return m
+
+
+def gen_wave(seed, B, L=160000, sigma=0.1):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, L, generator=g) * sigma
+
+
+def main():
+    sys.path.insert(0, REF)
+    from desed_task.nnet.CRNN import CRNN                                   # noqa
+    from desed_task.data_augm import mixup as ref_mixup, frame_shift as ref_frame_shift, add_noise as ref_add_noise
+    RefScaler = _load(f"{REF}/desed_task/utils/scaler.py", "ref_scaler").TorchScaler
+    RefWarm = _load(f"{REF}/desed_task/utils/schedulers.py", "ref_sched").ExponentialWarmup
+    RefMedian = _load(f"{REF}/desed_task/utils/postprocess.py", "ref_post").ClassWiseMedianFilter
+    import scipy.ndimage
+    from torchaudio.transforms import AmplitudeToDB, MelSpectrogram
+
+    from oracle import crnn as ocrnn, frontend as ofe, postprocess as opost, trainer as otr
+
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    report = {}
+
+    # ------------------------------------------------------------------ front end
+    mel_ref = MelSpectrogram(sample_rate=16000, n_fft=2048, win_length=2048, hop_length=256, f_min=0, f_max=8000,
+                             n_mels=128, window_fn=torch.hamming_window, wkwargs={"periodic": False}, power=1)
+    a2db = AmplitudeToDB(stype="amplitude")
+    a2db.amin = 1e-5
+    fb = ofe.melscale_fbanks()
+    win = ofe.hamming_window()
+    assert torch.equal(fb, mel_ref.mel_scale.fb), "fb differs from torchaudio"
+    assert torch.equal(win, mel_ref.spectrogram.window), "window differs from torchaudio"
+    wave = gen_wave(0, 2)
+    wave_short = gen_wave(1, 3, 16000)
+    tone = 0.3 * torch.sin(2 * np.pi * 440.0 * torch.arange(160000) / 16000.0)[None] + gen_wave(2, 1) * 1e-2
+    silent = torch.zeros(1, 160000)
+    silent[0, 50000:50100] = 1e-4
+    outs = {}
+    for name, w in [("wave", wave), ("short", wave_short), ("tone", tone), ("silent", silent)]:
+        m_ref = mel_ref(w)
+        m_or = ofe.mel_spectrogram(w)
+        assert torch.equal(m_ref, m_or), f"mel oracle != torchaudio on {name}: {(m_ref - m_or).abs().max()}"
+        l_ref = a2db(m_ref).clamp(min=-50, max=80)
+        l_or = ofe.take_log(m_or)
+        assert torch.equal(l_ref, l_or), name
+        s_ref = RefScaler("instance", "minmax", [1, 2])(l_ref)
+        s_or = ofe.scaler(l_or)
+        assert torch.equal(s_ref, s_or), name
+        outs[name] = (m_or, l_or, s_or)
+    for stat, norm in [("instance", "standard"), ("instance", "mean")]:
+        assert torch.equal(RefScaler(stat, norm, [1, 2])(outs["wave"][1]), ofe.scaler(outs["wave"][1], stat, norm))
+    np.savez(os.path.join(OUT, "frontend.npz"),
+             wave_seed=0, wave_short=wave_short.numpy(), tone=tone.numpy().astype(np.float32),
+             mel_wave0=outs["wave"][0][0].numpy(), logmel_wave=outs["wave"][1].numpy(),
+             logmel_short=outs["short"][1].numpy(), mel_short=outs["short"][0].numpy(),
+             logmel_tone=outs["tone"][1].numpy(), logmel_silent_minmax=np.array(
+                 [outs["silent"][1].min().item(), outs["silent"][1].max().item()], np.float32),
+             scaled_short=outs["short"][2].numpy(),
+             fb_sum=fb.sum().item(), fb_nnz=int((fb != 0).sum()), win_sum=win.sum().item(),
+             wave_head=wave[:, :8].numpy())
+    report["frontend"] = "oracle == torchaudio/reference bit-exact (mel, log, scaler) on 4 inputs"
+
+    # ------------------------------------------------------------------ CRNN
+    import yaml
+    cfg23 = yaml.safe_load(open(f"{REF}/recipes/dcase2023_task4_baseline/confs/default.yaml"))
+    cfg24 = yaml.safe_load(open(f"{REF}/recipes/dcase2024_task4_baseline/confs/pretrained.yaml"))
+    feats = outs["wave"][2]                                  # [2,128,626]
+    gold = {}
+    for tag, ycfg, ocfg in [("2023", cfg23, ocrnn.CFG_2023), ("2024", cfg24, ocrnn.CFG_2024)]:
+        for trained_like in (False, True):
+            P = ocrnn.init_params(ocfg, seed=42, trained_like=trained_like)
+            net = CRNN(**ycfg["net"])
+            missing = net.load_state_dict(P, strict=True)
+            assert [n for n, _ in net.named_parameters()] == ocrnn.param_names(P), "parameter order differs"
+            emb = None
+            cmask = None
+            if ocfg.use_embeddings:
+                g = torch.Generator().manual_seed(7)
+                emb = torch.randn(2, 768, 496, generator=g)
+                cmask = torch.zeros(2, 27, dtype=torch.bool)
+                cmask[0, :10] = True
+                cmask[1, 10:] = True
+            # eval
+            net.eval()
+            with torch.no_grad():
+                s_ref, w_ref = net(feats, embeddings=emb, classes_mask=cmask)
+                col = {}
+                s_or, w_or = ocrnn.crnn_forward(P, feats, ocfg, False, embeddings=emb, classes_mask=cmask, collect=col)
+                s_at, w_at = ocrnn.crnn_forward(P, feats, ocfg, False, embeddings=emb, classes_mask=cmask,
+                                                gru_impl="aten")
+            d = max((s_ref - s_or).abs().max().item(), (w_ref - w_or).abs().max().item())
+            d2 = max((s_ref - s_at).abs().max().item(), (w_ref - w_at).abs().max().item())
+            assert d < 2e-6 and d2 < 2e-6, (tag, d, d2)
+            report[f"crnn{tag}_eval_tl{int(trained_like)}"] = f"max|oracle-ref| = {d:.2e} (loop GRU), {d2:.2e} (aten GRU)"
+            key = f"{tag}_tl{int(trained_like)}"
+            gold[f"strong_eval_{key}"] = s_ref.numpy()
+            gold[f"weak_eval_{key}"] = w_ref.numpy()
+            gold[f"cnn_out_eval_{key}"] = col["cnn_out"].numpy()
+            gold[f"rnn_out_eval_{key}"] = col["rnn_out"][:, ::13].numpy()
+            # train mode, RNG-free (dropout 0, specaug off): forward + grads
+            ycfg_t = dict(ycfg["net"], dropout=0.0, specaugm_t_p=0.0, specaugm_f_p=0.0, dropstep_recurrent=0.0)
+            net_t = CRNN(**ycfg_t)
+            net_t.load_state_dict(P, strict=True)
+            net_t.train()
+            s_ref, w_ref = net_t(feats, embeddings=emb, classes_mask=cmask)
+            g = torch.Generator().manual_seed(11)
+            ys = (torch.rand(s_ref.shape, generator=g) < 0.1).float()
+            yw = (ys.sum(-1) > 0).float()
+            loss_ref = torch.nn.BCELoss()(s_ref, ys) + torch.nn.BCELoss()(w_ref, yw)
+            loss_ref.backward()
+            import dataclasses
+            ocfg_t = dataclasses.replace(ocfg, dropout=0.0)
+            Pt = {k: (v.clone().requires_grad_(True) if ocrnn.is_float_param(k) else v.clone()) for k, v in P.items()}
+            bn_state = {}
+            s_or, w_or = ocrnn.crnn_forward(Pt, feats, ocfg_t, True, embeddings=emb, classes_mask=cmask, bn_state=bn_state)
+            loss_or = otr.bce(s_or, ys) + otr.bce(w_or, yw)
+            loss_or.backward()
+            assert abs(loss_ref.item() - loss_or.item()) < 1e-6
+            gmax = 0.0
+            # gradients that are exactly 0 in real arithmetic (conv biases in front of a train-mode BatchNorm,
+            # attention biases of near-uniform softmax) are fp32 noise: measure against the global gradient scale
+            gscale = max(p.grad.abs().max().item() for p in net_t.parameters())
+            for n, p in net_t.named_parameters():
+                gr = p.grad
+                go = Pt[n].grad
+                if re.fullmatch(r"cnn\.cnn\.conv\d\.bias", n) and ocfg.normalization == "batch":
+                    # exact gradient is 0 (bias cancels in train-mode BN); both sides must be noise-level
+                    assert max(gr.abs().max().item(), go.abs().max().item()) < 1e-3 * gscale, (n, gscale)
+                    continue
+                rel = (gr - go).abs().max().item() / max(gr.abs().max().item(), 1e-2 * gscale)
+                if rel > 2e-4:
+                    print("grad mismatch", tag, n, rel, gr.abs().max().item())
+                gmax = max(gmax, rel)
+                gold[f"gradnorm_{key}_{n}"] = np.float32(gr.norm().item())
+            assert gmax < 2e-4, (tag, gmax)
+            for n, b in net_t.named_buffers():
+                if n in bn_state:
+                    assert (b - bn_state[n]).abs().max().item() < 1e-5, n
+            gold[f"bn0_running_mean_{key}"] = dict(net_t.named_buffers())["cnn.cnn.batchnorm0.running_mean"].numpy()
+            gold[f"bn6_running_var_{key}"] = dict(net_t.named_buffers())["cnn.cnn.batchnorm6.running_var"].numpy()
+            gold[f"strong_train_{key}"] = s_ref.detach().numpy()
+            gold[f"weak_train_{key}"] = w_ref.detach().numpy()
+            gold[f"loss_train_{key}"] = np.float32(loss_ref.item())
+            gold[f"grad_dense_w_{key}"] = net_t.dense.weight.grad.numpy()
+            gold[f"grad_conv0_w_{key}"] = net_t.cnn.cnn.conv0.weight.grad.numpy()
+            gold[f"grad_whh_l0_{key}"] = net_t.rnn.rnn.weight_hh_l0.grad[::16].numpy()
+            gold[f"labels_strong_{key}"] = ys.numpy()
+            report[f"crnn{tag}_train_tl{int(trained_like)}"] = f"loss equal, max rel grad diff = {gmax:.2e}"
+            gold[f"param_checksum_{key}"] = np.float64(sum(v.double().sum().item() for k, v in P.items()))
+    gold["emb_seed"] = 7
+    np.savez(os.path.join(OUT, "crnn.npz"), **gold)
+
+    # specaugment draw parity (torchaudio mask_along_axis_iid via CRNN.apply_specaugment)
+    net = CRNN(**cfg23["net"])
+    net.train()
+    torch.manual_seed(123)
+    x = torch.randn(4, 128, 626)
+    xa_ref = net.apply_specaugment(x.clone())
+    torch.manual_seed(123)
+    torch.randn(4, 128, 626)
+    spec = otr_draw_spec(4, 128, 626)
+    xa_or = ocrnn.apply_specaugment(x.clone(), spec)
+    assert torch.equal(xa_ref, xa_or), "specaugment restatement differs"
+    report["specaugment"] = "oracle draw+mask == CRNN.apply_specaugment under the same torch seed"
+
+    # ------------------------------------------------------------------ augmentation
+    np.random.seed(5)
+    torch.manual_seed(5)
+    data = torch.rand(12, 128, 626)
+    tgt = (torch.rand(12, 10, 156) < 0.1).float()
+    st = (np.random.get_state(), torch.get_rng_state())
+    md_ref, mt_ref = ref_mixup(data, tgt, mixup_label_type="soft")
+    np.random.set_state(st[0]); torch.set_rng_state(st[1])
+    c, perm = otr.draw_mixup(12)
+    md, mt = otr.mixup(data, tgt, c, perm, "soft")
+    assert torch.equal(md, md_ref) and torch.equal(mt, mt_ref)
+    _, mth_ref = (lambda: (np.random.set_state(st[0]), torch.set_rng_state(st[1]), ref_mixup(data, tgt, mixup_label_type="hard"))[2])()
+    assert torch.equal(otr.mixup(data, tgt, c, perm, "hard")[1], mth_ref)
+    random.seed(9)
+    fs_ref = ref_frame_shift(data, tgt)
+    random.seed(9)
+    shifts = otr.draw_frame_shift(12)
+    fs_or = otr.frame_shift(data, tgt, shifts)
+    assert torch.equal(fs_ref[0], fs_or[0]) and torch.equal(fs_ref[1], fs_or[1])
+    torch.manual_seed(3)
+    an_ref = ref_add_noise(data)
+    torch.manual_seed(3)
+    snr = (6 - 30) * torch.rand((12,)) + 30
+    noise = torch.randn(data.shape)
+    an_or = otr.add_noise(data, snr, noise)
+    assert torch.allclose(an_ref, an_or, atol=1e-6)
+    report["augm"] = "mixup soft/hard, frame_shift bit-exact; add_noise <=1e-6"
+    np.savez(os.path.join(OUT, "augm.npz"), mix_c=np.float64(c), mix_perm=perm.numpy(), data_seed=5,
+             mixed_head=md_ref[:, :4, :8].numpy(), mixed_target_sum=np.float64(mt_ref.double().sum().item()),
+             shifts=np.array(shifts))
+
+    # ------------------------------------------------------------------ schedule, median
+    opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], 1e-3)
+    sch = RefWarm(opt, 1e-3, 1000)
+    for step in (1, 10, 500, 1000, 2000):
+        sch.step_num = step
+        assert abs(sch._get_scaling_factor() - otr.warmup_scale(step, 1000)) < 1e-12
+    rng = np.random.RandomState(0)
+    sc = rng.rand(156, 10).astype(np.float32)
+    for k in (1, 2, 3, 4, 7, 8, 13, 17):
+        ref = scipy.ndimage.median_filter(sc, (k, 1))
+        assert np.array_equal(ref, opost.median_filter_time(sc, k)), k
+    lens = [1, 3, 5, 7, 9, 11, 13, 15, 17, 7]
+    assert np.array_equal(RefMedian(lens)(sc), opost.classwise_median_filter(sc, lens))
+    small = np.array([0, 1, 4, 2, 2, 4, 1, 0, 1, 4], np.float32)[:, None]
+    assert opost.median_filter_time(small, 7)[:, 0].tolist() == [1, 1, 2, 2, 2, 2, 2, 2, 1, 1]
+    np.savez(os.path.join(OUT, "median.npz"), scores=sc, med7=scipy.ndimage.median_filter(sc, (7, 1)),
+             lens=np.array(lens), med_cw=RefMedian(lens)(sc))
+    report["median"] = "oracle == scipy.ndimage.median_filter for k in 1..17 incl. even k; classwise == reference"
+
+    # Adam restatement vs torch.optim.Adam
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(1000, generator=g)
+    pr = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([pr], 1e-3, betas=(0.9, 0.999))
+    P = {"p": p0.clone()}
+    state = {}
+    for it in range(5):
+        gr = torch.randn(1000, generator=g)
+        pr.grad = gr.clone()
+        opt.step()
+        otr.adam_step(P, {"p": gr}, state, ["p"], 1e-3)
+    assert (pr.data - P["p"]).abs().max().item() < 1e-7
+    report["adam"] = "oracle adam_step == torch.optim.Adam (5 steps, <=1e-7)"
+
+    with open(os.path.join(OUT, "PINNING.txt"), "w") as f:
+        f.write("oracle pinned against the live reference (commit c6bcb45b) + torchaudio %s, torch %s\n"
+                % (__import__("torchaudio").__version__, torch.__version__))
+        for k, v in report.items():
+            f.write(f"{k}: {v}\n")
+        f.write("NOT pinned live (pytorch_lightning absent): the SEDTask4.training_step composition itself; "
+                "its components (mixup, scaler, CRNN, BCELoss/MSELoss, warm-up, Adam) are each pinned above.\n")
+    for k, v in report.items():
+        print(k, "->", v)
+
+
+def otr_draw_spec(B, n_f, n_t, f_l=10, f_p=0.2, t_l=5, t_p=0.2):
+    """Restates the draw order of CRNN.apply_specaugment (CRNN.py:207-219) through
+    torchaudio functional.py:857-869: per mask, value=rand(B)*param; min_value=rand(B)*(size-value)."""
+    def one(size, l, p):
+        param = l if p == 1.0 else min(l, int(size * p))
+        if param < 1:
+            return None
+        value = torch.rand(B) * param
+        min_value = torch.rand(B) * (size - value)
+        return min_value.long(), min_value.long() + value.long()
+    spec = {}
+    f = one(n_f, f_l, f_p)
+    if f is not None:
+        spec["f_start"], spec["f_end"] = f
+    t = one(n_t, t_l, t_p)
+    if t is not None:
+        spec["t_start"], spec["t_end"] = t
+    return spec
+
+
+if __name__ == "__main__":
+    main()
