@@ -1,0 +1,383 @@
+// HBM-bound elementwise / reduction kernels: mixup + log + per-clip min/max, scaler modes, label mixup, frame shift,
+// additive noise, fused Adam + EMA over a flat parameter buffer, median filter.
+// All are streaming kernels: 128-bit loads/stores where alignment allows, grid sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace sedk {
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+__device__ __forceinline__ float amp_to_db(float v, float amin, float lo, float hi) {
+    float d = 20.0f * log10f(fmaxf(v, amin));
+    return fminf(fmaxf(d, lo), hi);
+}
+
+__global__ void minmax_init_kernel(uint32_t* mm, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) {
+        mm[2 * i] = f2ord(INFINITY);
+        mm[2 * i + 1] = f2ord(-INFINITY);
+    }
+}
+__global__ void minmax_decode_kernel(const uint32_t* mm, float* out, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * B) out[i] = ord2f(mm[i]);
+}
+
+// grid = (chunks, B); each CTA streams a contiguous slice of one clip
+template <bool VEC>
+__global__ void __launch_bounds__(EW_THREADS)
+feat_mix_log_kernel(const float* __restrict__ x, const int64_t* __restrict__ perm, const float* __restrict__ coef,
+                    float* __restrict__ out, int64_t n, int log_mode, float amin, float lo, float hi,
+                    uint32_t* __restrict__ minmax) {
+    const int b = blockIdx.y;
+    const float* xa = x + (size_t)b * n;
+    const float* xb = perm ? x + (size_t)perm[b] * n : nullptr;
+    const float c = (perm && coef) ? coef[b] : 1.0f;
+    const float c1 = 1.0f - c;
+    float* o = out + (size_t)b * n;
+    float vmin = INFINITY, vmax = -INFINITY;
+    if (VEC) {
+        const int64_t n4 = n >> 2;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+            float4 a = reinterpret_cast<const float4*>(xa)[i];
+            if (xb) {
+                float4 p = reinterpret_cast<const float4*>(xb)[i];
+                a.x = c * a.x + c1 * p.x; a.y = c * a.y + c1 * p.y; a.z = c * a.z + c1 * p.z; a.w = c * a.w + c1 * p.w;
+            }
+            if (log_mode) {
+                a.x = amp_to_db(a.x, amin, lo, hi); a.y = amp_to_db(a.y, amin, lo, hi);
+                a.z = amp_to_db(a.z, amin, lo, hi); a.w = amp_to_db(a.w, amin, lo, hi);
+            }
+            reinterpret_cast<float4*>(o)[i] = a;
+            vmin = fminf(fminf(vmin, a.x), fminf(fminf(a.y, a.z), a.w));
+            vmax = fmaxf(fmaxf(vmax, a.x), fmaxf(fmaxf(a.y, a.z), a.w));
+        }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+            float a = xa[i];
+            if (xb) a = c * a + c1 * xb[i];
+            if (log_mode) a = amp_to_db(a, amin, lo, hi);
+            o[i] = a;
+            vmin = fminf(vmin, a);
+            vmax = fmaxf(vmax, a);
+        }
+    }
+    if (minmax) {
+        vmin = warp_min(vmin);
+        vmax = warp_max(vmax);
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(minmax + 2 * b, f2ord(vmin));
+            atomicMax(minmax + 2 * b + 1, f2ord(vmax));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+minmax_scale_kernel(const float* __restrict__ x, float* __restrict__ out, const uint32_t* __restrict__ minmax,
+                    int64_t n, float eps) {
+    const int b = blockIdx.y;
+    const float mn = ord2f(minmax[2 * b]), mx = ord2f(minmax[2 * b + 1]);
+    const float den = mx - mn + eps;
+    const float* xa = x + (size_t)b * n;
+    float* o = out + (size_t)b * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        o[i] = (xa[i] - mn) / den * 2.0f - 1.0f;
+}
+
+// one CTA per clip: two-pass mean / unbiased std in fp32 with fp64 block combine
+__global__ void __launch_bounds__(EW_THREADS) instance_stats_kernel(const float* __restrict__ x, float* __restrict__ stats,
+                                                                    int64_t n) {
+    __shared__ double red[EW_THREADS / 32];
+    __shared__ double s_mean;
+    const int b = blockIdx.x;
+    const float* xa = x + (size_t)b * n;
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += (double)xa[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < EW_THREADS / 32; i++) t += red[i];
+        s_mean = t / (double)n;
+    }
+    __syncthreads();
+    const double mean = s_mean;
+    double acc2 = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        double d = (double)xa[i] - mean;
+        acc2 += d * d;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < EW_THREADS / 32; i++) t += red[i];
+        stats[2 * b] = (float)mean;
+        stats[2 * b + 1] = (float)sqrt(t / (double)(n > 1 ? n - 1 : 1));
+    }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+affine_bcast_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ sub, int64_t sub_sb,
+                    int64_t sub_si, const float* __restrict__ mul, int64_t mul_sb, int64_t mul_si, int64_t n) {
+    const int b = blockIdx.y;
+    const float* xa = x + (size_t)b * n;
+    float* o = out + (size_t)b * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = xa[i];
+        if (sub) v -= sub[b * sub_sb + i * sub_si];
+        if (mul) v *= mul[b * mul_sb + i * mul_si];
+        o[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+label_mix_kernel(const float* __restrict__ y, const int64_t* __restrict__ perm, const float* __restrict__ coef,
+                 float* __restrict__ out, int64_t n, int hard) {
+    const int b = blockIdx.y;
+    const float* ya = y + (size_t)b * n;
+    const float* yb = y + (size_t)perm[b] * n;
+    const float c = coef ? coef[b] : 1.0f;
+    float* o = out + (size_t)b * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = hard ? ya[i] + yb[i] : c * ya[i] + (1.0f - c) * yb[i];
+        o[i] = fminf(fmaxf(v, 0.0f), 1.0f);
+    }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+roll_last_kernel(const float* __restrict__ x, float* __restrict__ out, const int32_t* __restrict__ shift, int rows,
+                 int cols) {
+    const int b = blockIdx.y;
+    int s = shift[b] % cols;
+    if (s < 0) s += cols;
+    const float* xa = x + (size_t)b * rows * cols;
+    float* o = out + (size_t)b * rows * cols;
+    const int64_t n = (int64_t)rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int r = (int)(i / cols), j = (int)(i - (int64_t)r * cols);
+        int src = j - s;
+        if (src < 0) src += cols;
+        o[i] = xa[(int64_t)r * cols + src];
+    }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+add_noise_kernel(const float* __restrict__ x, const float* __restrict__ noise, const float* __restrict__ snr_db,
+                 const float* __restrict__ stats, float* __restrict__ out, int64_t n) {
+    const int b = blockIdx.y;
+    const float sigma = stats[2 * b + 1] / powf(10.0f, snr_db[b] / 20.0f);
+    const float* xa = x + (size_t)b * n;
+    const float* na = noise + (size_t)b * n;
+    float* o = out + (size_t)b * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        o[i] = xa[i] + na[i] * sigma;
+}
+
+// fused EMA + Adam on flat buffers (12 B/param EMA traffic + 28 B/param Adam traffic in one pass)
+__global__ void __launch_bounds__(EW_THREADS)
+adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                float* __restrict__ ema, int64_t n, int do_adam, float step_size, float beta1, float beta2, float eps,
+                float inv_sqrt_bc2, float ema_alpha, float grad_scale) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float pi = p[i];
+        if (ema) ema[i] = ema[i] * ema_alpha + pi * (1.0f - ema_alpha);
+        if (do_adam) {
+            float gi = g[i] * grad_scale;
+            float mi = m[i] + (gi - m[i]) * (1.0f - beta1);        // torch: exp_avg.lerp_(grad, 1 - beta1)
+            float vi = v[i] * beta2 + (1.0f - beta2) * gi * gi;
+            m[i] = mi;
+            v[i] = vi;
+            float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+            p[i] = pi - step_size * (mi / denom);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) sumsq_kernel(const float* __restrict__ g, int64_t n, double* out) {
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = g[i];
+        acc += (double)v * (double)v;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+// median over a window of `k` frames (reflect boundary), one thread per output sample; k <= 31.
+// scipy.ndimage.median_filter semantics: window = [i - k/2, i + k - 1 - k/2], rank k/2.
+constexpr int MED_MAX = 31;
+__global__ void __launch_bounds__(EW_THREADS)
+median_kernel(const float* __restrict__ s, float* __restrict__ out, int C, int T, int64_t sb, int64_t sc, int64_t st,
+              int64_t ob, int64_t oc, int64_t ot, const int32_t* __restrict__ win, int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int t = (int)(i % T);
+        int64_t bc = i / T;
+        int c = (int)(bc % C);
+        int64_t b = bc / C;
+        const float* row = s + b * sb + c * sc;
+        int k = win[c];
+        k = k < 1 ? 1 : (k > MED_MAX ? MED_MAX : k);
+        float w[MED_MAX];
+        const int half = k / 2;
+        for (int j = 0; j < k; j++) {
+            int q = t - half + j;
+            // scipy 'reflect': (d c b a | a b c d | d c b a)
+            int period = 2 * T;
+            q %= period;
+            if (q < 0) q += period;
+            if (q >= T) q = period - 1 - q;
+            w[j] = row[(int64_t)q * st];
+        }
+        // partial selection sort up to rank `half`
+        for (int a = 0; a <= half; a++) {
+            int mi = a;
+            for (int j = a + 1; j < k; j++)
+                if (w[j] < w[mi]) mi = j;
+            float tmp = w[a];
+            w[a] = w[mi];
+            w[mi] = tmp;
+        }
+        out[b * ob + c * oc + (int64_t)t * ot] = w[half];
+    }
+}
+
+inline dim3 grid2(int64_t n, int B, int per_thread = 4) {
+    int64_t blocks = (n + (int64_t)EW_THREADS * per_thread - 1) / ((int64_t)EW_THREADS * per_thread);
+    int64_t cap = (int64_t)num_sms() * 8 / (B > 0 ? B : 1) + 1;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return dim3((unsigned)blocks, (unsigned)B);
+}
+inline int grid1(int64_t n, int per_thread = 4) {
+    int64_t blocks = (n + (int64_t)EW_THREADS * per_thread - 1) / ((int64_t)EW_THREADS * per_thread);
+    int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+}  // namespace sedk
+
+using namespace sedk;
+
+extern "C" int sedk_minmax_init(uint32_t* minmax, int B, void* stream) {
+    SEDK_REQUIRE(minmax && B > 0, "sedk_minmax_init: bad arguments");
+    minmax_init_kernel<<<cdiv(B, 128), 128, 0, (cudaStream_t)stream>>>(minmax, B);
+    SEDK_LAUNCH_CHECK("minmax_init_kernel");
+    return SEDK_OK;
+}
+
+extern "C" int sedk_minmax_decode(const uint32_t* minmax, float* out, int B, void* stream) {
+    SEDK_REQUIRE(minmax && out && B > 0, "sedk_minmax_decode: bad arguments");
+    minmax_decode_kernel<<<cdiv(2 * B, 128), 128, 0, (cudaStream_t)stream>>>(minmax, out, B);
+    SEDK_LAUNCH_CHECK("minmax_decode_kernel");
+    return SEDK_OK;
+}
+
+extern "C" int sedk_feat_mix_log(const float* x, const int64_t* perm, const float* coef, float* out, int B, int64_t n,
+                                 int log_mode, float amin, float db_lo, float db_hi, uint32_t* minmax, void* stream) {
+    SEDK_REQUIRE(x && out && B > 0 && n > 0, "sedk_feat_mix_log: bad arguments");
+    const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    dim3 grid = grid2(vec ? n / 4 : n, B, 2);
+    if (vec)
+        feat_mix_log_kernel<true><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, perm, coef, out, n, log_mode, amin,
+                                                                                 db_lo, db_hi, minmax);
+    else
+        feat_mix_log_kernel<false><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, perm, coef, out, n, log_mode, amin,
+                                                                                  db_lo, db_hi, minmax);
+    SEDK_LAUNCH_CHECK("feat_mix_log_kernel");
+    return SEDK_OK;
+}
+
+extern "C" int sedk_minmax_scale(const float* x, float* out, const uint32_t* minmax, int B, int64_t n, float eps,
+                                 void* stream) {
+    SEDK_REQUIRE(x && out && minmax && B > 0 && n > 0, "sedk_minmax_scale: bad arguments");
+    minmax_scale_kernel<<<grid2(n, B), EW_THREADS, 0, (cudaStream_t)stream>>>(x, out, minmax, n, eps);
+    SEDK_LAUNCH_CHECK("minmax_scale_kernel");
+    return SEDK_OK;
+}
+
+extern "C" int sedk_instance_stats(const float* x, float* stats, int B, int64_t n, void* stream) {
+    SEDK_REQUIRE(x && stats && B > 0 && n > 0, "sedk_instance_stats: bad arguments");
+    instance_stats_kernel<<<B, EW_THREADS, 0, (cudaStream_t)stream>>>(x, stats, n);
+    SEDK_LAUNCH_CHECK("instance_stats_kernel");
+    return SEDK_OK;
+}
+
+extern "C" int sedk_affine_bcast(const float* x, float* out, const float* sub, int64_t sub_sb, int64_t sub_si,
+                                 const float* mul, int64_t mul_sb, int64_t mul_si, int B, int64_t n, void* stream) {
+    SEDK_REQUIRE(x && out && B > 0 && n > 0, "sedk_affine_bcast: bad arguments");
+    affine_bcast_kernel<<<grid2(n, B), EW_THREADS, 0, (cudaStream_t)stream>>>(x, out, sub, sub_sb, sub_si, mul, mul_sb,
+                                                                              mul_si, n);
+    SEDK_LAUNCH_CHECK("affine_bcast_kernel");
+    return SEDK_OK;
+}
+
+extern "C" int sedk_label_mix(const float* y, const int64_t* perm, const float* coef, float* out, int B, int64_t n,
+                              int hard, void* stream) {
+    SEDK_REQUIRE(y && perm && out && B > 0 && n > 0, "sedk_label_mix: bad arguments");
+    label_mix_kernel<<<grid2(n, B), EW_THREADS, 0, (cudaStream_t)stream>>>(y, perm, coef, out, n, hard);
+    SEDK_LAUNCH_CHECK("label_mix_kernel");
+    return SEDK_OK;
+}
+
+extern "C" int sedk_roll_last(const float* x, float* out, const int32_t* shift, int B, int rows, int cols, void* stream) {
+    SEDK_REQUIRE(x && out && shift && B > 0 && rows > 0 && cols > 0, "sedk_roll_last: bad arguments");
+    SEDK_REQUIRE(x != out, "sedk_roll_last: in-place roll is not supported");
+    roll_last_kernel<<<grid2((int64_t)rows * cols, B), EW_THREADS, 0, (cudaStream_t)stream>>>(x, out, shift, rows, cols);
+    SEDK_LAUNCH_CHECK("roll_last_kernel");
+    return SEDK_OK;
+}
+
+extern "C" int sedk_add_noise(const float* x, const float* noise, const float* snr_db, const float* stats, float* out,
+                              int B, int64_t n, void* stream) {
+    SEDK_REQUIRE(x && noise && snr_db && stats && out && B > 0 && n > 0, "sedk_add_noise: bad arguments");
+    add_noise_kernel<<<grid2(n, B), EW_THREADS, 0, (cudaStream_t)stream>>>(x, noise, snr_db, stats, out, n);
+    SEDK_LAUNCH_CHECK("add_noise_kernel");
+    return SEDK_OK;
+}
+
+extern "C" int sedk_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n, int do_adam, float lr,
+                             float beta1, float beta2, float eps, int step, float ema_alpha, float grad_scale,
+                             void* stream) {
+    SEDK_REQUIRE(p && n > 0, "sedk_adam_ema: bad arguments");
+    SEDK_REQUIRE(!do_adam || (g && m && v && step >= 1), "sedk_adam_ema: Adam needs g, m, v and step >= 1");
+    float step_size = 0.f, inv_sqrt_bc2 = 1.f;
+    if (do_adam) {
+        double bc1 = 1.0 - pow((double)beta1, (double)step);
+        double bc2 = 1.0 - pow((double)beta2, (double)step);
+        step_size = (float)((double)lr / bc1);
+        inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    }
+    adam_ema_kernel<<<grid1(n, 1), EW_THREADS, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, n, do_adam, step_size, beta1,
+                                                                        beta2, eps, inv_sqrt_bc2, ema_alpha, grad_scale);
+    SEDK_LAUNCH_CHECK("adam_ema_kernel");
+    return SEDK_OK;
+}
+
+extern "C" int sedk_sumsq(const float* g, int64_t n, double* out, void* stream) {
+    SEDK_REQUIRE(g && out && n > 0, "sedk_sumsq: bad arguments");
+    SEDK_CUDA(cudaMemsetAsync(out, 0, sizeof(double), (cudaStream_t)stream));
+    sumsq_kernel<<<grid1(n), EW_THREADS, 0, (cudaStream_t)stream>>>(g, n, out);
+    SEDK_LAUNCH_CHECK("sumsq_kernel");
+    return SEDK_OK;
+}
+
+extern "C" int sedk_median_filter(const float* scores, float* out, int B, int C, int T, int64_t sb, int64_t sc,
+                                  int64_t st, int64_t ob, int64_t oc, int64_t ot, const int32_t* win, void* stream) {
+    SEDK_REQUIRE(scores && out && win && B > 0 && C > 0 && T > 0, "sedk_median_filter: bad arguments");
+    SEDK_REQUIRE(scores != out, "sedk_median_filter: in-place filtering is not supported");
+    int64_t total = (int64_t)B * C * T;
+    median_kernel<<<grid1(total, 1), EW_THREADS, 0, (cudaStream_t)stream>>>(scores, out, C, T, sb, sc, st, ob, oc, ot, win,
+                                                                           total);
+    SEDK_LAUNCH_CHECK("median_kernel");
+    return SEDK_OK;
+}

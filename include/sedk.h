@@ -1,0 +1,240 @@
+/* libsedk - C ABI of the B200-native sound-event-detection hot path (drop-in for DCASE-REPO/DESED_task).
+ *
+ * The reference has no FFI of its own (it is pure Python over PyTorch / torchaudio); these entry points are
+ * what a maintainer binds (ctypes stub in INTEGRATION.md) behind the reference's Python call sites.  Every
+ * function cites the reference interface it replaces (paths relative to the upstream repo).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 unless its name ends in _host or the comment says otherwise;
+ *   - caller owns all buffers; no hidden allocation, no hidden synchronisation; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*), so calls are CUDA-graph capturable;
+ *   - return value: SEDK_OK (0) or a negative error code; sedk_last_error() gives the message (thread-local);
+ *   - activations are channels-last: [B, T, F, C] ("T" = time frames = conv H, "F" = mel bins = conv W);
+ *   - sm_100a only.  There is no CPU fallback anywhere.
+ */
+#ifndef SEDK_H_
+#define SEDK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SEDK_API __attribute__((visibility("default")))
+#else
+#define SEDK_API
+#endif
+
+#define SEDK_OK 0
+#define SEDK_ERR_INVALID (-1)     /* bad argument (shape, alignment, null pointer)            */
+#define SEDK_ERR_CUDA (-2)        /* a CUDA runtime call / kernel launch failed               */
+#define SEDK_ERR_UNSUPPORTED (-3) /* configuration outside what the sm_100a kernels implement */
+
+#define SEDK_MAX_CONV 8
+#define SEDK_MAX_GRU_LAYERS 4
+
+SEDK_API const char* sedk_last_error(void);
+SEDK_API int sedk_version(void);
+/* compute capability of the current device as major*10+minor (100 on B200); <0 on error */
+SEDK_API int sedk_device_cc(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Front end: waveform -> (log-)mel.  Replaces torchaudio MelSpectrogram + AmplitudeToDB as built at
+ * recipes/dcase2023_task4_baseline/local/sed_trainer.py:79-91 and called at :282 / :253-264 (take_log).
+ * n_fft = win_length = 2048 (fixed by the kernel), center=True, reflect padding, onesided, power=1, HTK fb.
+ *
+ * Tables (device, built once by the host module):
+ *   window[2048]; tw2048[1024] float2 = exp(-2 pi i k/2048); tw32x32[32*32] float2 = exp(-2 pi i n2*k1/1024)
+ *   laid out [k1][n2]; sparse filterbank: fb_start[n_mels], fb_len[n_mels], fb_off[n_mels] (int32) and
+ *   fb_w[sum len] (the non-zero run of column m of torchaudio's fb[1025, n_mels]).
+ * wave  [B, L] contiguous.  out element (b, m, t) at out + b*out_sb + m*out_sm + t*out_st,
+ *   t in [0, 1 + L/hop).  log_mode 0: linear-amplitude mel;  1: 20*log10(max(x, amin)) clamped to [db_lo, db_hi].
+ * minmax: optional [B][2] uint32 (order-preserving encoding, see sedk_minmax_*): per-clip min / max of what was
+ *   written; must be initialised with sedk_minmax_init.  May be NULL.
+ */
+typedef struct {
+    const float* window;
+    const float* tw2048;  /* float2[1024] */
+    const float* tw32x32; /* float2[1024] */
+    const int32_t* fb_start;
+    const int32_t* fb_len;
+    const int32_t* fb_off;
+    const float* fb_w;
+    int32_t n_mels;
+    int32_t hop;
+} sedk_mel_tables;
+
+SEDK_API int sedk_logmel_fwd(const float* wave, int B, int L, const sedk_mel_tables* tab, float* out, int64_t out_sb,
+                    int64_t out_sm, int64_t out_st, int log_mode, float amin, float db_lo, float db_hi,
+                    uint32_t* minmax, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Elementwise feature ops.
+ */
+/* minmax[b] = {ord(+inf), ord(-inf)} */
+SEDK_API int sedk_minmax_init(uint32_t* minmax, int B, void* stream);
+/* decode to float pairs {min, max} */
+SEDK_API int sedk_minmax_decode(const uint32_t* minmax, float* out, int B, void* stream);
+
+/* take_log (sed_trainer.py:253-264) fused with mixup on linear mel (desed_task/data_augm.py:31-37, called at
+ * sed_trainer.py:296-301) and the per-clip min/max of TorchScaler (desed_task/utils/scaler.py:114-120):
+ *   v = perm ? c[b]*x[b] + (1-c[b])*x[perm[b]] : x[b];  out[b] = log_mode ? clamp(20*log10(max(v,amin))) : v
+ * x/out: [B, n] contiguous per clip.  perm: int64[B] device or NULL; coef: float[B] device or NULL (c=1).
+ * minmax: optional, as above.  */
+SEDK_API int sedk_feat_mix_log(const float* x, const int64_t* perm, const float* coef, float* out, int B, int64_t n,
+                      int log_mode, float amin, float db_lo, float db_hi, uint32_t* minmax, void* stream);
+
+/* TorchScaler instance/minmax apply (scaler.py:114-120): out = (x-min)/(max-min+eps)*2-1 */
+SEDK_API int sedk_minmax_scale(const float* x, float* out, const uint32_t* minmax, int B, int64_t n, float eps, void* stream);
+/* per-clip mean and (unbiased) std over n elements (scaler.py:107-112): stats[b] = {mean, std} */
+SEDK_API int sedk_instance_stats(const float* x, float* stats, int B, int64_t n, void* stream);
+/* out = (x - a[b or 0]) * s[b or 0] ... generic affine used by the mean/standard/dataset scaler modes:
+ * out[b,i] = (x[b,i] - sub[b*sub_sb + i*sub_si]) * mul[b*mul_sb + i*mul_si] */
+SEDK_API int sedk_affine_bcast(const float* x, float* out, const float* sub, int64_t sub_sb, int64_t sub_si, const float* mul,
+                      int64_t mul_sb, int64_t mul_si, int B, int64_t n, void* stream);
+
+/* label mixup (data_augm.py:38-44): soft: clamp(c*y + (1-c)*y[perm], 0, 1); hard: clamp(y + y[perm], 0, 1) */
+SEDK_API int sedk_label_mix(const float* y, const int64_t* perm, const float* coef, float* out, int B, int64_t n, int hard,
+                   void* stream);
+/* frame_shift (data_augm.py:7-16): out[b, r, (j + shift[b]) mod n_cols] = x[b, r, j];  shift int32[B] device */
+SEDK_API int sedk_roll_last(const float* x, float* out, const int32_t* shift, int B, int rows, int cols, void* stream);
+/* add_noise (data_augm.py:56-77): out = x + noise * std(x[b]) / 10^(snr_db[b]/20); stats from sedk_instance_stats */
+SEDK_API int sedk_add_noise(const float* x, const float* noise, const float* snr_db, const float* stats, float* out, int B,
+                   int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Optimiser / mean teacher: one flat multi-tensor kernel.
+ * update_ema (sed_trainer.py:187-199) + torch.optim.Adam (train_sed.py:199-201).  Order inside the kernel follows
+ * the reference step order under PL 1.9 (EMA of the *current* weights first, then the Adam update):
+ *   if (ema)  ema = ema_alpha*ema + (1-ema_alpha)*p
+ *   if (do_adam) { g *= grad_scale; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ *                  p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps) }         bc_i = 1 - b_i^step
+ */
+SEDK_API int sedk_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n, int do_adam, float lr,
+                  float beta1, float beta2, float eps, int step, float ema_alpha, float grad_scale, void* stream);
+/* sum of squares of g into out[0] (double), for gradient clipping (2024 recipe gradient_clip 5.0) */
+SEDK_API int sedk_sumsq(const float* g, int64_t n, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Median-filter post-processing: scipy.ndimage.median_filter(scores[T, C], (k, 1)), mode='reflect'
+ * (recipes/dcase2023_task4_baseline/local/utils.py:58; per class: desed_task/utils/postprocess.py:5-17).
+ * scores/out: element (b, c, t) at base + b*sb + c*sc + t*st.  win: int32[C] device window per class (1..31).
+ */
+SEDK_API int sedk_median_filter(const float* scores, float* out, int B, int C, int T, int64_t sb, int64_t sc, int64_t st,
+                       int64_t ob, int64_t oc, int64_t ot, const int32_t* win, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * CRNN (desed_task/nnet/CRNN.py, CNN.py, RNN.py) - whole-network forward / backward on a caller-provided plan.
+ */
+typedef struct {
+    /* geometry */
+    int32_t cin, cout;      /* channels                                                        */
+    int32_t T, F;           /* conv input = output spatial size (3x3, pad 1, stride 1)         */
+    int32_t pt, pf;         /* AvgPool2d kernel (= stride), CNN.py:96-98                       */
+    /* parameters (reference layouts, desed_task state_dict) */
+    const float* w;         /* conv weight [cout, cin, 3, 3]                                   */
+    const float* b;         /* conv bias [cout]                                                */
+    const float* gamma;     /* batchnorm weight [cout]                                         */
+    const float* beta;      /* batchnorm bias [cout]                                           */
+    float* running_mean;    /* [cout] (updated in training)                                    */
+    float* running_var;     /* [cout]                                                          */
+    int64_t* num_batches;   /* scalar int64, may be NULL                                       */
+    const float* glu_w;     /* GLU linear weight [cout, cout]                                  */
+    const float* glu_b;     /* [cout]                                                          */
+    /* gradients (same layouts), NULL when not training */
+    float *gw, *gb, *ggamma, *gbeta, *gglu_w, *gglu_b;
+    /* workspace */
+    float* wpack;           /* [2][9][cout][cin]: fwd pack [tap][co][ci] then dgrad pack [tap][ci][co]  */
+    float* gwpack;          /* [9][cout][cin] wgrad accumulator                                */
+    float* z;               /* conv output (pre-BN) [B,T,F,cout]                               */
+    float* gy;              /* grad wrt BN output / conv output (in place) [B,T,F,cout]        */
+    float* out;             /* pooled block output [B,T/pt,F/pf,cout]                          */
+    float* gout;            /* grad wrt out                                                    */
+    double* stats;          /* [4][cout]: sum z, sum z^2, sum gy, sum gy*zhat                   */
+    float* bn;              /* [4][cout]: scale, shift, mean, invstd (saved for backward)      */
+} sedk_conv_layer;
+
+typedef struct {
+    int32_t in_dim, hidden;
+    /* nn.GRU parameters, [dir] = forward, reverse (RNN.py:19-30) */
+    const float* w_ih[2];   /* [3H, in]  */
+    const float* w_hh[2];   /* [3H, H]   */
+    const float* b_ih[2];   /* [3H]      */
+    const float* b_hh[2];   /* [3H]      */
+    float *gw_ih[2], *gw_hh[2], *gb_ih[2], *gb_hh[2];
+    /* workspace, per direction */
+    float* gi[2];           /* [B,T,3H] input projections (fwd) / dgi (bwd, in place)          */
+    float* gates[2];        /* [B,T,4H]: r, z, n, hn_pre (saved for backward)                  */
+    float* hprev[2];        /* [B,T,H] h_{t-1} in processing order                             */
+    float* dghn[2];         /* [B,T,H]                                                          */
+    float* out;             /* [B,T,2H] layer output                                           */
+    float* gout;            /* [B,T,2H] grad wrt out                                           */
+} sedk_gru_layer;
+
+typedef struct {
+    int32_t B;
+    int32_t n_mels, n_frames;       /* model input [B, n_mels, n_frames]                       */
+    int32_t n_conv, n_gru;
+    int32_t nclass;
+    int32_t training;               /* 1: batch-stat BN + dropout + saves for backward         */
+    int32_t precision;              /* 0: TF32 tensor cores; 1: 3xTF32 (fp32-equivalent)       */
+    float dropout_p;                /* CNN.py:90-91, CRNN.py:103                               */
+    float bn_eps, bn_momentum;      /* CNN.py:76 (1e-3, 0.99)                                  */
+    uint64_t seed;                  /* dropout Philox seed for this forward                    */
+    /* input: log-mel (un-scaled) with strides; scaler + specaugment are fused into the first conv load */
+    const float* x;
+    int64_t x_sb, x_sm, x_st;
+    const uint32_t* minmax;         /* per-clip {min,max} (instance/minmax scaler); NULL: x is already scaled */
+    float scaler_eps;
+    const int32_t* specaug;         /* int32 [B][4] = f_start, f_end, t_start, t_end or NULL (CRNN.py:207-219) */
+    sedk_conv_layer conv[SEDK_MAX_CONV];
+    sedk_gru_layer gru[SEDK_MAX_GRU_LAYERS];
+    /* optional embedding fusion (aggregation_type="pool1d", CRNN.py:280-294) */
+    const float* emb;               /* [B, emb_dim, emb_T] or NULL                             */
+    int32_t emb_dim, emb_T;
+    const float* cat_w;             /* [nb, nb+emb_dim]                                        */
+    const float* cat_b;
+    float *gcat_w, *gcat_b;
+    float* cat_in;                  /* [B,T',nb+emb_dim] workspace (after dropout)             */
+    float* fused;                   /* [B,T',nb] workspace                                     */
+    float* gfused;
+    const int32_t* dropstep;        /* int32 [B][4] x_start,x_end,e_start,e_end or NULL        */
+    /* heads (CRNN.py:152-178) */
+    const float* dense_w;           /* [C, 2H] */
+    const float* dense_b;
+    const float* soft_w;            /* [C, 2H] */
+    const float* soft_b;
+    float *gdense_w, *gdense_b, *gsoft_w, *gsoft_b;
+    const uint8_t* classes_mask;    /* [B, C] (1 = valid class) or NULL                        */
+    float* rnn_drop;                /* [B,T',2H] workspace: post-RNN dropout output            */
+    float* grnn_drop;
+    float* strong;                  /* out: [B, C, T'] */
+    float* weak;                    /* out: [B, C]     */
+    float* sof;                     /* [B, T', C] workspace: clamped attention                 */
+    float* gstrong;                 /* in (backward): [B, C, T'] */
+    float* gweak;                   /* in (backward): [B, C]     */
+} sedk_crnn_plan;
+
+SEDK_API int sedk_crnn_forward(const sedk_crnn_plan* plan, void* stream);
+SEDK_API int sedk_crnn_backward(const sedk_crnn_plan* plan, void* stream);
+SEDK_API int sedk_sizeof_crnn_plan(void);
+
+/* Losses of SEDTask4.training_step (sed_trainer.py:309-342): BCE(strong rows [0,n_strong)) + BCE(weak rows
+ * [n_strong, n_strong+n_weak)) + weight * (MSE(strong, teacher) + MSE(weak, teacher)); teacher pointers may be NULL.
+ * labels [B,C,T'], labels_weak [n_weak, C].  Writes losses[8] = {total, bce_strong, bce_weak, mse_strong,
+ * mse_weak, bce_strong_teacher, bce_weak_teacher, 0} and the gradients wrt strong / weak (may be NULL). */
+SEDK_API int sedk_sed_loss(const float* strong, const float* weak, const float* t_strong, const float* t_weak,
+                  const float* labels, const float* labels_weak, int B, int C, int T, int n_strong, int n_weak,
+                  float cons_weight, float* losses, float* gstrong, float* gweak, void* stream);
+
+/* plain GEMM building block (TF32 / 3xTF32 mma): C[M,N] = alpha*op(A)op(B) + beta*C + bias[n]
+ * transA 0: A is [M,K] (lda), 1: A is [K,M];  transB 0: B is [K,N] (ldb), 1: B is [N,K]. */
+SEDK_API int sedk_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* Bm,
+              int ldb, float beta, float* C, int ldc, const float* bias, int precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEDK_H_ */

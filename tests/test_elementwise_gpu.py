@@ -1,0 +1,158 @@
+"""GPU parity: mixup / take_log / scaler / frame_shift / add_noise / Adam+EMA / median vs the oracle."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import frontend as ofe, postprocess as opost, trainer as otr
+from tests.util import golden, maxdiff
+
+pytestmark = pytest.mark.gpu
+
+
+def test_mixup_soft_hard_and_rng_order(dev):
+    from desed_task_b200.data_augm import mixup
+    torch.manual_seed(5)
+    data = torch.rand(12, 128, 626)
+    tgt = (torch.rand(12, 10, 156) < 0.1).float()
+    for kind in ("soft", "hard"):
+        np.random.seed(5)
+        torch.manual_seed(7)
+        c, perm = otr.draw_mixup(12)
+        rd, rt = otr.mixup(data, tgt, c, perm, kind)
+        np.random.seed(5)
+        torch.manual_seed(7)
+        md, mt = mixup(data.to(dev), tgt.to(dev), mixup_label_type=kind)
+        assert maxdiff(md, rd) < 1e-6 and maxdiff(mt, rt) < 1e-6
+    g = golden("augm")
+    np.random.seed(5)
+    torch.manual_seed(5)
+    data = torch.rand(12, 128, 626)
+    tgt = (torch.rand(12, 10, 156) < 0.1).float()
+    md, mt = mixup(data.to(dev), tgt.to(dev))
+    assert np.abs(md[:, :4, :8].cpu().numpy() - g["mixed_head"]).max() < 1e-6
+    assert mixup(data.to(dev)).shape == data.shape
+    with pytest.raises(NotImplementedError):
+        mixup(data.to(dev), tgt.to(dev), mixup_label_type="bogus")
+
+
+def test_mixup_fused_with_log_and_minmax(dev):
+    from desed_task_b200.frontend import take_log, new_minmax, decode_minmax
+    torch.manual_seed(0)
+    mel = torch.rand(6, 128, 626) * 10
+    perm = torch.tensor([3, 0, 5, 1, 2, 4])
+    coef = torch.tensor([0.3, 0.3, 0.3, 1.0, 1.0, 1.0])
+    ref = mel.clone()
+    ref[:3] = 0.3 * mel[:3] + 0.7 * mel[perm[:3]]
+    ref = ofe.take_log(ref)
+    perm_full = torch.tensor([3, 0, 5, 3, 4, 5])
+    mm = new_minmax(6, dev)
+    out = take_log(mel.to(dev), perm=perm_full.to(dev), coef=coef.to(dev), minmax=mm)
+    assert maxdiff(out, ref) < 1e-4
+    mmf = decode_minmax(mm).cpu()
+    assert torch.equal(mmf[:, 0], out.amin((1, 2)).cpu()) and torch.equal(mmf[:, 1], out.amax((1, 2)).cpu())
+
+
+@pytest.mark.parametrize("stat,norm", [("instance", "minmax"), ("instance", "standard"), ("instance", "mean"),
+                                       ("dataset", "standard"), ("dataset", "mean"), (None, None)])
+def test_scaler_modes(dev, stat, norm):
+    from desed_task_b200.utils.scaler import TorchScaler
+    torch.manual_seed(1)
+    x = torch.randn(4, 128, 626) * 12 + 3
+    sc = TorchScaler(stat, norm, (1, 2)) if stat else TorchScaler(None, None)
+    kw = {}
+    if stat == "dataset":
+        loader = [(x[:2],), (x[2:],)]
+        sc.fit(loader)
+        kw = dict(mean=sc.mean, mean_squared=sc.mean_squared)
+    out = sc(x.to(dev))
+    ref = ofe.scaler(x, stat, norm, (1, 2), **kw)
+    assert maxdiff(out, ref) < 2e-5
+    assert sc.state_dict().keys() == ({"mean", "mean_squared"} if stat == "dataset" else set())
+
+
+def test_scaler_errors():
+    from desed_task_b200.utils.scaler import TorchScaler
+    with pytest.raises(NotImplementedError):
+        TorchScaler("dataset", "minmax")
+    with pytest.raises(AssertionError):
+        TorchScaler("bogus", "minmax")
+
+
+def test_frame_shift(dev):
+    from desed_task_b200.data_augm import frame_shift
+    torch.manual_seed(2)
+    mels = torch.rand(12, 128, 626)
+    labels = (torch.rand(12, 10, 156) < 0.2).float()
+    random.seed(9)
+    shifts = otr.draw_frame_shift(12)
+    rm, rl = otr.frame_shift(mels, labels, shifts)
+    random.seed(9)
+    om, ol = frame_shift(mels.to(dev), labels.to(dev))
+    assert torch.equal(om.cpu(), rm) and torch.equal(ol.cpu(), rl)
+    assert np.array_equal(np.array(shifts), golden("augm")["shifts"])
+
+
+def test_add_noise(dev):
+    from desed_task_b200.data_augm import add_noise
+    torch.manual_seed(3)
+    mels = torch.rand(5, 128, 626, device=dev)
+    torch.manual_seed(11)
+    out = add_noise(mels)
+    torch.manual_seed(11)
+    snr = (6 - 30) * torch.rand((5,), device=dev) + 30
+    noise = torch.randn(mels.shape, device=dev)
+    ref = otr.add_noise(mels.cpu(), snr.cpu(), noise.cpu())
+    assert maxdiff(out, ref) < 1e-5
+
+
+def test_adam_ema_matches_oracle(dev):
+    from desed_task_b200._lib import check, lib, ptr, stream_ptr
+    g = torch.Generator().manual_seed(0)
+    n = 1112420
+    p0 = torch.randn(n, generator=g) * 0.1
+    P = {"p": p0.clone()}
+    T = {"p": p0.clone()}
+    state = {}
+    p = p0.clone().to(dev)
+    ema = p0.clone().to(dev)
+    m = torch.zeros(n, device=dev)
+    v = torch.zeros(n, device=dev)
+    for step in range(1, 6):
+        gr = torch.randn(n, generator=g) * 0.01
+        alpha = otr.update_ema(0.999, step, P, T, ["p"])
+        otr.adam_step(P, {"p": gr}, state, ["p"], 1e-3)
+        check(lib().sedk_adam_ema(ptr(p), ptr(gr.to(dev)), ptr(m), ptr(v), ptr(ema), n, 1, 1e-3, 0.9, 0.999, 1e-8,
+                                  step, alpha, 1.0, stream_ptr()))
+    assert maxdiff(p, P["p"]) < 1e-6 and maxdiff(ema, T["p"]) < 1e-6
+    # EMA only
+    before = p.clone()
+    check(lib().sedk_adam_ema(ptr(p), None, None, None, ptr(ema), n, 0, 0, 0, 0, 0, 0, 0.5, 1.0, stream_ptr()))
+    assert torch.equal(p, before)
+
+
+def test_sumsq(dev):
+    from desed_task_b200._lib import check, lib, ptr, stream_ptr
+    x = torch.randn(100003, device=dev)
+    out = torch.zeros(1, dtype=torch.float64, device=dev)
+    check(lib().sedk_sumsq(ptr(x), x.numel(), ptr(out), stream_ptr()))
+    assert abs(out.item() - (x.double() ** 2).sum().item()) < 1e-6 * out.item()
+
+
+def test_median_filter(dev):
+    from desed_task_b200.utils.postprocess import ClassWiseMedianFilter, median_filter
+    g = golden("median")
+    sc = torch.from_numpy(g["scores"])                       # [156, 10]
+    out = median_filter(sc.t()[None].contiguous().to(dev), 7)        # [1, C, T]
+    assert np.array_equal(out[0].t().cpu().numpy(), g["med7"])
+    assert np.array_equal(ClassWiseMedianFilter(g["lens"])(g["scores"]), g["med_cw"])
+    rng = np.random.RandomState(1)
+    big = rng.rand(64, 156, 27).astype(np.float32)
+    lens = [int(k) for k in rng.randint(1, 18, 27)]
+    got = median_filter(torch.from_numpy(big).to(dev), lens, class_dim=2).cpu().numpy()
+    for b in (0, 17, 63):
+        assert np.array_equal(got[b], opost.classwise_median_filter(big[b], lens))
+    for k in (1, 2, 4, 8, 31):                               # even windows and the maximum size
+        got = median_filter(torch.from_numpy(big[:2]).to(dev), k, class_dim=2).cpu().numpy()
+        assert np.array_equal(got[1], opost.median_filter_time(big[1], k))

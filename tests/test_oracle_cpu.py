@@ -1,0 +1,76 @@
+"""CPU: the oracle reproduces the golden fixtures minted from the live reference (oracle/make_golden.py)."""
+import numpy as np
+import torch
+
+from oracle import crnn as ocrnn, frontend as ofe, postprocess as opost, trainer as otr
+from tests.util import gen_wave, golden
+
+
+def test_frontend_tables_fingerprint():
+    g = golden("frontend")
+    fb = ofe.melscale_fbanks()
+    win = ofe.hamming_window()
+    assert fb.shape == (1025, 128) and int((fb != 0).sum()) == int(g["fb_nnz"]) == 2024
+    assert abs(fb.sum().item() - float(g["fb_sum"])) < 1e-3
+    assert abs(win.sum().item() - float(g["win_sum"])) < 1e-3
+    assert abs(win[0].item() - 0.08) < 1e-6
+
+
+def test_frontend_short_matches_golden():
+    g = golden("frontend")
+    wave = torch.from_numpy(g["wave_short"])
+    mel = ofe.mel_spectrogram(wave)
+    assert np.abs(mel.numpy() - g["mel_short"]).max() < 1e-4
+    lm = ofe.take_log(mel)
+    assert np.abs(lm.numpy() - g["logmel_short"]).max() < 1e-4
+    assert np.abs(ofe.scaler(lm).numpy() - g["scaled_short"]).max() < 1e-5
+
+
+def test_wave_generator_is_stable():
+    g = golden("frontend")
+    assert np.array_equal(gen_wave(0, 2)[:, :8].numpy(), g["wave_head"])
+
+
+def test_crnn_eval_matches_golden():
+    g = golden("crnn")
+    feats = ofe.features(gen_wave(0, 2))
+    for key, cfg in (("2023_tl1", ocrnn.CFG_2023),):
+        P = ocrnn.init_params(cfg, seed=42, trained_like=True)
+        assert abs(sum(v.double().sum().item() for v in P.values()) - float(g["param_checksum_" + key])) < 1e-6
+        with torch.no_grad():
+            s, w = ocrnn.crnn_forward(P, feats, cfg, False, gru_impl="aten")
+        assert np.abs(s.numpy() - g["strong_eval_" + key]).max() < 1e-5
+        assert np.abs(w.numpy() - g["weak_eval_" + key]).max() < 1e-5
+
+
+def test_gru_loop_equals_aten():
+    cfg = ocrnn.CFG_2023
+    P = ocrnn.init_params(cfg, seed=1)
+    x = torch.randn(2, 20, 128)
+    a = ocrnn.gru_loop(x, P, "rnn.rnn.", 128, 2)
+    b = ocrnn.gru_aten(x, P, "rnn.rnn.", 128, 2)
+    assert (a - b).abs().max().item() < 1e-5
+
+
+def test_median_matches_golden():
+    g = golden("median")
+    assert np.array_equal(opost.median_filter_time(g["scores"], 7), g["med7"])
+    assert np.array_equal(opost.classwise_median_filter(g["scores"], g["lens"]), g["med_cw"])
+    small = np.array([0, 1, 4, 2, 2, 4, 1, 0, 1, 4], np.float32)[:, None]
+    assert opost.median_filter_time(small, 7)[:, 0].tolist() == [1, 1, 2, 2, 2, 2, 2, 2, 1, 1]
+
+
+def test_mixup_matches_golden():
+    g = golden("augm")
+    torch.manual_seed(5)
+    data = torch.rand(12, 128, 626)
+    tgt = (torch.rand(12, 10, 156) < 0.1).float()
+    md, mt = otr.mixup(data, tgt, float(g["mix_c"]), torch.from_numpy(g["mix_perm"]), "soft")
+    assert np.abs(md[:, :4, :8].numpy() - g["mixed_head"]).max() < 1e-7
+    assert abs(mt.double().sum().item() - float(g["mixed_target_sum"])) < 1e-6
+
+
+def test_warmup_scale():
+    assert abs(otr.warmup_scale(1000, 1000) - 1.0) < 1e-12
+    assert abs(otr.warmup_scale(0, 1000) - np.exp(-5.0)) < 1e-12
+    assert otr.warmup_scale(5, 0) == 1.0
