@@ -48,9 +48,9 @@ class GruLayer(C.Structure):
 class CrnnPlan(C.Structure):
     _fields_ = [("B", C.c_int32), ("n_mels", C.c_int32), ("n_frames", C.c_int32), ("n_conv", C.c_int32),
                 ("n_gru", C.c_int32), ("nclass", C.c_int32), ("training", C.c_int32), ("precision", C.c_int32),
-                ("dropout_p", f32), ("bn_eps", f32), ("bn_momentum", f32), ("seed", u64),
+                ("dropout_p", f32), ("bn_eps", f32), ("bn_momentum", f32), ("seed", u64), ("seed_dev", vp),
                 ("x", vp), ("x_sb", i64), ("x_sm", i64), ("x_st", i64), ("minmax", vp), ("scaler_eps", f32),
-                ("specaug", vp),
+                ("specaug", vp), ("x0", vp),
                 ("conv", ConvLayer * SEDK_MAX_CONV), ("gru", GruLayer * SEDK_MAX_GRU_LAYERS),
                 ("emb", vp), ("emb_dim", C.c_int32), ("emb_T", C.c_int32), ("cat_w", vp), ("cat_b", vp),
                 ("gcat_w", vp), ("gcat_b", vp), ("cat_in", vp), ("fused", vp), ("gfused", vp), ("dropstep", vp),
@@ -75,6 +75,8 @@ _SIGS = {
     "sedk_roll_last": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "sedk_add_noise": (i32, [vp, vp, vp, vp, vp, i32, i64, vp]),
     "sedk_adam_ema": (i32, [vp, vp, vp, vp, vp, i64, i32, f32, f32, f32, f32, i32, f32, f32, vp]),
+    "sedk_adam_ema_dev": (i32, [vp, vp, vp, vp, vp, i64, i32, f32, f32, f32, vp, vp]),
+    "sedk_bump_counter": (i32, [vp, u64, vp]),
     "sedk_sumsq": (i32, [vp, i64, vp, vp]),
     "sedk_median_filter": (i32, [vp, vp, i32, i32, i32, i64, i64, i64, i64, i64, i64, vp, vp]),
     "sedk_crnn_forward": (i32, [C.POINTER(CrnnPlan), vp]),

@@ -1,13 +1,242 @@
-// placeholder entry points - replaced as the CRNN kernels land
-#include "common.cuh"
-using namespace sedk;
-extern "C" int sedk_crnn_forward(const sedk_crnn_plan*, void*) { SEDK_UNSUPPORTED("sedk_crnn_forward: not built yet"); }
-extern "C" int sedk_crnn_backward(const sedk_crnn_plan*, void*) { SEDK_UNSUPPORTED("sedk_crnn_backward: not built yet"); }
-extern "C" int sedk_sed_loss(const float*, const float*, const float*, const float*, const float*, const float*, int, int,
-                             int, int, int, float, float*, float*, float*, void*) {
-    SEDK_UNSUPPORTED("sedk_sed_loss: not built yet");
+// Whole-network forward / backward of desed_task.nnet.CRNN (CRNN.py:221-306) as a stream-ordered kernel sequence over a
+// caller-provided plan (include/sedk.h: sedk_crnn_plan).  No allocation, no host synchronisation: capturable in a CUDA graph.
+//
+//   forward : [scaler + specaug + conv0] -> per layer {conv3x3 (+BN stats) -> bn_finalize -> BN+GLU+dropout+pool}
+//             -> [embedding fusion] -> per GRU layer {2 input GEMMs -> persistent bidirectional recurrence}
+//             -> dropout -> heads (sigmoid / class-softmax attention pooling)
+//   backward: heads -> dropout -> GRU BPTT (+ weight/input GEMMs) -> [fusion] -> per layer {BN+GLU+pool bwd -> BN bwd
+//             apply -> conv wgrad -> conv dgrad}
+// Dropout stream ids: conv layer i -> i, embedding concat -> 100, post-RNN -> 200 (masks are regenerated, never stored).
+#include "kernels.h"
+
+namespace sedk {
+namespace {
+
+constexpr uint64_t STREAM_EMB = 100, STREAM_RNN = 200;
+
+int validate(const sedk_crnn_plan* p, bool backward) {
+    SEDK_REQUIRE(p != nullptr, "crnn: null plan");
+    SEDK_REQUIRE(p->B > 0 && p->n_conv >= 1 && p->n_conv <= SEDK_MAX_CONV, "crnn: bad B / n_conv");
+    SEDK_REQUIRE(p->n_gru >= 1 && p->n_gru <= SEDK_MAX_GRU_LAYERS, "crnn: bad n_gru");
+    SEDK_REQUIRE(p->x && p->strong && p->weak && p->sof, "crnn: missing input / output buffers");
+    SEDK_REQUIRE(p->conv[0].cin == 1, "crnn: the first conv layer must have one input channel (n_in_channel=1)");
+    SEDK_REQUIRE(p->conv[0].T == p->n_frames && p->conv[0].F == p->n_mels, "crnn: layer-0 geometry mismatch");
+    for (int i = 0; i < p->n_conv; i++) {
+        const sedk_conv_layer& L = p->conv[i];
+        SEDK_REQUIRE(L.w && L.b && L.gamma && L.beta && L.running_mean && L.running_var && L.glu_w && L.glu_b,
+                     "crnn: conv layer %d has null parameters", i);
+        SEDK_REQUIRE(L.z && L.out && L.stats && L.bn, "crnn: conv layer %d has null workspace", i);
+        if (i > 0) {
+            SEDK_REQUIRE(L.wpack, "crnn: conv layer %d needs wpack", i);
+            SEDK_REQUIRE(L.cin == p->conv[i - 1].cout && L.T == p->conv[i - 1].T / p->conv[i - 1].pt &&
+                             L.F == p->conv[i - 1].F / p->conv[i - 1].pf,
+                         "crnn: conv layer %d geometry does not chain", i);
+        }
+        if (backward) {
+            SEDK_REQUIRE(L.gw && L.gb && L.ggamma && L.gbeta && L.gglu_w && L.gglu_b && L.gy && L.gout,
+                         "crnn: conv layer %d has null gradient buffers", i);
+            SEDK_REQUIRE(i == 0 || L.gwpack, "crnn: conv layer %d needs gwpack", i);
+        }
+    }
+    const sedk_conv_layer& last = p->conv[p->n_conv - 1];
+    SEDK_REQUIRE(last.F / last.pf == 1, "crnn: the CNN must pool the mel axis down to 1 (got %d)", last.F / last.pf);
+    if (backward) {
+        SEDK_REQUIRE(p->training, "crnn backward: the forward pass must have run with training=1");
+        SEDK_REQUIRE(p->x0, "crnn backward: x0 workspace missing");
+        SEDK_REQUIRE(p->gdense_w && p->gdense_b && p->gsoft_w && p->gsoft_b && p->grnn_drop,
+                     "crnn backward: head gradient buffers missing");
+    }
+    return SEDK_OK;
 }
-extern "C" int sedk_gemm(int, int, int, int, int, float, const float*, int, const float*, int, float, float*, int,
-                         const float*, int, void*) {
-    SEDK_UNSUPPORTED("sedk_gemm: not built yet");
+
+}  // namespace
+}  // namespace sedk
+
+using namespace sedk;
+
+extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
+    int rc = validate(p, false);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = p->B;
+    const float pdrop = p->training ? p->dropout_p : 0.f;
+    // ---------------- CNN
+    for (int i = 0; i < p->n_conv; i++) {
+        const sedk_conv_layer& L = p->conv[i];
+        const int C = L.cout;
+        if (p->training) SEDK_CUDA(cudaMemsetAsync(L.stats, 0, 4 * C * sizeof(double), s));
+        double* st = p->training ? L.stats : nullptr;
+        if (i == 0) {
+            rc = launch_conv0_fwd(p->x, p->x_sb, p->x_sm, p->x_st, p->minmax, p->scaler_eps,
+                                  p->training ? p->specaug : nullptr, L.w, L.b, p->training ? p->x0 : nullptr, L.z, st, B,
+                                  L.T, L.F, C, s);
+        } else {
+            rc = launch_pack_weights(L.w, L.wpack, L.cin, C, s);
+            if (rc) return rc;
+            rc = launch_conv3x3(p->conv[i - 1].out, L.wpack, L.b, L.z, st, B, L.T, L.F, L.cin, C, p->precision, s);
+        }
+        if (rc) return rc;
+        rc = launch_bn_finalize(L.stats, L.gamma, L.beta, L.running_mean, L.running_var, L.num_batches, L.bn,
+                                (double)B * L.T * L.F, p->bn_eps, p->bn_momentum, p->training, C, s);
+        if (rc) return rc;
+        rc = launch_bnglu_pool_fwd(L.z, L.bn, L.glu_w, L.glu_b, L.out, B, L.T, L.F, C, L.pt, L.pf, pdrop, p->seed,
+                                   p->seed_dev, (uint64_t)i, p->precision, s);
+        if (rc) return rc;
+    }
+    const sedk_conv_layer& last = p->conv[p->n_conv - 1];
+    const int Tp = last.T / last.pt;
+    const int nb = last.cout;
+    const float* xr = last.out;      // [B, T', nb]
+    int in_dim = nb;
+    // ---------------- embedding fusion
+    if (p->emb != nullptr) {
+        SEDK_REQUIRE(p->cat_w && p->cat_b && p->cat_in && p->fused, "crnn: embedding fusion buffers missing");
+        rc = launch_emb_concat(xr, p->emb, p->training ? p->dropstep : nullptr, p->cat_in, B, Tp, nb, p->emb_dim,
+                               p->emb_T, pdrop, p->seed, p->seed_dev, STREAM_EMB, s);
+        if (rc) return rc;
+        const int W = nb + p->emb_dim;
+        rc = launch_gemm(0, 1, B * Tp, nb, W, 1.f, p->cat_in, W, p->cat_w, W, 0.f, p->fused, nb, p->cat_b, p->precision, s);
+        if (rc) return rc;
+        xr = p->fused;
+    }
+    // ---------------- BiGRU
+    for (int l = 0; l < p->n_gru; l++) {
+        const sedk_gru_layer& G = p->gru[l];
+        SEDK_REQUIRE(G.in_dim == in_dim, "crnn: GRU layer %d expects %d inputs, gets %d", l, G.in_dim, in_dim);
+        const int H = G.hidden;
+        for (int d = 0; d < 2; d++) {
+            SEDK_REQUIRE(G.w_ih[d] && G.w_hh[d] && G.b_ih[d] && G.b_hh[d] && G.gi[d], "crnn: GRU layer %d null", l);
+            rc = launch_gemm(0, 1, B * Tp, 3 * H, in_dim, 1.f, xr, in_dim, G.w_ih[d], in_dim, 0.f, G.gi[d], 3 * H,
+                             G.b_ih[d], p->precision, s);
+            if (rc) return rc;
+        }
+        SEDK_REQUIRE(G.out && (!p->training || (G.gates[0] && G.gates[1] && G.hprev[0] && G.hprev[1])),
+                     "crnn: GRU layer %d workspace missing", l);
+        rc = launch_gru_seq_fwd(G.gi, G.w_hh, G.b_hh, G.out, G.gates, G.hprev, B, Tp, H, p->training, s);
+        if (rc) return rc;
+        xr = G.out;
+        in_dim = 2 * H;
+    }
+    // ---------------- dropout + heads
+    const float* hx = xr;
+    if (pdrop > 0.f) {
+        SEDK_REQUIRE(p->rnn_drop, "crnn: rnn_drop workspace missing");
+        rc = launch_dropout(xr, p->rnn_drop, (int64_t)B * Tp * in_dim, pdrop, p->seed, p->seed_dev, STREAM_RNN, s);
+        if (rc) return rc;
+        hx = p->rnn_drop;
+    }
+    return launch_heads_fwd(hx, p->dense_w, p->dense_b, p->soft_w, p->soft_b, p->classes_mask, p->strong, p->weak,
+                            p->sof, B, Tp, in_dim, p->nclass, s);
+}
+
+extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
+    int rc = validate(p, true);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = p->B;
+    const float pdrop = p->dropout_p;
+    const sedk_conv_layer& last = p->conv[p->n_conv - 1];
+    const int Tp = last.T / last.pt;
+    const int nb = last.cout;
+    const int BT = B * Tp;
+    const int Hl = p->gru[p->n_gru - 1].hidden;
+    const int D = 2 * Hl, C = p->nclass;
+    // ---------------- heads
+    SEDK_CUDA(cudaMemsetAsync(p->gdense_w, 0, (size_t)C * D * sizeof(float), s));
+    SEDK_CUDA(cudaMemsetAsync(p->gsoft_w, 0, (size_t)C * D * sizeof(float), s));
+    SEDK_CUDA(cudaMemsetAsync(p->gdense_b, 0, (size_t)C * sizeof(float), s));
+    SEDK_CUDA(cudaMemsetAsync(p->gsoft_b, 0, (size_t)C * sizeof(float), s));
+    const float* hx = pdrop > 0.f ? p->rnn_drop : p->gru[p->n_gru - 1].out;
+    float* ghx = pdrop > 0.f ? p->grnn_drop : p->gru[p->n_gru - 1].gout;
+    rc = launch_heads_bwd(hx, p->dense_w, p->soft_w, p->classes_mask, p->strong, p->weak, p->sof, p->gstrong, p->gweak,
+                          ghx, p->gdense_w, p->gdense_b, p->gsoft_w, p->gsoft_b, B, Tp, D, C, s);
+    if (rc) return rc;
+    if (pdrop > 0.f) {
+        rc = launch_dropout(p->grnn_drop, p->gru[p->n_gru - 1].gout, (int64_t)BT * D, pdrop, p->seed, p->seed_dev, STREAM_RNN, s);
+        if (rc) return rc;
+    }
+    // ---------------- BiGRU
+    for (int l = p->n_gru - 1; l >= 0; l--) {
+        const sedk_gru_layer& G = p->gru[l];
+        const int H = G.hidden, in_dim = G.in_dim;
+        SEDK_REQUIRE(G.gout && G.dghn[0] && G.dghn[1], "crnn backward: GRU layer %d gradient workspace missing", l);
+        rc = launch_gru_seq_bwd(G.gout, G.w_hh, G.gates, G.hprev, G.gi, G.dghn, B, Tp, H, s);
+        if (rc) return rc;
+        const float* xin = l > 0 ? p->gru[l - 1].out : (p->emb ? p->fused : last.out);
+        float* gin = l > 0 ? p->gru[l - 1].gout : (p->emb ? p->gfused : last.gout);
+        SEDK_REQUIRE(gin, "crnn backward: input-gradient buffer of GRU layer %d missing", l);
+        for (int d = 0; d < 2; d++) {
+            SEDK_REQUIRE(G.gw_ih[d] && G.gw_hh[d] && G.gb_ih[d] && G.gb_hh[d], "crnn backward: GRU grads null");
+            SEDK_CUDA(cudaMemsetAsync(G.gw_ih[d], 0, (size_t)3 * H * in_dim * sizeof(float), s));
+            SEDK_CUDA(cudaMemsetAsync(G.gw_hh[d], 0, (size_t)3 * H * H * sizeof(float), s));
+            // dW_ih = dgi^T x
+            rc = launch_gemm(1, 0, 3 * H, in_dim, BT, 1.f, G.gi[d], 3 * H, xin, in_dim, 1.f, G.gw_ih[d], in_dim, nullptr,
+                             p->precision, s);
+            if (rc) return rc;
+            // dW_hh rows [0,2H) from (dr, dz), rows [2H,3H) from d(hn)
+            rc = launch_gemm(1, 0, 2 * H, H, BT, 1.f, G.gi[d], 3 * H, G.hprev[d], H, 1.f, G.gw_hh[d], H, nullptr,
+                             p->precision, s);
+            if (rc) return rc;
+            rc = launch_gemm(1, 0, H, H, BT, 1.f, G.dghn[d], H, G.hprev[d], H, 1.f, G.gw_hh[d] + (size_t)2 * H * H, H,
+                             nullptr, p->precision, s);
+            if (rc) return rc;
+            rc = launch_colsum(G.gi[d], BT, 3 * H, 3 * H, G.gb_ih[d], 0, s);
+            if (rc) return rc;
+            rc = launch_colsum(G.gi[d], BT, 2 * H, 3 * H, G.gb_hh[d], 0, s);
+            if (rc) return rc;
+            rc = launch_colsum(G.dghn[d], BT, H, H, G.gb_hh[d] + 2 * H, 0, s);
+            if (rc) return rc;
+            // dx (+)= dgi W_ih
+            rc = launch_gemm(0, 0, BT, in_dim, 3 * H, 1.f, G.gi[d], 3 * H, G.w_ih[d], in_dim, d == 0 ? 0.f : 1.f, gin,
+                             in_dim, nullptr, p->precision, s);
+            if (rc) return rc;
+        }
+    }
+    // ---------------- embedding fusion
+    if (p->emb != nullptr) {
+        SEDK_REQUIRE(p->gcat_w && p->gcat_b && p->gfused && last.gout, "crnn backward: fusion gradient buffers missing");
+        const int W = nb + p->emb_dim;
+        SEDK_CUDA(cudaMemsetAsync(p->gcat_w, 0, (size_t)nb * W * sizeof(float), s));
+        rc = launch_gemm(1, 0, nb, W, BT, 1.f, p->gfused, nb, p->cat_in, W, 1.f, p->gcat_w, W, nullptr, p->precision, s);
+        if (rc) return rc;
+        rc = launch_colsum(p->gfused, BT, nb, nb, p->gcat_b, 0, s);
+        if (rc) return rc;
+        // gcat = gfused cat_w, written over cat_in (no longer needed)
+        rc = launch_gemm(0, 0, BT, W, nb, 1.f, p->gfused, nb, p->cat_w, W, 0.f, p->cat_in, W, nullptr, p->precision, s);
+        if (rc) return rc;
+        rc = launch_emb_concat_bwd(p->cat_in, p->dropstep, last.gout, B, Tp, nb, p->emb_dim, pdrop, p->seed, p->seed_dev, STREAM_EMB,
+                                   s);
+        if (rc) return rc;
+    }
+    // ---------------- CNN
+    for (int i = p->n_conv - 1; i >= 0; i--) {
+        const sedk_conv_layer& L = p->conv[i];
+        const int Cc = L.cout;
+        const int64_t npix = (int64_t)B * L.T * L.F;
+        SEDK_CUDA(cudaMemsetAsync(L.stats + 2 * Cc, 0, 2 * Cc * sizeof(double), s));
+        SEDK_CUDA(cudaMemsetAsync(L.gglu_w, 0, (size_t)Cc * Cc * sizeof(float), s));
+        SEDK_CUDA(cudaMemsetAsync(L.gglu_b, 0, (size_t)Cc * sizeof(float), s));
+        rc = launch_bnglu_pool_bwd(L.z, L.bn, L.glu_w, L.glu_b, L.gout, L.gy, L.gglu_w, L.gglu_b, L.stats, B, L.T, L.F, Cc,
+                                   L.pt, L.pf, pdrop, p->seed, p->seed_dev, (uint64_t)i, p->precision, s);
+        if (rc) return rc;
+        rc = launch_bn_bwd_apply(L.gy, L.z, L.bn, L.stats, L.ggamma, L.gbeta, L.gb, (double)npix, npix, Cc, s);
+        if (rc) return rc;
+        if (i > 0) {
+            const sedk_conv_layer& P = p->conv[i - 1];
+            SEDK_REQUIRE(P.gout, "crnn backward: gout of conv layer %d missing", i - 1);
+            SEDK_CUDA(cudaMemsetAsync(L.gwpack, 0, (size_t)9 * Cc * L.cin * sizeof(float), s));
+            rc = launch_conv_wgrad(P.out, L.gy, L.gwpack, B, L.T, L.F, L.cin, Cc, p->precision, s);
+            if (rc) return rc;
+            rc = launch_unpack_wgrad(L.gwpack, L.gw, L.cin, Cc, s);
+            if (rc) return rc;
+            rc = launch_conv3x3(L.gy, L.wpack + (size_t)9 * Cc * L.cin, nullptr, P.gout, nullptr, B, L.T, L.F, Cc, L.cin,
+                                p->precision, s);
+            if (rc) return rc;
+        } else {
+            SEDK_CUDA(cudaMemsetAsync(L.gw, 0, (size_t)9 * Cc * sizeof(float), s));
+            rc = launch_conv0_wgrad(p->x0, L.gy, L.gw, B, L.T, L.F, Cc, p->precision, s);
+            if (rc) return rc;
+        }
+    }
+    return SEDK_OK;
 }

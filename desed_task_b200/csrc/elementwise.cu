@@ -183,7 +183,13 @@ add_noise_kernel(const float* __restrict__ x, const float* __restrict__ noise, c
 __global__ void __launch_bounds__(EW_THREADS)
 adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                 float* __restrict__ ema, int64_t n, int do_adam, float step_size, float beta1, float beta2, float eps,
-                float inv_sqrt_bc2, float ema_alpha, float grad_scale) {
+                float inv_sqrt_bc2, float ema_alpha, float grad_scale, const float* __restrict__ hyper) {
+    if (hyper != nullptr) {
+        step_size = hyper[0];
+        inv_sqrt_bc2 = hyper[1];
+        ema_alpha = hyper[2];
+        grad_scale = hyper[3];
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float pi = p[i];
         if (ema) ema[i] = ema[i] * ema_alpha + pi * (1.0f - ema_alpha);
@@ -358,8 +364,27 @@ extern "C" int sedk_adam_ema(float* p, const float* g, float* m, float* v, float
         inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     }
     adam_ema_kernel<<<grid1(n, 1), EW_THREADS, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, n, do_adam, step_size, beta1,
-                                                                        beta2, eps, inv_sqrt_bc2, ema_alpha, grad_scale);
+                                                                        beta2, eps, inv_sqrt_bc2, ema_alpha, grad_scale, nullptr);
     SEDK_LAUNCH_CHECK("adam_ema_kernel");
+    return SEDK_OK;
+}
+
+__global__ void bump_kernel(uint64_t* c, uint64_t inc) { *c += inc; }
+
+extern "C" int sedk_adam_ema_dev(float* p, const float* g, float* m, float* v, float* ema, int64_t n, int do_adam,
+                                 float beta1, float beta2, float eps, const float* hyper, void* stream) {
+    SEDK_REQUIRE(p && hyper && n > 0, "sedk_adam_ema_dev: bad arguments");
+    SEDK_REQUIRE(!do_adam || (g && m && v), "sedk_adam_ema_dev: Adam needs g, m, v");
+    adam_ema_kernel<<<grid1(n, 1), EW_THREADS, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, n, do_adam, 0.f, beta1, beta2,
+                                                                        eps, 1.f, 0.f, 1.f, hyper);
+    SEDK_LAUNCH_CHECK("adam_ema_kernel");
+    return SEDK_OK;
+}
+
+extern "C" int sedk_bump_counter(uint64_t* counter, uint64_t inc, void* stream) {
+    SEDK_REQUIRE(counter, "sedk_bump_counter: null counter");
+    bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, inc);
+    SEDK_LAUNCH_CHECK("bump_kernel");
     return SEDK_OK;
 }
 

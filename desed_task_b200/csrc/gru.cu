@@ -1,0 +1,351 @@
+// Persistent bidirectional GRU recurrence (nn.GRU semantics, gate order r,z,n; desed_task/nnet/RNN.py:19-30).
+//
+// The input-side GEMMs (x W_ih^T + b_ih for all T steps) are hoisted out (gemm.cu).  What is left is strictly
+// sequential: h_t = f(W_hh h_{t-1}, gi_t).  Batch rows are independent in the recurrence, so a CTA owns NB batch rows
+// of one direction and keeps W_hh RESIDENT IN REGISTERS for all T steps: thread (row j, 64-wide k segment) holds 64
+// weights; per step it does 64*NB FMAs against h (broadcast from shared memory), segment partials meet in shared
+// memory, and H*NB "gate" threads finish the cell (exact fp32; tanhf/expf).  Two __syncthreads per step, no global
+// traffic on the dependency chain except the prefetched gi row.  The backward kernel mirrors it with W_hh^T.
+//
+// H = 128 (2023 recipe) runs as a single CTA of 768 threads.  H = 192 (2024 recipe) does not fit one SM's register
+// file, so the hidden units are split over a cluster of 3 CTAs (64 units each, 576 threads) which exchange the new h
+// through distributed shared memory each step.
+#include "kernels.h"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace sedk {
+namespace {
+
+constexpr int SEG = 64;
+
+template <int H, int CS>
+struct GruCfg {
+    static constexpr int HU = H / CS;             // hidden units owned by one CTA
+    static constexpr int R = 3 * HU;              // gate rows owned by one CTA
+    static constexpr int SEGS = H / SEG;          // k segments (forward) per row
+    static constexpr int NT_F = R * SEGS;         // forward threads
+    static constexpr int JSEGS = 3 * H / SEG;     // j segments (backward) per column
+    static constexpr int NT_B = HU * JSEGS;       // backward threads
+    static_assert(H % SEG == 0 && H % CS == 0 && (HU % 32) == 0, "unsupported hidden size");
+    static_assert(NT_F <= 1024 && NT_B <= 1024, "too many threads");
+};
+template <int H, int CS, int NB>
+struct GruNbOk {
+    static_assert(NB * GruCfg<H, CS>::HU <= GruCfg<H, CS>::NT_F && NB * GruCfg<H, CS>::HU <= GruCfg<H, CS>::NT_B,
+                  "not enough threads for the gate phase");
+    static constexpr bool ok = true;
+};
+
+// ----------------------------------------------------------------------------------------------------------------
+template <int H, int CS, int NB>
+__global__ void __launch_bounds__(GruCfg<H, CS>::NT_F, 1)
+gru_fwd_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, const float* __restrict__ whh0,
+               const float* __restrict__ whh1, const float* __restrict__ bhh0, const float* __restrict__ bhh1,
+               float* __restrict__ out, float* __restrict__ gates0, float* __restrict__ gates1,
+               float* __restrict__ hprev0, float* __restrict__ hprev1, int B, int T, int save) {
+    using Cfg = GruCfg<H, CS>;
+    constexpr int HU = Cfg::HU, R = Cfg::R, SEGS = Cfg::SEGS, NT = Cfg::NT_F;
+    __shared__ __align__(16) float h_s[2][NB][H];          // double-buffered when CS > 1 (remote writes)
+    __shared__ float part[SEGS][NB][R];
+    const int tid = threadIdx.x;
+    const int dir = blockIdx.y;
+    int crank = 0;
+    if (CS > 1) crank = (int)cg::this_cluster().block_rank();
+    const int b0 = (blockIdx.x / CS) * NB;
+    const int u0 = crank * HU;                              // first hidden unit owned by this CTA
+    const float* gi = dir ? gi1 : gi0;
+    const float* whh = dir ? whh1 : whh0;
+    const float* bhh = dir ? bhh1 : bhh0;
+    float* gates = dir ? gates1 : gates0;
+    float* hprev = dir ? hprev1 : hprev0;
+
+    const int seg = tid / R, row = tid - seg * R;           // row in [0, R): gate = row / HU, unit = row % HU
+    const int gate = row / HU, unit = row - gate * HU;
+    const int grow = gate * H + u0 + unit;                  // row of W_hh [3H, H]
+    float w[SEG];
+#pragma unroll
+    for (int k = 0; k < SEG; k++) w[k] = whh[(size_t)grow * H + seg * SEG + k];
+
+    for (int i = tid; i < 2 * NB * H; i += NT) (&h_s[0][0][0])[i] = 0.f;
+    const bool is_gate = tid < NB * HU;
+    const int gb = tid / HU, gu = tid - gb * HU;            // batch row / local unit of a gate thread
+    const int bglob = b0 + gb;
+    const bool active = is_gate && (bglob < B);
+    float bhr = 0.f, bhz = 0.f, bhn = 0.f, hval = 0.f;
+    if (is_gate) {
+        bhr = bhh[u0 + gu];
+        bhz = bhh[H + u0 + gu];
+        bhn = bhh[2 * H + u0 + gu];
+    }
+    if (CS > 1) cg::this_cluster().sync(); else __syncthreads();
+
+    int cur = 0;
+    for (int step = 0; step < T; step++) {
+        const int t = dir ? (T - 1 - step) : step;
+        float gir = 0.f, giz = 0.f, gin = 0.f;
+        if (active) {
+            const float* gp = gi + ((size_t)bglob * T + t) * 3 * H + u0 + gu;
+            gir = gp[0];
+            giz = gp[H];
+            gin = gp[2 * H];
+        }
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++) {
+            const float4* hv = reinterpret_cast<const float4*>(&h_s[cur][nb][seg * SEG]);
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int k4 = 0; k4 < SEG / 4; k4++) {
+                float4 hh = hv[k4];
+                a0 = fmaf(w[4 * k4], hh.x, a0);
+                a1 = fmaf(w[4 * k4 + 1], hh.y, a1);
+                a0 = fmaf(w[4 * k4 + 2], hh.z, a0);
+                a1 = fmaf(w[4 * k4 + 3], hh.w, a1);
+            }
+            part[seg][nb][row] = a0 + a1;
+        }
+        __syncthreads();
+        const int nxt = CS > 1 ? cur ^ 1 : cur;
+        if (is_gate) {
+            float ghr = bhr, ghz = bhz, ghn = bhn;
+#pragma unroll
+            for (int s = 0; s < SEGS; s++) {
+                ghr += part[s][gb][gu];
+                ghz += part[s][gb][HU + gu];
+                ghn += part[s][gb][2 * HU + gu];
+            }
+            const float r = sigmoidf_(gir + ghr);
+            const float zg = sigmoidf_(giz + ghz);
+            const float n = tanhf(gin + r * ghn);
+            const float hnew = (1.0f - zg) * n + zg * hval;
+            if (active) {
+                const size_t bt = (size_t)bglob * T + t;
+                if (save) {
+                    float* gs = gates + bt * 4 * H + u0 + gu;
+                    gs[0] = r;
+                    gs[H] = zg;
+                    gs[2 * H] = n;
+                    gs[3 * H] = ghn;
+                    hprev[bt * H + u0 + gu] = hval;
+                }
+                out[bt * 2 * H + dir * H + u0 + gu] = hnew;
+            }
+            hval = hnew;
+            if (CS > 1) {
+                cg::cluster_group cl = cg::this_cluster();
+#pragma unroll
+                for (int rk = 0; rk < CS; rk++) {
+                    float* remote = cl.map_shared_rank(&h_s[nxt][gb][u0 + gu], rk);
+                    *remote = hnew;
+                }
+            } else {
+                h_s[nxt][gb][u0 + gu] = hnew;
+            }
+        }
+        if (CS > 1) cg::this_cluster().sync(); else __syncthreads();
+        cur = nxt;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+template <int H, int CS, int NB>
+__global__ void __launch_bounds__(GruCfg<H, CS>::NT_B, 1)
+gru_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ whh0, const float* __restrict__ whh1,
+               const float* __restrict__ gates0, const float* __restrict__ gates1, const float* __restrict__ hprev0,
+               const float* __restrict__ hprev1, float* __restrict__ dgi0, float* __restrict__ dgi1,
+               float* __restrict__ dghn0, float* __restrict__ dghn1, int B, int T) {
+    using Cfg = GruCfg<H, CS>;
+    constexpr int HU = Cfg::HU, JSEGS = Cfg::JSEGS, NT = Cfg::NT_B;
+    __shared__ __align__(16) float dgh_s[2][NB][3 * H];     // recurrent pre-activation grads (r, z, hn), all units
+    __shared__ float part[JSEGS][NB][HU];
+    const int tid = threadIdx.x;
+    const int dir = blockIdx.y;
+    int crank = 0;
+    if (CS > 1) crank = (int)cg::this_cluster().block_rank();
+    const int b0 = (blockIdx.x / CS) * NB;
+    const int u0 = crank * HU;
+    const float* whh = dir ? whh1 : whh0;
+    const float* gates = dir ? gates1 : gates0;
+    const float* hprev = dir ? hprev1 : hprev0;
+    float* dgi = dir ? dgi1 : dgi0;
+    float* dghn = dir ? dghn1 : dghn0;
+
+    const int jseg = tid / HU, col = tid - jseg * HU;        // column u0+col of W_hh, rows jseg*64 .. +64
+    float w[SEG];
+#pragma unroll
+    for (int k = 0; k < SEG; k++) w[k] = whh[(size_t)(jseg * SEG + k) * H + u0 + col];
+
+    for (int i = tid; i < 2 * NB * 3 * H; i += NT) (&dgh_s[0][0][0])[i] = 0.f;
+    const bool is_gate = tid < NB * HU;
+    const int gb = tid / HU, gu = tid - gb * HU;
+    const int bglob = b0 + gb;
+    const bool active = is_gate && (bglob < B);
+    float dh = 0.f;
+    if (CS > 1) cg::this_cluster().sync(); else __syncthreads();
+
+    int cur = 0;
+    for (int step = T - 1; step >= 0; step--) {
+        const int t = dir ? (T - 1 - step) : step;
+        float dh_direct = 0.f, dr_pre = 0.f, dz_pre = 0.f, dn_pre = 0.f, dhn = 0.f;
+        if (active) {
+            const size_t bt = (size_t)bglob * T + t;
+            const float g = gout[bt * 2 * H + dir * H + u0 + gu] + dh;
+            const float* gs = gates + bt * 4 * H + u0 + gu;
+            const float r = gs[0], zg = gs[H], n = gs[2 * H], ghn = gs[3 * H];
+            const float hp = hprev[bt * H + u0 + gu];
+            const float dn = g * (1.0f - zg);
+            const float dz = g * (hp - n);
+            dh_direct = g * zg;
+            dn_pre = dn * (1.0f - n * n);
+            dz_pre = dz * zg * (1.0f - zg);
+            dr_pre = dn_pre * ghn * r * (1.0f - r);
+            dhn = dn_pre * r;
+            float* dp = dgi + bt * 3 * H + u0 + gu;
+            dp[0] = dr_pre;
+            dp[H] = dz_pre;
+            dp[2 * H] = dn_pre;
+            dghn[bt * H + u0 + gu] = dhn;
+        }
+        if (is_gate) {
+            if (CS > 1) {
+                cg::cluster_group cl = cg::this_cluster();
+#pragma unroll
+                for (int rk = 0; rk < CS; rk++) {
+                    float* base = cl.map_shared_rank(&dgh_s[cur][gb][0], rk);
+                    base[u0 + gu] = dr_pre;
+                    base[H + u0 + gu] = dz_pre;
+                    base[2 * H + u0 + gu] = dhn;
+                }
+            } else {
+                dgh_s[cur][gb][u0 + gu] = dr_pre;
+                dgh_s[cur][gb][H + u0 + gu] = dz_pre;
+                dgh_s[cur][gb][2 * H + u0 + gu] = dhn;
+            }
+        }
+        if (CS > 1) cg::this_cluster().sync(); else __syncthreads();
+        // dh_prev[u] += sum_j W_hh[j][u] * dgh[j]
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++) {
+            const float4* dv = reinterpret_cast<const float4*>(&dgh_s[cur][nb][jseg * SEG]);
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int k4 = 0; k4 < SEG / 4; k4++) {
+                float4 d = dv[k4];
+                a0 = fmaf(w[4 * k4], d.x, a0);
+                a1 = fmaf(w[4 * k4 + 1], d.y, a1);
+                a0 = fmaf(w[4 * k4 + 2], d.z, a0);
+                a1 = fmaf(w[4 * k4 + 3], d.w, a1);
+            }
+            part[jseg][nb][col] = a0 + a1;
+        }
+        __syncthreads();
+        if (is_gate) {
+            float s = dh_direct;
+#pragma unroll
+            for (int js = 0; js < JSEGS; js++) s += part[js][gb][gu];
+            dh = s;
+        }
+        if (CS > 1) cur ^= 1;      // next step's remote writes must not race with slower CTAs still reading
+    }
+}
+
+template <int H, int CS, int NB>
+int run_fwd(const float* const gi[2], const float* const w_hh[2], const float* const b_hh[2], float* out,
+            float* const gates[2], float* const hprev[2], int B, int T, int save, cudaStream_t s) {
+    using Cfg = GruCfg<H, CS>;
+    static_assert(GruNbOk<H, CS, NB>::ok, "");
+    auto kern = gru_fwd_kernel<H, CS, NB>;
+    dim3 grid(cdiv(B, NB) * CS, 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(Cfg::NT_F);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SEDK_CUDA(cudaLaunchKernelEx(&cfg, kern, gi[0], gi[1], w_hh[0], w_hh[1], b_hh[0], b_hh[1], out, gates[0], gates[1],
+                                 hprev[0], hprev[1], B, T, save));
+    return SEDK_OK;
+}
+
+template <int H, int CS, int NB>
+int run_bwd(const float* gout, const float* const w_hh[2], const float* const gates[2], const float* const hprev[2],
+            float* const dgi[2], float* const dghn[2], int B, int T, cudaStream_t s) {
+    using Cfg = GruCfg<H, CS>;
+    auto kern = gru_bwd_kernel<H, CS, NB>;
+    dim3 grid(cdiv(B, NB) * CS, 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(Cfg::NT_B);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SEDK_CUDA(cudaLaunchKernelEx(&cfg, kern, gout, w_hh[0], w_hh[1], gates[0], gates[1], hprev[0], hprev[1], dgi[0],
+                                 dgi[1], dghn[0], dghn[1], B, T));
+    return SEDK_OK;
+}
+
+// batch rows per CTA: keep every (row, direction) pair on its own SM while they fit, then double up
+inline int pick_nb(int B, int CS) {
+    const int sms = num_sms();
+    int nb = 1;
+    while (nb < 4 && cdiv(B, nb) * 2 * CS > sms) nb *= 2;
+    return nb;
+}
+
+}  // namespace
+
+int launch_gru_seq_fwd(const float* const gi[2], const float* const w_hh[2], const float* const b_hh[2], float* out,
+                       float* const gates[2], float* const hprev[2], int B, int T, int H, int save, cudaStream_t s) {
+    if (H == 128) {
+        switch (pick_nb(B, 1)) {
+            case 1: return run_fwd<128, 1, 1>(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
+            case 2: return run_fwd<128, 1, 2>(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
+            default: return run_fwd<128, 1, 4>(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
+        }
+    }
+    if (H == 64) return run_fwd<64, 1, 2>(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
+    if (H == 192) {
+        switch (pick_nb(B, 3)) {
+            case 1: return run_fwd<192, 3, 1>(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
+            case 2: return run_fwd<192, 3, 2>(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
+            default: return run_fwd<192, 3, 4>(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
+        }
+    }
+    SEDK_UNSUPPORTED("GRU hidden size %d has no sm_100a instantiation (supported: 64, 128, 192)", H);
+}
+
+int launch_gru_seq_bwd(const float* gout, const float* const w_hh[2], const float* const gates[2],
+                       const float* const hprev[2], float* const dgi[2], float* const dghn[2], int B, int T, int H,
+                       cudaStream_t s) {
+    if (H == 128) {
+        switch (pick_nb(B, 1)) {
+            case 1: return run_bwd<128, 1, 1>(gout, w_hh, gates, hprev, dgi, dghn, B, T, s);
+            case 2: return run_bwd<128, 1, 2>(gout, w_hh, gates, hprev, dgi, dghn, B, T, s);
+            default: return run_bwd<128, 1, 4>(gout, w_hh, gates, hprev, dgi, dghn, B, T, s);
+        }
+    }
+    if (H == 64) return run_bwd<64, 1, 2>(gout, w_hh, gates, hprev, dgi, dghn, B, T, s);
+    if (H == 192) {
+        switch (pick_nb(B, 3)) {
+            case 1: return run_bwd<192, 3, 1>(gout, w_hh, gates, hprev, dgi, dghn, B, T, s);
+            case 2: return run_bwd<192, 3, 2>(gout, w_hh, gates, hprev, dgi, dghn, B, T, s);
+            default: return run_bwd<192, 3, 4>(gout, w_hh, gates, hprev, dgi, dghn, B, T, s);
+        }
+    }
+    SEDK_UNSUPPORTED("GRU hidden size %d has no sm_100a instantiation (supported: 64, 128, 192)", H);
+}
+
+}  // namespace sedk

@@ -1,0 +1,82 @@
+// Internal launcher prototypes shared by the libsedk translation units (not part of the C ABI).
+#pragma once
+#include "common.cuh"
+
+namespace sedk {
+
+// ---- conv.cu ------------------------------------------------------------------------------------------------
+// wpack[0][tap][co][ci] = w[co][ci][tap];  wpack[1][tap][ci][co] = w[co][ci][8 - tap]   (tap = ky*3 + kx)
+int launch_pack_weights(const float* w, float* wpack, int cin, int cout, cudaStream_t s);
+// gw[co][ci][tap] = gwpack[tap][co][ci]
+int launch_unpack_wgrad(const float* gwpack, float* gw, int cin, int cout, cudaStream_t s);
+// first layer (Cin = 1): fused instance-minmax scaler + specaugment mask + 3x3 stencil.
+//   x: log-mel (b, m, t) strided; writes x0 [B,T,F] (the scaled/masked conv input, for backward; may be NULL),
+//   z [B,T,F,cout] (+bias) and accumulates per-channel sum / sum^2 into stats[0..2*cout) when stats != NULL.
+int launch_conv0_fwd(const float* x, int64_t sb, int64_t sm, int64_t st, const uint32_t* minmax, float scaler_eps,
+                     const int32_t* specaug, const float* w, const float* bias, float* x0, float* z, double* stats,
+                     int B, int T, int F, int cout, cudaStream_t s);
+// gw[co][tap] += sum_pix gz[pix][co] * x0[pix + shift(tap)]     (gw must be zeroed by the caller)
+int launch_conv0_wgrad(const float* x0, const float* gz, float* gw, int B, int T, int F, int cout, int precision,
+                       cudaStream_t s);
+// generic 3x3 / pad 1 / stride 1 conv on channels-last tensors with tensor-core MMA:
+//   out[b,t,f,n] = bias[n] + sum_{tap,k} in[b,t+dy,f+dx,k] * wp[tap][n][k]; optional per-channel sum / sum^2.
+// The same kernel computes dgrad when given the flipped/transposed pack (wpack[1]).
+int launch_conv3x3(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T, int F,
+                   int cin, int cout, int precision, cudaStream_t s);
+// gwpack[tap][co][ci] += sum_pix gz[pix][co] * x[pix + shift(tap)][ci]   (gwpack zeroed by the caller)
+int launch_conv_wgrad(const float* x, const float* gz, float* gwpack, int B, int T, int F, int cin, int cout,
+                      int precision, cudaStream_t s);
+
+// ---- bnglu.cu -----------------------------------------------------------------------------------------------
+// bn[0]=scale, bn[1]=shift, bn[2]=mean, bn[3]=invstd from batch sums (training) or running stats (eval);
+// training also updates running_mean / running_var (momentum, unbiased var) and num_batches.
+int launch_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, int64_t* num_batches, float* bn, double count, float eps, float momentum,
+                       int training, int C, cudaStream_t s);
+// out = avgpool( dropout( (Wg y + bg) * sigmoid(y) ) ),  y = scale*z + shift
+int launch_bnglu_pool_fwd(const float* z, const float* bn, const float* glu_w, const float* glu_b, float* out, int B,
+                          int T, int F, int C, int pt, int pf, float drop_p, uint64_t seed, const uint64_t* seed_dev,
+                          uint64_t drop_stream, int precision, cudaStream_t s);
+// backward of the block above: writes gy (grad wrt y = BN output) for every pooled pixel, accumulates gglu_w, gglu_b
+// and stats[2C..4C) = {sum gy, sum gy*zhat}.  gy must be pre-zeroed when the pooling drops rows/cols.
+int launch_bnglu_pool_bwd(const float* z, const float* bn, const float* glu_w, const float* glu_b, const float* gout,
+                          float* gy, float* gglu_w, float* gglu_b, double* stats, int B, int T, int F, int C, int pt,
+                          int pf, float drop_p, uint64_t seed, const uint64_t* seed_dev, uint64_t drop_stream, int precision,
+                          cudaStream_t s);
+// train-mode BN backward: gy -> gz in place; writes ggamma, gbeta (and zero conv-bias grad gb)
+int launch_bn_bwd_apply(float* gy, const float* z, const float* bn, const double* stats, float* ggamma, float* gbeta,
+                        float* gb, double count, int64_t n_pix, int C, cudaStream_t s);
+
+// ---- gemm.cu ------------------------------------------------------------------------------------------------
+int launch_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+                int ldb, float beta, float* C, int ldc, const float* bias, int precision, cudaStream_t s);
+// column sums: out[n] (+)= sum_m A[m*lda + n]
+int launch_colsum(const float* A, int M, int N, int lda, float* out, int accumulate, cudaStream_t s);
+
+// ---- gru.cu -------------------------------------------------------------------------------------------------
+// one direction-pair launch: gi[dir] [B,T,3H] (= x W_ih^T + b_ih), out [B,T,2H]; saves gates/hprev when training
+int launch_gru_seq_fwd(const float* const gi[2], const float* const w_hh[2], const float* const b_hh[2], float* out,
+                       float* const gates[2], float* const hprev[2], int B, int T, int H, int save, cudaStream_t s);
+// BPTT: gout [B,T,2H] -> dgi[dir] [B,T,3H] (written over gi) and dghn[dir] [B,T,H]
+int launch_gru_seq_bwd(const float* gout, const float* const w_hh[2], const float* const gates[2],
+                       const float* const hprev[2], float* const dgi[2], float* const dghn[2], int B, int T, int H,
+                       cudaStream_t s);
+
+// ---- heads.cu -----------------------------------------------------------------------------------------------
+int launch_heads_fwd(const float* x, const float* dw, const float* db, const float* sw, const float* sb,
+                     const uint8_t* cmask, float* strong, float* weak, float* sof, int B, int T, int D, int C,
+                     cudaStream_t s);
+int launch_heads_bwd(const float* x, const float* dw, const float* sw, const uint8_t* cmask, const float* strong,
+                     const float* weak, const float* sof, const float* gstrong, const float* gweak, float* gx,
+                     float* gdw, float* gdb, float* gsw, float* gsb, int B, int T, int D, int C, cudaStream_t s);
+// y = keep ? x/(1-p) : 0 (stream-indexed Philox mask); used forward and backward
+int launch_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev,
+                   uint64_t stream_id, cudaStream_t s);
+// adaptive_avg_pool1d + concat + dropout for the embedding fusion (CRNN.py:280-294) and its backward (x part only)
+int launch_emb_concat(const float* x, const float* emb, const int32_t* dropstep, float* cat, int B, int T, int nb,
+                      int emb_dim, int emb_T, float p, uint64_t seed, const uint64_t* seed_dev, uint64_t stream_id,
+                      cudaStream_t s);
+int launch_emb_concat_bwd(const float* gcat, const int32_t* dropstep, float* gx, int B, int T, int nb, int emb_dim,
+                          float p, uint64_t seed, const uint64_t* seed_dev, uint64_t stream_id, cudaStream_t s);
+
+}  // namespace sedk

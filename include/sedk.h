@@ -114,6 +114,12 @@ SEDK_API int sedk_add_noise(const float* x, const float* noise, const float* snr
  */
 SEDK_API int sedk_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n, int do_adam, float lr,
                   float beta1, float beta2, float eps, int step, float ema_alpha, float grad_scale, void* stream);
+/* Same kernel with the per-step scalars read from DEVICE memory so that a captured CUDA graph can be replayed with new
+ * values: hyper[4] = { lr / (1 - beta1^step), 1 / sqrt(1 - beta2^step), ema_alpha, grad_scale }. */
+SEDK_API int sedk_adam_ema_dev(float* p, const float* g, float* m, float* v, float* ema, int64_t n, int do_adam, float beta1,
+                      float beta2, float eps, const float* hyper, void* stream);
+/* *counter += inc (one thread); pair with sedk_crnn_plan.seed_dev */
+SEDK_API int sedk_bump_counter(uint64_t* counter, uint64_t inc, void* stream);
 /* sum of squares of g into out[0] (double), for gradient clipping (2024 recipe gradient_clip 5.0) */
 SEDK_API int sedk_sumsq(const float* g, int64_t n, double* out, void* stream);
 
@@ -183,12 +189,15 @@ typedef struct {
     float dropout_p;                /* CNN.py:90-91, CRNN.py:103                               */
     float bn_eps, bn_momentum;      /* CNN.py:76 (1e-3, 0.99)                                  */
     uint64_t seed;                  /* dropout Philox seed for this forward                    */
+    const uint64_t* seed_dev;       /* optional device counter added to `seed` inside the kernels (lets a captured CUDA
+                                       graph draw fresh dropout masks on every replay); NULL: unused           */
     /* input: log-mel (un-scaled) with strides; scaler + specaugment are fused into the first conv load */
     const float* x;
     int64_t x_sb, x_sm, x_st;
     const uint32_t* minmax;         /* per-clip {min,max} (instance/minmax scaler); NULL: x is already scaled */
     float scaler_eps;
     const int32_t* specaug;         /* int32 [B][4] = f_start, f_end, t_start, t_end or NULL (CRNN.py:207-219) */
+    float* x0;                      /* [B, n_frames, n_mels] workspace: scaled + masked first-layer input (saved for bwd) */
     sedk_conv_layer conv[SEDK_MAX_CONV];
     sedk_gru_layer gru[SEDK_MAX_GRU_LAYERS];
     /* optional embedding fusion (aggregation_type="pool1d", CRNN.py:280-294) */
@@ -223,8 +232,9 @@ SEDK_API int sedk_sizeof_crnn_plan(void);
 
 /* Losses of SEDTask4.training_step (sed_trainer.py:309-342): BCE(strong rows [0,n_strong)) + BCE(weak rows
  * [n_strong, n_strong+n_weak)) + weight * (MSE(strong, teacher) + MSE(weak, teacher)); teacher pointers may be NULL.
- * labels [B,C,T'], labels_weak [n_weak, C].  Writes losses[8] = {total, bce_strong, bce_weak, mse_strong,
- * mse_weak, bce_strong_teacher, bce_weak_teacher, 0} and the gradients wrt strong / weak (may be NULL). */
+ * labels [B,C,T'], labels_weak [n_weak, C].  `losses` is a 16-float device buffer: on return losses[0..8) =
+ * {total, bce_strong, bce_weak, mse_strong, mse_weak, bce_strong_teacher, bce_weak_teacher, cons_weight}
+ * (losses[8..16) is scratch); gstrong / gweak (may be NULL) receive d total / d strong, d total / d weak. */
 SEDK_API int sedk_sed_loss(const float* strong, const float* weak, const float* t_strong, const float* t_weak,
                   const float* labels, const float* labels_weak, int B, int C, int T, int n_strong, int n_weak,
                   float cons_weight, float* losses, float* gstrong, float* gweak, void* stream);

@@ -1,0 +1,164 @@
+"""GPU parity: CUDA CRNN (forward, backward, BN statistics) vs the CPU oracle and the golden fixtures.
+
+Tolerances (north_star): frame posteriors <= 1e-3 max-abs in the TF32 production mode; the 3xTF32 'fp32' mode is held to
+2e-5.  Gradients are compared relative to the largest reference gradient entry of the same tensor (floored at 1% of the
+global gradient scale, exactly as oracle/make_golden.py pins the oracle against the reference)."""
+import dataclasses
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import crnn as ocrnn, frontend as ofe, trainer as otr
+from tests.util import gen_wave, golden, maxdiff
+
+pytestmark = pytest.mark.gpu
+
+
+def build(cfg, P, dev, precision, **over):
+    from desed_task_b200.nnet.CRNN import CRNN
+    kw = dict(nclass=cfg.nclass, dropout=cfg.dropout, n_RNN_cell=cfg.n_RNN_cell, nb_filters=list(cfg.nb_filters),
+              pooling=[list(p) for p in cfg.pooling], kernel_size=[3] * 7, padding=[1] * 7, stride=[1] * 7,
+              activation="glu", rnn_layers=1, median_filter=7)
+    if cfg.use_embeddings:
+        kw.update(use_embeddings=True, embedding_size=768, embedding_type="frame", aggregation_type="pool1d")
+    kw.update(over)
+    net = CRNN(**kw)
+    net.load_state_dict(P, strict=True)
+    net = net.to(dev)
+    net.precision = precision
+    return net
+
+
+@pytest.fixture(scope="module")
+def feats():
+    return ofe.features(gen_wave(0, 2))
+
+
+def aux(cfg, B):
+    if not cfg.use_embeddings:
+        return None, None
+    g = torch.Generator().manual_seed(7)
+    emb = torch.randn(2, 768, 496, generator=g)
+    cm = torch.zeros(2, 27, dtype=torch.bool)
+    cm[0, :10] = True
+    cm[1, 10:] = True
+    return emb, cm
+
+
+@pytest.mark.parametrize("tag", ["2023", "2024"])
+@pytest.mark.parametrize("tl", [0, 1])
+@pytest.mark.parametrize("precision,tol", [(1, 2e-5), (0, 1e-3)])
+def test_eval_forward_matches_golden(dev, feats, tag, tl, precision, tol):
+    cfg = ocrnn.CFG_2023 if tag == "2023" else ocrnn.CFG_2024
+    P = ocrnn.init_params(cfg, seed=42, trained_like=bool(tl))
+    net = build(cfg, P, dev, precision)
+    assert net.eval() is None                                   # reference quirk: train()/eval() return None
+    emb, cm = aux(cfg, 2)
+    with torch.no_grad():
+        s, w = net(feats.to(dev), embeddings=None if emb is None else emb.to(dev),
+                   classes_mask=None if cm is None else cm.to(dev))
+    g = golden("crnn")
+    key = "%s_tl%d" % (tag, tl)
+    assert s.shape == (2, cfg.nclass, 156) and w.shape == (2, cfg.nclass)
+    assert np.abs(s.cpu().numpy() - g["strong_eval_" + key]).max() < tol
+    assert np.abs(w.cpu().numpy() - g["weak_eval_" + key]).max() < tol
+    if cm is not None:
+        assert (s[0, 10:] == 0).all() and (w[1, :10] == 0).all()    # masked classes are exactly 0
+
+
+@pytest.mark.parametrize("tag", ["2023", "2024"])
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [(1, 2e-5, 2e-3), (0, 1e-3, 5e-2)])
+def test_train_forward_backward_matches_oracle(dev, feats, tag, precision, tol_out, tol_grad):
+    cfg0 = ocrnn.CFG_2023 if tag == "2023" else ocrnn.CFG_2024
+    cfg = dataclasses.replace(cfg0, dropout=0.0)
+    P = ocrnn.init_params(cfg, seed=42, trained_like=True)
+    net = build(cfg, P, dev, precision, specaugm_t_p=0.0, specaugm_f_p=0.0)
+    net.train()
+    emb, cm = aux(cfg, 2)
+    g = golden("crnn")
+    key = "%s_tl1" % tag
+    ys = torch.from_numpy(g["labels_strong_" + key])
+    yw = (ys.sum(-1) > 0).float()
+    s, w = net(feats.to(dev), embeddings=None if emb is None else emb.to(dev),
+               classes_mask=None if cm is None else cm.to(dev))
+    assert np.abs(s.detach().cpu().numpy() - g["strong_train_" + key]).max() < tol_out
+    assert np.abs(w.detach().cpu().numpy() - g["weak_train_" + key]).max() < tol_out
+    loss = torch.nn.functional.binary_cross_entropy(s, ys.to(dev)) + \
+        torch.nn.functional.binary_cross_entropy(w, yw.to(dev))
+    assert abs(loss.item() - float(g["loss_train_" + key])) < 10 * tol_out
+    loss.backward()
+    # BatchNorm running statistics (momentum 0.99, unbiased variance)
+    sd = net.state_dict()
+    assert np.abs(sd["cnn.cnn.batchnorm0.running_mean"].cpu().numpy() - g["bn0_running_mean_" + key]).max() < 1e-4
+    assert np.abs(sd["cnn.cnn.batchnorm6.running_var"].cpu().numpy() - g["bn6_running_var_" + key]).max() < 1e-3
+    assert int(sd["cnn.cnn.batchnorm3.num_batches_tracked"]) == 1
+    # gradients vs the oracle's autograd
+    Pt = {k: (v.clone().requires_grad_(True) if ocrnn.is_float_param(k) else v.clone()) for k, v in P.items()}
+    so, wo = ocrnn.crnn_forward(Pt, feats, cfg, True, embeddings=emb, classes_mask=cm)
+    (otr.bce(so, ys) + otr.bce(wo, yw)).backward()
+    gscale = max(Pt[n].grad.abs().max().item() for n in ocrnn.param_names(P))
+    worst = ("", 0.0)
+    for n, p in net.named_parameters():
+        ref = Pt[n].grad
+        assert p.grad is not None and p.grad.shape == ref.shape, n
+        err = (p.grad.cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-2 * gscale)
+        if err > worst[1]:
+            worst = (n, err)
+    assert worst[1] < tol_grad, worst
+    assert np.abs(net.dense.weight.grad.cpu().numpy() - g["grad_dense_w_" + key]).max() < tol_grad * gscale
+
+
+def test_dropout_and_specaugment_statistics(dev, feats):
+    """Train mode with the shipped dropout 0.5 + SpecAugment: outputs stay finite, differ run to run, backward runs, the
+    same seed reproduces the same masks in backward (finite-difference check on one weight)."""
+    cfg = ocrnn.CFG_2023
+    P = ocrnn.init_params(cfg, seed=42, trained_like=True)
+    net = build(cfg, P, dev, 1)
+    net.train()
+    x = feats.to(dev).repeat(4, 1, 1)
+    s1, w1 = net(x)
+    s2, w2 = net(x)
+    assert torch.isfinite(s1).all() and torch.isfinite(w1).all()
+    assert (s1 - s2).abs().max().item() > 1e-4
+    (s1.mean() + w1.mean()).backward  # graph of the first call was overwritten by the second: must raise
+    with pytest.raises(RuntimeError):
+        (s1.mean() + w1.mean()).backward()
+    (s2.mean() + w2.mean()).backward()
+    gsum = sum(p.grad.abs().sum().item() for p in net.parameters())
+    assert np.isfinite(gsum) and gsum > 0
+
+
+def test_dropout_kernel_rate(dev):
+    """Philox dropout: keep-rate and scaling of the stand-alone block used after the RNN (p = 0.5 and 0.2)."""
+    cfg = dataclasses.replace(ocrnn.CFG_2023, dropout=0.5)
+    P = ocrnn.init_params(cfg, seed=1)
+    net = build(cfg, P, dev, 0, specaugm_t_p=0.0, specaugm_f_p=0.0)
+    net.train()
+    x = ofe.features(gen_wave(9, 4)).to(dev)
+    with torch.no_grad():
+        net(x)
+    ws = list(net._ws.values())[0]
+    out, dropped = ws.gru[-1]["out"], ws.rnn_drop
+    keep = (dropped != 0).float().mean().item()
+    assert abs(keep - 0.5) < 0.01
+    nz = dropped != 0
+    assert maxdiff(dropped[nz], out[nz] * 2.0) < 1e-6
+
+
+def test_unsupported_configs_raise(dev):
+    from desed_task_b200.nnet.CRNN import CRNN
+    x = torch.zeros(1, 128, 626, device=dev)
+    with pytest.raises(NotImplementedError):
+        CRNN(activation="relu", nb_filters=[16, 32, 64, 128, 128, 128, 128], kernel_size=[3] * 7, padding=[1] * 7,
+             stride=[1] * 7, pooling=[[2, 2], [2, 2], [1, 2], [1, 2], [1, 2], [1, 2], [1, 2]]).to(dev)(x)
+    with pytest.raises(AttributeError):
+        CRNN(nclass=(10, 17))                                     # same failure as the reference (CRNN.py:113)
+    with pytest.raises(_import_sedk_error()):
+        CRNN(nb_filters=[16, 32, 64, 128, 128, 128, 128], kernel_size=[3] * 7, padding=[1] * 7, stride=[1] * 7,
+             pooling=[[2, 2], [2, 2], [1, 2], [1, 2], [1, 2], [1, 2], [1, 2]])(torch.zeros(1, 128, 626))
+
+
+def _import_sedk_error():
+    from desed_task_b200._lib import SedkError
+    return SedkError
