@@ -64,6 +64,9 @@ _SIGS = {
     "sedk_version": (i32, []),
     "sedk_device_cc": (i32, []),
     "sedk_sizeof_crnn_plan": (i32, []),
+    "sedk_launch_count": (C.c_longlong, []),
+    "sedk_profile_enable": (i32, [i32]),
+    "sedk_profile_report": (i32, [C.c_char_p, i32]),
     "sedk_logmel_fwd": (i32, [vp, i32, i32, C.POINTER(MelTables), vp, i64, i64, i64, i32, f32, f32, f32, vp, vp]),
     "sedk_minmax_init": (i32, [vp, i32, vp]),
     "sedk_minmax_decode": (i32, [vp, vp, i32, vp]),
@@ -82,6 +85,7 @@ _SIGS = {
     "sedk_crnn_forward": (i32, [C.POINTER(CrnnPlan), vp]),
     "sedk_crnn_backward": (i32, [C.POINTER(CrnnPlan), vp]),
     "sedk_sed_loss": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp]),
+    "sedk_sed_loss_dev": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
     "sedk_gemm": (i32, [i32, i32, i32, i32, i32, f32, vp, i32, vp, i32, f32, vp, i32, vp, i32, vp]),
 }
 

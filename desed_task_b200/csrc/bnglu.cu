@@ -494,6 +494,7 @@ int run_bwd(const float* z, const float* bn, const float* glu_w, const float* gl
 int launch_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
                        float* running_var, int64_t* num_batches, float* bn, double count, float eps, float momentum,
                        int training, int C, cudaStream_t s) {
+    SEDK_PROF("bn_finalize", s);
     bn_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(stats, gamma, beta, running_mean, running_var, num_batches, bn, count,
                                                     eps, momentum, training, C);
     SEDK_LAUNCH_CHECK("bn_finalize_kernel");
@@ -503,6 +504,9 @@ int launch_bn_finalize(const double* stats, const float* gamma, const float* bet
 int launch_bnglu_pool_fwd(const float* z, const float* bn, const float* glu_w, const float* glu_b, float* out, int B,
                           int T, int F, int C, int pt, int pf, float drop_p, uint64_t seed, const uint64_t* seed_dev,
                           uint64_t drop_stream, int precision, cudaStream_t s) {
+    char pname[64];
+    snprintf(pname, sizeof(pname), "bnglu_pool_fwd_c%d", C);
+    SEDK_PROF(pname, s);
     TileGeom gm = make_geom(T, F, pt, pf);
     SEDK_REQUIRE(geom_ok(gm), "bnglu_pool: pooling (%d,%d) on a %dx%d map is not supported", pt, pf, T, F);
     switch (C) {
@@ -518,6 +522,9 @@ int launch_bnglu_pool_bwd(const float* z, const float* bn, const float* glu_w, c
                           float* gy, float* gglu_w, float* gglu_b, double* stats, int B, int T, int F, int C, int pt,
                           int pf, float drop_p, uint64_t seed, const uint64_t* seed_dev, uint64_t drop_stream, int precision,
                           cudaStream_t s) {
+    char pname[64];
+    snprintf(pname, sizeof(pname), "bnglu_pool_bwd_c%d", C);
+    SEDK_PROF(pname, s);
     TileGeom gm = make_geom(T, F, pt, pf);
     SEDK_REQUIRE(geom_ok(gm), "bnglu_pool: pooling (%d,%d) on a %dx%d map is not supported", pt, pf, T, F);
     if (gm.Te != T || gm.Fe != F) SEDK_CUDA(cudaMemsetAsync(gy, 0, (size_t)B * T * F * C * sizeof(float), s));
@@ -532,6 +539,9 @@ int launch_bnglu_pool_bwd(const float* z, const float* bn, const float* glu_w, c
 
 int launch_bn_bwd_apply(float* gy, const float* z, const float* bn, const double* stats, float* ggamma, float* gbeta,
                         float* gb, double count, int64_t n_pix, int C, cudaStream_t s) {
+    char pname[64];
+    snprintf(pname, sizeof(pname), "bn_bwd_apply_c%d", C);
+    SEDK_PROF(pname, s);
     SEDK_REQUIRE(C % 4 == 0, "bn_bwd_apply: C %% 4 != 0");
     const int64_t n4 = n_pix * C / 4;
     int64_t blocks = (n4 + 256 * 4 - 1) / (256 * 4);

@@ -13,6 +13,15 @@ namespace sedk {
 // error plumbing (no exceptions cross the C ABI)
 void set_error(const char* fmt, ...);
 int  check_launch(const char* what);
+void count_launch();
+// RAII device-timing scope around one launcher (no-op unless sedk_profile_enable(1) and the stream is not capturing)
+struct ProfScope {
+    ProfScope(const char* name, cudaStream_t s);
+    ~ProfScope();
+    int idx_;
+    cudaStream_t s_;
+};
+#define SEDK_PROF(name, stream) ::sedk::ProfScope prof_scope__(name, stream)
 
 #define SEDK_REQUIRE(cond, ...)                                   \
     do {                                                          \

@@ -504,12 +504,14 @@ int launch_with_smem(K kernel, dim3 grid, size_t smem, cudaStream_t s, const cha
 
 // ------------------------------------------------------------------------------------------------------------
 int launch_pack_weights(const float* w, float* wpack, int cin, int cout, cudaStream_t s) {
+    SEDK_PROF("pack_weights", s);
     int n = 2 * 9 * cin * cout;
     pack_kernel<<<cdiv(n, 256), 256, 0, s>>>(w, wpack, cin, cout);
     SEDK_LAUNCH_CHECK("pack_kernel");
     return SEDK_OK;
 }
 int launch_unpack_wgrad(const float* gwpack, float* gw, int cin, int cout, cudaStream_t s) {
+    SEDK_PROF("unpack_wgrad", s);
     int n = 9 * cin * cout;
     unpack_kernel<<<cdiv(n, 256), 256, 0, s>>>(gwpack, gw, cin, cout);
     SEDK_LAUNCH_CHECK("unpack_kernel");
@@ -519,6 +521,7 @@ int launch_unpack_wgrad(const float* gwpack, float* gw, int cin, int cout, cudaS
 int launch_conv0_fwd(const float* x, int64_t sb, int64_t sm, int64_t st, const uint32_t* minmax, float scaler_eps,
                      const int32_t* specaug, const float* w, const float* bias, float* x0, float* z, double* stats,
                      int B, int T, int F, int cout, cudaStream_t s) {
+    SEDK_PROF("conv0_fwd", s);
     const int nTt = cdiv(T, C0_TT);
 #define SEDK_C0(CO)                                                                                              \
     {                                                                                                            \
@@ -538,6 +541,7 @@ int launch_conv0_fwd(const float* x, int64_t sb, int64_t sm, int64_t st, const u
 
 int launch_conv0_wgrad(const float* x0, const float* gz, float* gw, int B, int T, int F, int cout, int precision,
                        cudaStream_t s) {
+    SEDK_PROF("conv0_wgrad", s);
     const int tiles = B * cdiv(T, W0_TT) * cdiv(F, W0_FW);
     const int grid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
 #define SEDK_W0(CO, X3)                                                                                          \
@@ -584,6 +588,9 @@ static int run_conv_tiles(const float* in, const float* wp, const float* bias, f
 
 int launch_conv3x3(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T, int F,
                    int cin, int cout, int precision, cudaStream_t s) {
+    char pname[64];
+    snprintf(pname, sizeof(pname), "conv3x3_%dto%d_F%d", cin, cout, F);
+    SEDK_PROF(pname, s);
     const int nt = cout >= 128 ? 128 : cout;
     SEDK_REQUIRE(cout % nt == 0, "conv3x3: cout %d must be a multiple of %d", cout, nt);
 #define SEDK_CONV(CI, NTV) \
@@ -628,6 +635,9 @@ static int run_wgrad_tiles(const float* x, const float* gz, float* gwp, int B, i
 
 int launch_conv_wgrad(const float* x, const float* gz, float* gwpack, int B, int T, int F, int cin, int cout,
                       int precision, cudaStream_t s) {
+    char pname[64];
+    snprintf(pname, sizeof(pname), "conv_wgrad_%dto%d_F%d", cin, cout, F);
+    SEDK_PROF(pname, s);
     //                                         CIN  COUT NTAPS WM WN WK
     if (cin == 16 && cout == 32) return run_wgrad_tiles<16, 32, 9, 2, 1, 4>(x, gz, gwpack, B, T, F, precision, s);
     if (cin == 32 && cout == 64) return run_wgrad_tiles<32, 64, 9, 4, 2, 1>(x, gz, gwpack, B, T, F, precision, s);

@@ -289,6 +289,7 @@ extern "C" int sedk_minmax_decode(const uint32_t* minmax, float* out, int B, voi
 
 extern "C" int sedk_feat_mix_log(const float* x, const int64_t* perm, const float* coef, float* out, int B, int64_t n,
                                  int log_mode, float amin, float db_lo, float db_hi, uint32_t* minmax, void* stream) {
+    SEDK_PROF("feat_mix_log", (cudaStream_t)stream);
     SEDK_REQUIRE(x && out && B > 0 && n > 0, "sedk_feat_mix_log: bad arguments");
     const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
@@ -354,6 +355,7 @@ extern "C" int sedk_add_noise(const float* x, const float* noise, const float* s
 extern "C" int sedk_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n, int do_adam, float lr,
                              float beta1, float beta2, float eps, int step, float ema_alpha, float grad_scale,
                              void* stream) {
+    SEDK_PROF("adam_ema", (cudaStream_t)stream);
     SEDK_REQUIRE(p && n > 0, "sedk_adam_ema: bad arguments");
     SEDK_REQUIRE(!do_adam || (g && m && v && step >= 1), "sedk_adam_ema: Adam needs g, m, v and step >= 1");
     float step_size = 0.f, inv_sqrt_bc2 = 1.f;
@@ -373,6 +375,7 @@ __global__ void bump_kernel(uint64_t* c, uint64_t inc) { *c += inc; }
 
 extern "C" int sedk_adam_ema_dev(float* p, const float* g, float* m, float* v, float* ema, int64_t n, int do_adam,
                                  float beta1, float beta2, float eps, const float* hyper, void* stream) {
+    SEDK_PROF("adam_ema", (cudaStream_t)stream);
     SEDK_REQUIRE(p && hyper && n > 0, "sedk_adam_ema_dev: bad arguments");
     SEDK_REQUIRE(!do_adam || (g && m && v), "sedk_adam_ema_dev: Adam needs g, m, v");
     adam_ema_kernel<<<grid1(n, 1), EW_THREADS, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, n, do_adam, 0.f, beta1, beta2,

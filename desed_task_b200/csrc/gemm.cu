@@ -125,6 +125,9 @@ colsum_kernel(const float* __restrict__ A, int M, int N, int lda, float* __restr
 
 int launch_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
                 int ldb, float beta, float* C, int ldc, const float* bias, int precision, cudaStream_t s) {
+    char pname[64];
+    snprintf(pname, sizeof(pname), "gemm_%c%c_%dx%dx%d", transA ? 'T' : 'N', transB ? 'T' : 'N', M, N, K);
+    SEDK_PROF(pname, s);
     SEDK_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && C, "gemm: bad arguments");
     dim3 grid(cdiv(N, BN), cdiv(M, BM), 1);
     int k_per_split = cdiv(K, BK) * BK;
@@ -156,6 +159,7 @@ int launch_gemm(int transA, int transB, int M, int N, int K, float alpha, const 
 }
 
 int launch_colsum(const float* A, int M, int N, int lda, float* out, int accumulate, cudaStream_t s) {
+    SEDK_PROF("colsum", s);
     if (!accumulate) SEDK_CUDA(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), s));
     int splits = min(cdiv(M, 64), max(1, 2 * num_sms() / cdiv(N, 32)));
     int rpb = cdiv(M, splits);

@@ -271,6 +271,7 @@ int run_fwd(const float* const gi[2], const float* const w_hh[2], const float* c
     cfg.numAttrs = 1;
     SEDK_CUDA(cudaLaunchKernelEx(&cfg, kern, gi[0], gi[1], w_hh[0], w_hh[1], b_hh[0], b_hh[1], out, gates[0], gates[1],
                                  hprev[0], hprev[1], B, T, save));
+    count_launch();
     return SEDK_OK;
 }
 
@@ -294,6 +295,7 @@ int run_bwd(const float* gout, const float* const w_hh[2], const float* const ga
     cfg.numAttrs = 1;
     SEDK_CUDA(cudaLaunchKernelEx(&cfg, kern, gout, w_hh[0], w_hh[1], gates[0], gates[1], hprev[0], hprev[1], dgi[0],
                                  dgi[1], dghn[0], dghn[1], B, T));
+    count_launch();
     return SEDK_OK;
 }
 
@@ -309,6 +311,7 @@ inline int pick_nb(int B, int CS) {
 
 int launch_gru_seq_fwd(const float* const gi[2], const float* const w_hh[2], const float* const b_hh[2], float* out,
                        float* const gates[2], float* const hprev[2], int B, int T, int H, int save, cudaStream_t s) {
+    SEDK_PROF("gru_seq_fwd", s);
     if (H == 128) {
         switch (pick_nb(B, 1)) {
             case 1: return run_fwd<128, 1, 1>(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
@@ -330,6 +333,7 @@ int launch_gru_seq_fwd(const float* const gi[2], const float* const w_hh[2], con
 int launch_gru_seq_bwd(const float* gout, const float* const w_hh[2], const float* const gates[2],
                        const float* const hprev[2], float* const dgi[2], float* const dghn[2], int B, int T, int H,
                        cudaStream_t s) {
+    SEDK_PROF("gru_seq_bwd", s);
     if (H == 128) {
         switch (pick_nb(B, 1)) {
             case 1: return run_bwd<128, 1, 1>(gout, w_hh, gates, hprev, dgi, dghn, B, T, s);

@@ -220,8 +220,9 @@ __device__ __forceinline__ float bce_grad(float p, float y) { return (p - y) / f
 __global__ void __launch_bounds__(256)
 sed_loss_kernel(const float* __restrict__ strong, const float* __restrict__ weak, const float* __restrict__ ts,
                 const float* __restrict__ tw, const float* __restrict__ labels, const float* __restrict__ lweak, int B,
-                int C, int T, int n_strong, int n_weak, float cw, float* __restrict__ sums,
-                float* __restrict__ gstrong, float* __restrict__ gweak) {
+                int C, int T, int n_strong, int n_weak, float cw, const float* __restrict__ cw_dev,
+                float* __restrict__ sums, float* __restrict__ gstrong, float* __restrict__ gweak) {
+    if (cw_dev != nullptr) cw = *cw_dev;
     const int64_t ns = (int64_t)B * C * T, nw = (int64_t)B * C;
     const float inv_bs = n_strong > 0 ? 1.f / (float)((int64_t)n_strong * C * T) : 0.f;
     const float inv_bw = n_weak > 0 ? 1.f / (float)((int64_t)n_weak * C) : 0.f;
@@ -271,8 +272,9 @@ sed_loss_kernel(const float* __restrict__ strong, const float* __restrict__ weak
 }
 
 __global__ void sed_loss_finalize(float* losses, const float* sums, int B, int C, int T, int n_strong, int n_weak,
-                                  float cw) {
+                                  float cw, const float* cw_dev) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (cw_dev != nullptr) cw = *cw_dev;
     const float bs = n_strong > 0 ? sums[0] / (float)((int64_t)n_strong * C * T) : 0.f;
     const float bw = n_weak > 0 ? sums[1] / (float)((int64_t)n_weak * C) : 0.f;
     const float ms = sums[2] / (float)((int64_t)B * C * T);
@@ -367,6 +369,7 @@ emb_concat_bwd_kernel(const float* __restrict__ gcat, const int32_t* __restrict_
 int launch_heads_fwd(const float* x, const float* dw, const float* db, const float* sw, const float* sb,
                      const uint8_t* cmask, float* strong, float* weak, float* sof, int B, int T, int D, int C,
                      cudaStream_t s) {
+    SEDK_PROF("heads_fwd", s);
     SEDK_REQUIRE(C >= 1 && C <= HC_MAX, "heads: nclass %d must be in [1, %d]", C, HC_MAX);
     size_t smem = (size_t)(2 * C * (D + 1) + HT * (D + 1) + HT * 2 * HC_MAX + 2 * HC_MAX) * sizeof(float);
     SEDK_REQUIRE(smem <= 227 * 1024, "heads: feature width %d too large", D);
@@ -384,6 +387,7 @@ int launch_heads_fwd(const float* x, const float* dw, const float* db, const flo
 int launch_heads_bwd(const float* x, const float* dw, const float* sw, const uint8_t* cmask, const float* strong,
                      const float* weak, const float* sof, const float* gstrong, const float* gweak, float* gx,
                      float* gdw, float* gdb, float* gsw, float* gsb, int B, int T, int D, int C, cudaStream_t s) {
+    SEDK_PROF("heads_bwd", s);
     SEDK_REQUIRE(C >= 1 && C <= HC_MAX, "heads: nclass %d must be in [1, %d]", C, HC_MAX);
     size_t smem = (size_t)(T * 2 * C + 2 * HC_MAX) * sizeof(float);
     SEDK_REQUIRE(smem <= 227 * 1024, "heads: sequence of %d frames too long", T);
@@ -401,6 +405,7 @@ int launch_heads_bwd(const float* x, const float* dw, const float* sw, const uin
 
 int launch_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev,
                    uint64_t stream_id, cudaStream_t s) {
+    SEDK_PROF("dropout", s);
     const uint32_t thresh = drop_threshold(p);
     const float inv_keep = 1.0f / (1.0f - p);
     int64_t blocks = ((n + 3) / 4 + 255) / 256;
@@ -415,6 +420,7 @@ int launch_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, 
 int launch_emb_concat(const float* x, const float* emb, const int32_t* dropstep, float* cat, int B, int T, int nb,
                       int emb_dim, int emb_T, float p, uint64_t seed, const uint64_t* seed_dev, uint64_t stream_id,
                       cudaStream_t s) {
+    SEDK_PROF("emb_concat", s);
     const uint32_t thresh = p > 0.f ? drop_threshold(p) : 0u;
     const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
     dim3 grid(cdiv(T, 32), cdiv(emb_dim, 32) + cdiv(nb, 32), B);
@@ -426,6 +432,7 @@ int launch_emb_concat(const float* x, const float* emb, const int32_t* dropstep,
 
 int launch_emb_concat_bwd(const float* gcat, const int32_t* dropstep, float* gx, int B, int T, int nb, int emb_dim,
                           float p, uint64_t seed, const uint64_t* seed_dev, uint64_t stream_id, cudaStream_t s) {
+    SEDK_PROF("emb_concat_bwd", s);
     const uint32_t thresh = p > 0.f ? drop_threshold(p) : 0u;
     const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
     const int64_t total = (int64_t)B * T * nb;
@@ -440,9 +447,10 @@ int launch_emb_concat_bwd(const float* gcat, const int32_t* dropstep, float* gx,
 
 }  // namespace sedk
 
-extern "C" int sedk_sed_loss(const float* strong, const float* weak, const float* t_strong, const float* t_weak,
-                             const float* labels, const float* labels_weak, int B, int C, int T, int n_strong,
-                             int n_weak, float cons_weight, float* losses, float* gstrong, float* gweak, void* stream) {
+static int sed_loss_impl(const float* strong, const float* weak, const float* t_strong, const float* t_weak,
+                         const float* labels, const float* labels_weak, int B, int C, int T, int n_strong, int n_weak,
+                         float cons_weight, const float* cw_dev, float* losses, float* gstrong, float* gweak,
+                         void* stream) {
     using namespace sedk;
     SEDK_REQUIRE(strong && weak && losses && B > 0 && C > 0 && T > 0, "sedk_sed_loss: bad arguments");
     SEDK_REQUIRE(n_strong >= 0 && n_weak >= 0 && n_strong + n_weak <= B, "sedk_sed_loss: n_strong + n_weak > B");
@@ -450,15 +458,34 @@ extern "C" int sedk_sed_loss(const float* strong, const float* weak, const float
     SEDK_REQUIRE(n_weak == 0 || labels_weak, "sedk_sed_loss: labels_weak missing");
     SEDK_REQUIRE((t_strong == nullptr) == (t_weak == nullptr), "sedk_sed_loss: give both teacher tensors or none");
     cudaStream_t s = (cudaStream_t)stream;
-    // losses[8..15] is NOT available: the running sums live in losses[8..13] of a 16-float buffer
-    SEDK_CUDA(cudaMemsetAsync(losses, 0, 16 * sizeof(float), s));
+    SEDK_PROF("sed_loss", s);
+    SEDK_CUDA(cudaMemsetAsync(losses, 0, 16 * sizeof(float), s));      // [0,8) results, [8,16) running sums
     const int64_t n = (int64_t)B * C * T + (int64_t)B * C;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
     sed_loss_kernel<<<blocks, 256, 0, s>>>(strong, weak, t_strong, t_weak, labels, labels_weak, B, C, T, n_strong, n_weak,
-                                           cons_weight, losses + 8, gstrong, gweak);
+                                           cons_weight, cw_dev, losses + 8, gstrong, gweak);
     SEDK_LAUNCH_CHECK("sed_loss_kernel");
-    sed_loss_finalize<<<1, 32, 0, s>>>(losses, losses + 8, B, C, T, n_strong, n_weak, cons_weight);
+    sed_loss_finalize<<<1, 32, 0, s>>>(losses, losses + 8, B, C, T, n_strong, n_weak, cons_weight, cw_dev);
     SEDK_LAUNCH_CHECK("sed_loss_finalize");
     return SEDK_OK;
+}
+
+extern "C" int sedk_sed_loss(const float* strong, const float* weak, const float* t_strong, const float* t_weak,
+                             const float* labels, const float* labels_weak, int B, int C, int T, int n_strong,
+                             int n_weak, float cons_weight, float* losses, float* gstrong, float* gweak, void* stream) {
+    return sed_loss_impl(strong, weak, t_strong, t_weak, labels, labels_weak, B, C, T, n_strong, n_weak, cons_weight,
+                         nullptr, losses, gstrong, gweak, stream);
+}
+
+extern "C" int sedk_sed_loss_dev(const float* strong, const float* weak, const float* t_strong, const float* t_weak,
+                                 const float* labels, const float* labels_weak, int B, int C, int T, int n_strong,
+                                 int n_weak, const float* cons_weight_dev, float* losses, float* gstrong, float* gweak,
+                                 void* stream) {
+    if (cons_weight_dev == nullptr) {
+        sedk::set_error("sedk_sed_loss_dev: cons_weight_dev is null");
+        return SEDK_ERR_INVALID;
+    }
+    return sed_loss_impl(strong, weak, t_strong, t_weak, labels, labels_weak, B, C, T, n_strong, n_weak, 0.f,
+                         cons_weight_dev, losses, gstrong, gweak, stream);
 }

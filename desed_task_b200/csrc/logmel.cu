@@ -301,6 +301,7 @@ extern "C" int sedk_logmel_fwd(const float* wave, int B, int L, const sedk_mel_t
                                int64_t out_sm, int64_t out_st, int log_mode, float amin, float db_lo, float db_hi,
                                uint32_t* minmax, void* stream) {
     using namespace sedk;
+    SEDK_PROF("logmel", (cudaStream_t)stream);
     SEDK_REQUIRE(wave && tab && out, "sedk_logmel_fwd: null pointer");
     SEDK_REQUIRE(B > 0, "sedk_logmel_fwd: B must be positive (got %d)", B);
     SEDK_REQUIRE(L > kHalf, "sedk_logmel_fwd: reflect padding needs L > %d samples (got %d)", kHalf, L);

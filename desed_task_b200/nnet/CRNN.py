@@ -286,6 +286,7 @@ class CRNN(nn.Module):
         self.embedding_size = embedding_size
         self._ws = {}
         self._fwd_count = 0
+        self.seed_dev = None            # optional device uint64 counter added to the dropout seed (CUDA-graph replays)
 
     # ------------------------------------------------------------------------------------------------------------
     def _unsupported(self):
@@ -376,6 +377,7 @@ class CRNN(nn.Module):
         plan.training = 1 if training else 0
         plan.precision = self._precision()
         plan.seed = seed
+        plan.seed_dev = _vp(getattr(self, "seed_dev", None))
         plan.dropout_p = float(self.dropout.p)
         plan.x = _vp(x)
         plan.x_sb, plan.x_sm, plan.x_st = x.stride(0), x.stride(1), x.stride(2)

@@ -39,6 +39,12 @@ SEDK_API const char* sedk_last_error(void);
 SEDK_API int sedk_version(void);
 /* compute capability of the current device as major*10+minor (100 on B200); <0 on error */
 SEDK_API int sedk_device_cc(void);
+/* number of kernels this library has launched (or captured into a CUDA graph) so far in this process */
+SEDK_API long long sedk_launch_count(void);
+/* Optional eager-mode kernel timing: between sedk_profile_enable(1) and sedk_profile_report every launcher is bracketed by
+ * CUDA events on its stream; the report is text, one line per kernel family: "<name> <launches> <total_ms>". */
+SEDK_API int sedk_profile_enable(int on);
+SEDK_API int sedk_profile_report(char* buf, int buflen);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Front end: waveform -> (log-)mel.  Replaces torchaudio MelSpectrogram + AmplitudeToDB as built at
@@ -238,6 +244,11 @@ SEDK_API int sedk_sizeof_crnn_plan(void);
 SEDK_API int sedk_sed_loss(const float* strong, const float* weak, const float* t_strong, const float* t_weak,
                   const float* labels, const float* labels_weak, int B, int C, int T, int n_strong, int n_weak,
                   float cons_weight, float* losses, float* gstrong, float* gweak, void* stream);
+
+/* Same, with the consistency weight read from device memory (CUDA-graph replay with a new ramp value each step). */
+SEDK_API int sedk_sed_loss_dev(const float* strong, const float* weak, const float* t_strong, const float* t_weak,
+                      const float* labels, const float* labels_weak, int B, int C, int T, int n_strong, int n_weak,
+                      const float* cons_weight_dev, float* losses, float* gstrong, float* gweak, void* stream);
 
 /* plain GEMM building block (TF32 / 3xTF32 mma): C[M,N] = alpha*op(A)op(B) + beta*C + bias[n]
  * transA 0: A is [M,K] (lda), 1: A is [K,M];  transB 0: B is [K,N] (ldb), 1: B is [N,K]. */

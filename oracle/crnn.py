@@ -94,6 +94,27 @@ def span_mask(n, start, end, device=None):
     return (idx >= start[:, None]) & (idx < end[:, None])
 
 
+def draw_specaugment(B, n_f, n_t, f_l=10, f_p=0.2, t_l=5, t_p=0.2, device=None):
+    """Draw the mask spans exactly like CRNN.apply_specaugment (CRNN.py:207-219) does through torchaudio
+    functional.py:857-869: per mask value = rand(B) * param, min_value = rand(B) * (size - value); the 'freq' mask
+    is drawn first.  param = l if p == 1 else min(l, int(size * p))."""
+    def one(size, l, p):
+        param = l if p == 1.0 else min(l, int(size * p))
+        if param < 1:
+            return None
+        value = torch.rand(B, device=device) * param
+        min_value = torch.rand(B, device=device) * (size - value)
+        return min_value.long(), min_value.long() + value.long()
+    spec = {}
+    f = one(n_f, f_l, f_p)
+    if f is not None:
+        spec["f_start"], spec["f_end"] = f
+    t = one(n_t, t_l, t_p)
+    if t is not None:
+        spec["t_start"], spec["t_end"] = t
+    return spec
+
+
 def apply_specaugment(x, spec):
     """CRNN.py:207-219: 'freq' mask (TimeMasking on the transposed tensor) then time mask, fill 0.0.
     spec = dict(f_start, f_end, t_start, t_end) int64 [B] (already drawn)."""

@@ -184,7 +184,7 @@ def main():
     xa_ref = net.apply_specaugment(x.clone())
     torch.manual_seed(123)
     torch.randn(4, 128, 626)
-    spec = otr_draw_spec(4, 128, 626)
+    spec = ocrnn.draw_specaugment(4, 128, 626)
     xa_or = ocrnn.apply_specaugment(x.clone(), spec)
     assert torch.equal(xa_ref, xa_or), "specaugment restatement differs"
     report["specaugment"] = "oracle draw+mask == CRNN.apply_specaugment under the same torch seed"
@@ -263,26 +263,6 @@ def main():
                 "its components (mixup, scaler, CRNN, BCELoss/MSELoss, warm-up, Adam) are each pinned above.\n")
     for k, v in report.items():
         print(k, "->", v)
-
-
-def otr_draw_spec(B, n_f, n_t, f_l=10, f_p=0.2, t_l=5, t_p=0.2):
-    """Restates the draw order of CRNN.apply_specaugment (CRNN.py:207-219) through
-    torchaudio functional.py:857-869: per mask, value=rand(B)*param; min_value=rand(B)*(size-value)."""
-    def one(size, l, p):
-        param = l if p == 1.0 else min(l, int(size * p))
-        if param < 1:
-            return None
-        value = torch.rand(B) * param
-        min_value = torch.rand(B) * (size - value)
-        return min_value.long(), min_value.long() + value.long()
-    spec = {}
-    f = one(n_f, f_l, f_p)
-    if f is not None:
-        spec["f_start"], spec["f_end"] = f
-    t = one(n_t, t_l, t_p)
-    if t is not None:
-        spec["t_start"], spec["t_end"] = t
-    return spec
 
 
 if __name__ == "__main__":
