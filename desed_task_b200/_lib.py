@@ -56,7 +56,7 @@ class CrnnPlan(C.Structure):
                 ("gcat_w", vp), ("gcat_b", vp), ("cat_in", vp), ("fused", vp), ("gfused", vp), ("dropstep", vp),
                 ("dense_w", vp), ("dense_b", vp), ("soft_w", vp), ("soft_b", vp),
                 ("gdense_w", vp), ("gdense_b", vp), ("gsoft_w", vp), ("gsoft_b", vp),
-                ("classes_mask", vp), ("rnn_drop", vp), ("grnn_drop", vp), ("strong", vp), ("weak", vp), ("sof", vp),
+                ("classes_mask", vp), ("rnn_drop", vp), ("grnn_drop", vp), ("strong", vp), ("weak", vp), ("sof", vp), ("hsum", vp),
                 ("gstrong", vp), ("gweak", vp)]
 
 

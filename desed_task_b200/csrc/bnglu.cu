@@ -57,14 +57,15 @@ struct GluCfg {
 
 struct TileGeom {
     int T, F, Te, Fe, pt, pf, TT, TF, nTt, nTf, To, Fo;
+    int tf_shift, otw_shift;      // log2(TF), log2(TF / pf): tile sides are powers of two
 };
 
-__device__ __forceinline__ void philox_pair(const Philox& ph, uint64_t e, uint64_t stream, uint32_t thresh, bool& k0,
-                                            bool& k1) {
-    // e is even: elements e and e+1 live in the same 4-wide Philox block
-    uint4 r = ph(e >> 2, stream);
-    if (e & 2) { k0 = r.z >= thresh; k1 = r.w >= thresh; }
-    else       { k0 = r.x >= thresh; k1 = r.y >= thresh; }
+// Dropout keep-flags of the 4 elements a thread owns in one pair of adjacent n-fragments (columns n0+2t, n0+2t+1 of
+// fragment 2q and of fragment 2q+1) of pixel `pix`: one Philox call serves all four.  The element -> random mapping only has
+// to agree between the forward and the backward kernel of the same layer, which share this tiling.
+__device__ __forceinline__ uint4 philox_frag_pair(const Philox& ph, uint64_t pix, int pairs_per_pixel, int pair, int t4,
+                                                  uint64_t stream) {
+    return ph((pix * (uint64_t)pairs_per_pixel + (uint64_t)pair) * 4ull + (uint64_t)t4, stream);
 }
 
 template <int C, bool X3>
@@ -101,7 +102,7 @@ bnglu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
         const int t0 = (r / gm.nTf) * TT, f0 = (r % gm.nTf) * TF;
         for (int idx = tid; idx < 128 * (C / 4); idx += 256) {
             int p = idx / (C / 4), q = idx - p * (C / 4);
-            int ty = p / TF, tx = p - ty * TF;
+            int ty = p >> gm.tf_shift, tx = p & (TF - 1);
             int t = t0 + ty, f = f0 + tx;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (t < gm.Te && f < gm.Fe) {
@@ -133,8 +134,9 @@ bnglu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
 #pragma unroll
             for (int rr = 0; rr < 2; rr++) {
                 const int m = wm0 + i * 16 + g + 8 * rr;
-                const int ty = m / TF, tx = m - ty * TF;
+                const int ty = m >> gm.tf_shift, tx = m & (TF - 1);
                 const size_t pix = ((size_t)b * gm.T + (t0 + ty)) * gm.F + (f0 + tx);
+                uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int j = 0; j < NF; j++) {
                     const int n = wn0 + j * 8 + 2 * t4;
@@ -142,8 +144,8 @@ bnglu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
                     float a0 = (acc[i][j][2 * rr] + vec[2 * C + n]) * sigmoidf_(y.x);
                     float a1 = (acc[i][j][2 * rr + 1] + vec[2 * C + n + 1]) * sigmoidf_(y.y);
                     if (thresh != 0u) {
-                        bool k0, k1;
-                        philox_pair(ph, (uint64_t)pix * C + n, dstream, thresh, k0, k1);
+                        if ((j & 1) == 0) rnd = philox_frag_pair(ph, pix, C / 16, (wn0 >> 4) + (j >> 1), t4, dstream);
+                        const bool k0 = ((j & 1) ? rnd.z : rnd.x) >= thresh, k1 = ((j & 1) ? rnd.w : rnd.y) >= thresh;
                         a0 = k0 ? a0 * inv_keep : 0.f;
                         a1 = k1 ? a1 * inv_keep : 0.f;
                     }
@@ -154,7 +156,7 @@ bnglu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
         const int otw = TF / gm.pf, oth = TT / gm.pt;
         for (int idx = tid; idx < oth * otw * (C / 4); idx += 256) {
             int op = idx / (C / 4), q = idx - op * (C / 4);
-            int oy = op / otw, ox = op - oy * otw;
+            int oy = op >> gm.otw_shift, ox = op & (otw - 1);
             int to = t0 / gm.pt + oy, fo = f0 / gm.pf + ox;
             if (to < gm.To && fo < gm.Fo) {
                 float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -222,7 +224,7 @@ bnglu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
         const int t0 = (r / gm.nTf) * TT, f0 = (r % gm.nTf) * TF;
         for (int idx = tid; idx < 128 * (C / 4); idx += 256) {
             int p = idx / (C / 4), q = idx - p * (C / 4);
-            int ty = p / TF, tx = p - ty * TF;
+            int ty = p >> gm.tf_shift, tx = p & (TF - 1);
             int t = t0 + ty, f = f0 + tx;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (t < gm.Te && f < gm.Fe) {
@@ -258,11 +260,12 @@ bnglu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
 #pragma unroll
             for (int rr = 0; rr < 2; rr++) {
                 const int m = wm0 + i * 16 + g + 8 * rr;
-                const int ty = m / TF, tx = m - ty * TF;
+                const int ty = m >> gm.tf_shift, tx = m & (TF - 1);
                 const int t = t0 + ty, f = f0 + tx;
                 const bool valid = (t < gm.Te) && (f < gm.Fe);
                 const size_t pix = ((size_t)b * gm.T + t) * gm.F + f;
-                const float* gop = gout + (((size_t)b * gm.To + t / gm.pt) * gm.Fo + f / gm.pf) * C;
+                const float* gop = gout + (((size_t)b * gm.To + (t >> (gm.pt - 1))) * gm.Fo + (f >> (gm.pf - 1))) * C;
+                uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int j = 0; j < NF; j++) {
                     const int n = wn0 + j * 8 + 2 * t4;
@@ -272,8 +275,8 @@ bnglu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
                         ga0 = go.x * inv_pool;
                         ga1 = go.y * inv_pool;
                         if (thresh != 0u) {
-                            bool k0, k1;
-                            philox_pair(ph, (uint64_t)pix * C + n, dstream, thresh, k0, k1);
+                            if ((j & 1) == 0) rnd = philox_frag_pair(ph, pix, C / 16, (wn0 >> 4) + (j >> 1), t4, dstream);
+                            const bool k0 = ((j & 1) ? rnd.z : rnd.x) >= thresh, k1 = ((j & 1) ? rnd.w : rnd.y) >= thresh;
                             ga0 = k0 ? ga0 * inv_keep : 0.f;
                             ga1 = k1 ? ga1 * inv_keep : 0.f;
                         }
@@ -322,7 +325,7 @@ bnglu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
 #pragma unroll
             for (int rr = 0; rr < 2; rr++) {
                 const int m = wm0 + i * 16 + g + 8 * rr;
-                const int ty = m / TF, tx = m - ty * TF;
+                const int ty = m >> gm.tf_shift, tx = m & (TF - 1);
                 const int t = t0 + ty, f = f0 + tx;
                 if (t < gm.Te && f < gm.Fe) {
                     const size_t pix = ((size_t)b * gm.T + t) * gm.F + f;
@@ -421,6 +424,10 @@ inline TileGeom make_geom(int T, int F, int pt, int pf) {
     else { g.TT = 64; g.TF = 2; }
     g.nTt = cdiv(g.Te, g.TT);
     g.nTf = cdiv(g.Fe, g.TF);
+    g.tf_shift = 0;
+    while ((1 << g.tf_shift) < g.TF) g.tf_shift++;
+    g.otw_shift = 0;
+    while ((1 << g.otw_shift) < g.TF / g.pf) g.otw_shift++;
     return g;
 }
 

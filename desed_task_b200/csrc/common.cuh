@@ -215,7 +215,8 @@ __device__ __forceinline__ void warp_mma_k8(float (&acc)[MF][NF][4], FA fa, FB f
 }
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 counter RNG (dropout masks are regenerated in backward from (seed, stream, index))
+// Philox4x32-7 counter RNG (the 7-round variant of Salmon et al., which still passes BigCrush; dropout masks are
+// regenerated in backward from (seed, stream, index) instead of being stored)
 struct Philox {
     uint32_t key0, key1;
     __device__ __forceinline__ Philox(uint64_t seed) : key0((uint32_t)seed), key1((uint32_t)(seed >> 32)) {}
@@ -223,7 +224,7 @@ struct Philox {
         uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32), c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
         uint32_t k0 = key0, k1 = key1;
 #pragma unroll
-        for (int r = 0; r < 10; r++) {
+        for (int r = 0; r < 7; r++) {
             uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
             uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
             uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;

@@ -18,7 +18,7 @@ int validate(const sedk_crnn_plan* p, bool backward) {
     SEDK_REQUIRE(p != nullptr, "crnn: null plan");
     SEDK_REQUIRE(p->B > 0 && p->n_conv >= 1 && p->n_conv <= SEDK_MAX_CONV, "crnn: bad B / n_conv");
     SEDK_REQUIRE(p->n_gru >= 1 && p->n_gru <= SEDK_MAX_GRU_LAYERS, "crnn: bad n_gru");
-    SEDK_REQUIRE(p->x && p->strong && p->weak && p->sof, "crnn: missing input / output buffers");
+    SEDK_REQUIRE(p->x && p->strong && p->weak && p->sof && p->hsum, "crnn: missing input / output buffers");
     SEDK_REQUIRE(p->conv[0].cin == 1, "crnn: the first conv layer must have one input channel (n_in_channel=1)");
     SEDK_REQUIRE(p->conv[0].T == p->n_frames && p->conv[0].F == p->n_mels, "crnn: layer-0 geometry mismatch");
     for (int i = 0; i < p->n_conv; i++) {
@@ -104,10 +104,15 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
         const sedk_gru_layer& G = p->gru[l];
         SEDK_REQUIRE(G.in_dim == in_dim, "crnn: GRU layer %d expects %d inputs, gets %d", l, G.in_dim, in_dim);
         const int H = G.hidden;
-        for (int d = 0; d < 2; d++) {
+        for (int d = 0; d < 2; d++)
             SEDK_REQUIRE(G.w_ih[d] && G.w_hh[d] && G.b_ih[d] && G.b_hh[d] && G.gi[d], "crnn: GRU layer %d null", l);
-            rc = launch_gemm(0, 1, B * Tp, 3 * H, in_dim, 1.f, xr, in_dim, G.w_ih[d], in_dim, 0.f, G.gi[d], 3 * H,
-                             G.b_ih[d], p->precision, s);
+        {
+            const float* As[2] = {xr, xr};
+            const float* Bs[2] = {G.w_ih[0], G.w_ih[1]};
+            float* Cs[2] = {G.gi[0], G.gi[1]};
+            const float* bs[2] = {G.b_ih[0], G.b_ih[1]};
+            rc = launch_gemm_batched(0, 1, B * Tp, 3 * H, in_dim, 1.f, As, in_dim, Bs, in_dim, 0.f, Cs, 3 * H, bs, 2,
+                                     p->precision, s);
             if (rc) return rc;
         }
         SEDK_REQUIRE(G.out && (!p->training || (G.gates[0] && G.gates[1] && G.hprev[0] && G.hprev[1])),
@@ -126,7 +131,7 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
         hx = p->rnn_drop;
     }
     return launch_heads_fwd(hx, p->dense_w, p->dense_b, p->soft_w, p->soft_b, p->classes_mask, p->strong, p->weak,
-                            p->sof, B, Tp, in_dim, p->nclass, s);
+                            p->sof, p->hsum, B, Tp, in_dim, p->nclass, s);
 }
 
 extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
@@ -148,7 +153,7 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
     SEDK_CUDA(cudaMemsetAsync(p->gsoft_b, 0, (size_t)C * sizeof(float), s));
     const float* hx = pdrop > 0.f ? p->rnn_drop : p->gru[p->n_gru - 1].out;
     float* ghx = pdrop > 0.f ? p->grnn_drop : p->gru[p->n_gru - 1].gout;
-    rc = launch_heads_bwd(hx, p->dense_w, p->soft_w, p->classes_mask, p->strong, p->weak, p->sof, p->gstrong, p->gweak,
+    rc = launch_heads_bwd(hx, p->dense_w, p->soft_w, p->classes_mask, p->strong, p->hsum, p->sof, p->gstrong, p->gweak,
                           ghx, p->gdense_w, p->gdense_b, p->gsoft_w, p->gsoft_b, B, Tp, D, C, s);
     if (rc) return rc;
     if (pdrop > 0.f) {
@@ -169,17 +174,25 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
             SEDK_REQUIRE(G.gw_ih[d] && G.gw_hh[d] && G.gb_ih[d] && G.gb_hh[d], "crnn backward: GRU grads null");
             SEDK_CUDA(cudaMemsetAsync(G.gw_ih[d], 0, (size_t)3 * H * in_dim * sizeof(float), s));
             SEDK_CUDA(cudaMemsetAsync(G.gw_hh[d], 0, (size_t)3 * H * H * sizeof(float), s));
-            // dW_ih = dgi^T x
-            rc = launch_gemm(1, 0, 3 * H, in_dim, BT, 1.f, G.gi[d], 3 * H, xin, in_dim, 1.f, G.gw_ih[d], in_dim, nullptr,
-                             p->precision, s);
+        }
+        {
+            // dW_ih = dgi^T x ; dW_hh rows [0,2H) from (dr, dz), rows [2H,3H) from d(hn) - both directions per launch
+            const float* dgi[2] = {G.gi[0], G.gi[1]};
+            const float* xs[2] = {xin, xin};
+            float* gwih[2] = {G.gw_ih[0], G.gw_ih[1]};
+            rc = launch_gemm_batched(1, 0, 3 * H, in_dim, BT, 1.f, dgi, 3 * H, xs, in_dim, 1.f, gwih, in_dim, nullptr, 2,
+                                     p->precision, s);
             if (rc) return rc;
-            // dW_hh rows [0,2H) from (dr, dz), rows [2H,3H) from d(hn)
-            rc = launch_gemm(1, 0, 2 * H, H, BT, 1.f, G.gi[d], 3 * H, G.hprev[d], H, 1.f, G.gw_hh[d], H, nullptr,
-                             p->precision, s);
+            const float* hp[2] = {G.hprev[0], G.hprev[1]};
+            float* gwhh[2] = {G.gw_hh[0], G.gw_hh[1]};
+            rc = launch_gemm_batched(1, 0, 2 * H, H, BT, 1.f, dgi, 3 * H, hp, H, 1.f, gwhh, H, nullptr, 2, p->precision, s);
             if (rc) return rc;
-            rc = launch_gemm(1, 0, H, H, BT, 1.f, G.dghn[d], H, G.hprev[d], H, 1.f, G.gw_hh[d] + (size_t)2 * H * H, H,
-                             nullptr, p->precision, s);
+            const float* dhn[2] = {G.dghn[0], G.dghn[1]};
+            float* gwhn[2] = {G.gw_hh[0] + (size_t)2 * H * H, G.gw_hh[1] + (size_t)2 * H * H};
+            rc = launch_gemm_batched(1, 0, H, H, BT, 1.f, dhn, H, hp, H, 1.f, gwhn, H, nullptr, 2, p->precision, s);
             if (rc) return rc;
+        }
+        for (int d = 0; d < 2; d++) {
             rc = launch_colsum(G.gi[d], BT, 3 * H, 3 * H, G.gb_ih[d], 0, s);
             if (rc) return rc;
             rc = launch_colsum(G.gi[d], BT, 2 * H, 3 * H, G.gb_hh[d], 0, s);

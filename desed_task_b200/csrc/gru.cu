@@ -20,6 +20,23 @@ namespace {
 
 constexpr int SEG = 64;
 
+// fast, accurate-enough gate nonlinearities (MUFU.EX2 based: abs error ~1e-7, far inside the 1e-3 posterior budget)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
+// dot product of 64 register-resident weights with 64 shared-memory values using packed FP32 FMA (FFMA2, sm_100+)
+__device__ __forceinline__ float dot64_ffma2(const float2 (&w)[SEG / 2], const float* __restrict__ v) {
+    const float4* v4 = reinterpret_cast<const float4*>(v);
+    float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k4 = 0; k4 < SEG / 4; k4++) {
+        const float4 hh = v4[k4];
+        a0 = __ffma2_rn(w[2 * k4], make_float2(hh.x, hh.y), a0);
+        a1 = __ffma2_rn(w[2 * k4 + 1], make_float2(hh.z, hh.w), a1);
+    }
+    return (a0.x + a0.y) + (a1.x + a1.y);
+}
+
 template <int H, int CS>
 struct GruCfg {
     static constexpr int HU = H / CS;             // hidden units owned by one CTA
@@ -64,9 +81,10 @@ gru_fwd_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, con
     const int seg = tid / R, row = tid - seg * R;           // row in [0, R): gate = row / HU, unit = row % HU
     const int gate = row / HU, unit = row - gate * HU;
     const int grow = gate * H + u0 + unit;                  // row of W_hh [3H, H]
-    float w[SEG];
+    float2 w[SEG / 2];
 #pragma unroll
-    for (int k = 0; k < SEG; k++) w[k] = whh[(size_t)grow * H + seg * SEG + k];
+    for (int k = 0; k < SEG / 2; k++)
+        w[k] = *reinterpret_cast<const float2*>(whh + (size_t)grow * H + seg * SEG + 2 * k);
 
     for (int i = tid; i < 2 * NB * H; i += NT) (&h_s[0][0][0])[i] = 0.f;
     const bool is_gate = tid < NB * HU;
@@ -82,29 +100,26 @@ gru_fwd_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, con
     if (CS > 1) cg::this_cluster().sync(); else __syncthreads();
 
     int cur = 0;
+    // the gi row of step s+1 is fetched while step s computes (the only global read on the dependency chain)
+    float gir = 0.f, giz = 0.f, gin = 0.f;
+    if (active) {
+        const float* gp = gi + ((size_t)bglob * T + (dir ? T - 1 : 0)) * 3 * H + u0 + gu;
+        gir = gp[0];
+        giz = gp[H];
+        gin = gp[2 * H];
+    }
     for (int step = 0; step < T; step++) {
         const int t = dir ? (T - 1 - step) : step;
-        float gir = 0.f, giz = 0.f, gin = 0.f;
-        if (active) {
-            const float* gp = gi + ((size_t)bglob * T + t) * 3 * H + u0 + gu;
-            gir = gp[0];
-            giz = gp[H];
-            gin = gp[2 * H];
+        float nir = 0.f, niz = 0.f, nin = 0.f;
+        if (active && step + 1 < T) {
+            const int tn = dir ? (T - 2 - step) : step + 1;
+            const float* gp = gi + ((size_t)bglob * T + tn) * 3 * H + u0 + gu;
+            nir = gp[0];
+            niz = gp[H];
+            nin = gp[2 * H];
         }
 #pragma unroll
-        for (int nb = 0; nb < NB; nb++) {
-            const float4* hv = reinterpret_cast<const float4*>(&h_s[cur][nb][seg * SEG]);
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int k4 = 0; k4 < SEG / 4; k4++) {
-                float4 hh = hv[k4];
-                a0 = fmaf(w[4 * k4], hh.x, a0);
-                a1 = fmaf(w[4 * k4 + 1], hh.y, a1);
-                a0 = fmaf(w[4 * k4 + 2], hh.z, a0);
-                a1 = fmaf(w[4 * k4 + 3], hh.w, a1);
-            }
-            part[seg][nb][row] = a0 + a1;
-        }
+        for (int nb = 0; nb < NB; nb++) part[seg][nb][row] = dot64_ffma2(w, &h_s[cur][nb][seg * SEG]);
         __syncthreads();
         const int nxt = CS > 1 ? cur ^ 1 : cur;
         if (is_gate) {
@@ -115,9 +130,9 @@ gru_fwd_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, con
                 ghz += part[s][gb][HU + gu];
                 ghn += part[s][gb][2 * HU + gu];
             }
-            const float r = sigmoidf_(gir + ghr);
-            const float zg = sigmoidf_(giz + ghz);
-            const float n = tanhf(gin + r * ghn);
+            const float r = fast_sigmoid(gir + ghr);
+            const float zg = fast_sigmoid(giz + ghz);
+            const float n = fast_tanh(gin + r * ghn);
             const float hnew = (1.0f - zg) * n + zg * hval;
             if (active) {
                 const size_t bt = (size_t)bglob * T + t;
@@ -145,6 +160,9 @@ gru_fwd_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, con
         }
         if (CS > 1) cg::this_cluster().sync(); else __syncthreads();
         cur = nxt;
+        gir = nir;
+        giz = niz;
+        gin = nin;
     }
 }
 
@@ -172,9 +190,11 @@ gru_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ whh0, c
     float* dghn = dir ? dghn1 : dghn0;
 
     const int jseg = tid / HU, col = tid - jseg * HU;        // column u0+col of W_hh, rows jseg*64 .. +64
-    float w[SEG];
+    float2 w[SEG / 2];
 #pragma unroll
-    for (int k = 0; k < SEG; k++) w[k] = whh[(size_t)(jseg * SEG + k) * H + u0 + col];
+    for (int k = 0; k < SEG / 2; k++)
+        w[k] = make_float2(whh[(size_t)(jseg * SEG + 2 * k) * H + u0 + col],
+                           whh[(size_t)(jseg * SEG + 2 * k + 1) * H + u0 + col]);
 
     for (int i = tid; i < 2 * NB * 3 * H; i += NT) (&dgh_s[0][0][0])[i] = 0.f;
     const bool is_gate = tid < NB * HU;
@@ -185,15 +205,32 @@ gru_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ whh0, c
     if (CS > 1) cg::this_cluster().sync(); else __syncthreads();
 
     int cur = 0;
+    // saved activations of the next processed step are prefetched one step ahead
+    float p_go = 0.f, p_r = 0.f, p_z = 0.f, p_n = 0.f, p_ghn = 0.f, p_hp = 0.f;
+    if (active) {
+        const size_t bt = (size_t)bglob * T + (dir ? 0 : T - 1);
+        p_go = gout[bt * 2 * H + dir * H + u0 + gu];
+        const float* gs = gates + bt * 4 * H + u0 + gu;
+        p_r = gs[0]; p_z = gs[H]; p_n = gs[2 * H]; p_ghn = gs[3 * H];
+        p_hp = hprev[bt * H + u0 + gu];
+    }
     for (int step = T - 1; step >= 0; step--) {
         const int t = dir ? (T - 1 - step) : step;
+        float n_go = 0.f, n_r = 0.f, n_z = 0.f, n_n = 0.f, n_ghn = 0.f, n_hp = 0.f;
+        if (active && step > 0) {
+            const int tn = dir ? (T - step) : step - 1;
+            const size_t btn = (size_t)bglob * T + tn;
+            n_go = gout[btn * 2 * H + dir * H + u0 + gu];
+            const float* gs = gates + btn * 4 * H + u0 + gu;
+            n_r = gs[0]; n_z = gs[H]; n_n = gs[2 * H]; n_ghn = gs[3 * H];
+            n_hp = hprev[btn * H + u0 + gu];
+        }
         float dh_direct = 0.f, dr_pre = 0.f, dz_pre = 0.f, dn_pre = 0.f, dhn = 0.f;
         if (active) {
             const size_t bt = (size_t)bglob * T + t;
-            const float g = gout[bt * 2 * H + dir * H + u0 + gu] + dh;
-            const float* gs = gates + bt * 4 * H + u0 + gu;
-            const float r = gs[0], zg = gs[H], n = gs[2 * H], ghn = gs[3 * H];
-            const float hp = hprev[bt * H + u0 + gu];
+            const float g = p_go + dh;
+            const float r = p_r, zg = p_z, n = p_n, ghn = p_ghn;
+            const float hp = p_hp;
             const float dn = g * (1.0f - zg);
             const float dz = g * (hp - n);
             dh_direct = g * zg;
@@ -226,19 +263,7 @@ gru_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ whh0, c
         if (CS > 1) cg::this_cluster().sync(); else __syncthreads();
         // dh_prev[u] += sum_j W_hh[j][u] * dgh[j]
 #pragma unroll
-        for (int nb = 0; nb < NB; nb++) {
-            const float4* dv = reinterpret_cast<const float4*>(&dgh_s[cur][nb][jseg * SEG]);
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int k4 = 0; k4 < SEG / 4; k4++) {
-                float4 d = dv[k4];
-                a0 = fmaf(w[4 * k4], d.x, a0);
-                a1 = fmaf(w[4 * k4 + 1], d.y, a1);
-                a0 = fmaf(w[4 * k4 + 2], d.z, a0);
-                a1 = fmaf(w[4 * k4 + 3], d.w, a1);
-            }
-            part[jseg][nb][col] = a0 + a1;
-        }
+        for (int nb = 0; nb < NB; nb++) part[jseg][nb][col] = dot64_ffma2(w, &dgh_s[cur][nb][jseg * SEG]);
         __syncthreads();
         if (is_gate) {
             float s = dh_direct;
@@ -246,6 +271,7 @@ gru_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ whh0, c
             for (int js = 0; js < JSEGS; js++) s += part[js][gb][gu];
             dh = s;
         }
+        p_go = n_go; p_r = n_r; p_z = n_z; p_n = n_n; p_ghn = n_ghn; p_hp = n_hp;
         if (CS > 1) cur ^= 1;      // next step's remote writes must not race with slower CTAs still reading
     }
 }

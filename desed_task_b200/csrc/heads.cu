@@ -10,128 +10,126 @@ namespace {
 constexpr int HC_MAX = 32;     // classes
 constexpr int HT = 32;         // time steps per chunk
 
-// one CTA per clip
+// grid (time chunks of HT steps, clips).  hsum[b][0][c] += sum_t s*a, hsum[b][1][c] += sum_t a (zeroed by the launcher)
 __global__ void __launch_bounds__(256)
 heads_fwd_kernel(const float* __restrict__ x, const float* __restrict__ dw, const float* __restrict__ db,
                  const float* __restrict__ sw, const float* __restrict__ sb, const uint8_t* __restrict__ cmask,
-                 float* __restrict__ strong, float* __restrict__ weak, float* __restrict__ sof, int T, int D, int C) {
+                 float* __restrict__ strong, float* __restrict__ hsum, float* __restrict__ sof, int T, int D, int C) {
     extern __shared__ float smem[];
     const int DS = D + 1;
     float* Wd = smem;                    // [C][DS]
     float* Ws = Wd + C * DS;             // [C][DS]
     float* xs = Ws + C * DS;             // [HT][DS]
     float* lg = xs + HT * DS;            // [HT][2*HC_MAX]
-    float* num = lg + HT * 2 * HC_MAX;   // [HC_MAX]
-    float* den = num + HC_MAX;           // [HC_MAX]
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int tc = blockIdx.x * HT;
+    const int nt = min(HT, T - tc);
     for (int i = tid; i < C * D; i += 256) {
         int c = i / D, k = i - c * D;
         Wd[c * DS + k] = dw[i];
         Ws[c * DS + k] = sw[i];
     }
-    if (tid < HC_MAX) num[tid] = den[tid] = 0.f;
     const float* xb = x + (size_t)b * T * D;
+    for (int i = tid; i < nt * D; i += 256) {
+        int r = i / D, k = i - r * D;
+        xs[r * DS + k] = xb[(size_t)(tc + r) * D + k];
+    }
+    __syncthreads();
     const int tl = tid >> 3, cg8 = tid & 7;
-    for (int tc = 0; tc < T; tc += HT) {
-        const int nt = min(HT, T - tc);
-        __syncthreads();
-        for (int i = tid; i < nt * D; i += 256) {
-            int r = i / D, k = i - r * D;
-            xs[r * DS + k] = xb[(size_t)(tc + r) * D + k];
-        }
-        __syncthreads();
-        if (tl < nt) {
-            float ad[4] = {0.f, 0.f, 0.f, 0.f}, as[4] = {0.f, 0.f, 0.f, 0.f};
-            const float* xr = xs + tl * DS;
-            for (int k = 0; k < D; k++) {
-                const float xv = xr[k];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int c = cg8 + 8 * q;
-                    if (c < C) {
-                        ad[q] = fmaf(xv, Wd[c * DS + k], ad[q]);
-                        as[q] = fmaf(xv, Ws[c * DS + k], as[q]);
-                    }
-                }
-            }
+    if (tl < nt) {
+        float ad[4] = {0.f, 0.f, 0.f, 0.f}, as[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* xr = xs + tl * DS;
+        for (int k = 0; k < D; k++) {
+            const float xv = xr[k];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int c = cg8 + 8 * q;
                 if (c < C) {
-                    lg[tl * 2 * HC_MAX + c] = ad[q] + db[c];
-                    lg[tl * 2 * HC_MAX + HC_MAX + c] = as[q] + sb[c];
+                    ad[q] = fmaf(xv, Wd[c * DS + k], ad[q]);
+                    as[q] = fmaf(xv, Ws[c * DS + k], as[q]);
                 }
             }
         }
-        __syncthreads();
-        if (tid < nt) {
-            const int t = tc + tid;
-            const float* l = lg + tid * 2 * HC_MAX;
-            float mx = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int c = cg8 + 8 * q;
+            if (c < C) {
+                lg[tl * 2 * HC_MAX + c] = ad[q] + db[c];
+                lg[tl * 2 * HC_MAX + HC_MAX + c] = as[q] + sb[c];
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {                                      // warp 0: one lane per time step
+        const bool live = tid < nt;
+        const int t = tc + tid;
+        const float* l = lg + tid * 2 * HC_MAX;
+        float mx = -INFINITY, ssum = 0.f;
+        if (live) {
             for (int c = 0; c < C; c++) {
                 float v = l[HC_MAX + c];
                 if (cmask && !cmask[b * C + c]) v = -1e30f;
                 mx = fmaxf(mx, v);
             }
-            float ssum = 0.f;
             for (int c = 0; c < C; c++) {
                 float v = l[HC_MAX + c];
                 if (cmask && !cmask[b * C + c]) v = -1e30f;
                 ssum += expf(v - mx);
             }
-            for (int c = 0; c < C; c++) {
+        }
+        for (int c = 0; c < C; c++) {
+            float sa = 0.f, a = 0.f;
+            if (live) {
                 const bool ok = !cmask || cmask[b * C + c];
-                float v = ok ? l[HC_MAX + c] : -1e30f;
+                const float v = ok ? l[HC_MAX + c] : -1e30f;
                 const float p = expf(v - mx) / ssum;
-                const float a = fminf(fmaxf(p, 1e-7f), 1.0f);
-                const float s = sigmoidf_(l[c]);
+                a = fminf(fmaxf(p, 1e-7f), 1.0f);
+                const float sg = sigmoidf_(l[c]);
                 sof[((size_t)b * T + t) * C + c] = p;
-                strong[((size_t)b * C + c) * T + t] = ok ? s : 0.f;
-                atomicAdd(&num[c], s * a);
-                atomicAdd(&den[c], a);
+                strong[((size_t)b * C + c) * T + t] = ok ? sg : 0.f;
+                sa = sg * a;
+            }
+            sa = warp_sum(sa);
+            a = warp_sum(a);
+            if (tid == 0) {
+                atomicAdd(&hsum[(b * 2 + 0) * C + c], sa);
+                atomicAdd(&hsum[(b * 2 + 1) * C + c], a);
             }
         }
     }
-    __syncthreads();
-    if (tid < C) {
-        const bool ok = !cmask || cmask[b * C + tid];
-        weak[b * C + tid] = ok ? num[tid] / den[tid] : 0.f;
-    }
 }
 
-// one CTA per clip; gl = grads wrt the two logit sets
+__global__ void heads_weak_kernel(const float* __restrict__ hsum, const uint8_t* __restrict__ cmask,
+                                  float* __restrict__ weak, int B, int C) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * C) return;
+    int b = i / C, c = i - b * C;
+    const bool ok = !cmask || cmask[i];
+    weak[i] = ok ? hsum[(b * 2) * C + c] / hsum[(b * 2 + 1) * C + c] : 0.f;
+}
+
+// grid (time chunks, clips); gl = grads wrt the two logit sets of this chunk
 __global__ void __launch_bounds__(256)
 heads_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dw, const float* __restrict__ sw,
-                 const uint8_t* __restrict__ cmask, const float* __restrict__ strong, const float* __restrict__ weak,
+                 const uint8_t* __restrict__ cmask, const float* __restrict__ strong, const float* __restrict__ hsum,
                  const float* __restrict__ sof, const float* __restrict__ gstrong, const float* __restrict__ gweak,
                  float* __restrict__ gx, float* __restrict__ gdw, float* __restrict__ gdb, float* __restrict__ gsw,
                  float* __restrict__ gsb, int T, int D, int C) {
-    extern __shared__ float smem[];
-    float* gl = smem;                    // [T][2C]
-    float* den = gl + T * 2 * C;         // [C]
-    float* num = den + HC_MAX;           // [C]  (unmasked weak numerator)
-    const int b = blockIdx.x, tid = threadIdx.x;
-    if (tid < HC_MAX) den[tid] = num[tid] = 0.f;
-    __syncthreads();
-    // pass 1: D_c = sum_t a, N_c = sum_t s*a   (strong buffer is masked for invalid classes: their grads are 0 anyway)
-    for (int i = tid; i < T * C; i += 256) {
-        int t = i / C, c = i - t * C;
-        float p = sof[((size_t)b * T + t) * C + c];
-        float a = fminf(fmaxf(p, 1e-7f), 1.0f);
-        atomicAdd(&den[c], a);
-        atomicAdd(&num[c], strong[((size_t)b * C + c) * T + t] * a);
-    }
-    __syncthreads();
-    // pass 2: logit gradients, one thread per time step
-    for (int t = tid; t < T; t += 256) {
+    __shared__ float gl[HT][2 * HC_MAX];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int tc = blockIdx.x * HT;
+    const int nt = min(HT, T - tc);
+    if (tid < nt) {
+        const int t = tc + tid;
         float S = 0.f;
         for (int c = 0; c < C; c++) {
             const bool ok = !cmask || cmask[b * C + c];
             const float p = sof[((size_t)b * T + t) * C + c];
             const float s = strong[((size_t)b * C + c) * T + t];
             const float gw = (ok && gweak) ? gweak[b * C + c] : 0.f;
-            const float wk = num[c] / den[c];
-            const float ga = gw * (s - wk) / den[c];
+            const float den = hsum[(b * 2 + 1) * C + c];
+            const float wk = hsum[(b * 2) * C + c] / den;
+            const float ga = gw * (s - wk) / den;
             const float gp = (p >= 1e-7f && p <= 1.0f) ? ga : 0.f;
             S += gp * p;
         }
@@ -142,18 +140,18 @@ heads_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dw, cons
             const float s = strong[((size_t)b * C + c) * T + t];
             const float gw = (ok && gweak) ? gweak[b * C + c] : 0.f;
             const float gst = (ok && gstrong) ? gstrong[((size_t)b * C + c) * T + t] : 0.f;
-            const float wk = num[c] / den[c];
-            const float ga = gw * (s - wk) / den[c];
+            const float den = hsum[(b * 2 + 1) * C + c];
+            const float wk = hsum[(b * 2) * C + c] / den;
+            const float ga = gw * (s - wk) / den;
             const float gp = (p >= 1e-7f && p <= 1.0f) ? ga : 0.f;
-            const float gs = gst + gw * a / den[c];
-            gl[t * 2 * C + c] = gs * s * (1.0f - s);
-            gl[t * 2 * C + C + c] = p * (gp - S);
+            const float gs = gst + gw * a / den;
+            gl[tid][c] = gs * s * (1.0f - s);
+            gl[tid][HC_MAX + c] = p * (gp - S);
         }
     }
     __syncthreads();
-    // pass 3: gx[t,k] and the weight gradients, one thread per feature k
-    const float* xb = x + (size_t)b * T * D;
-    float* gxb = gx + (size_t)b * T * D;
+    const float* xb = x + ((size_t)b * T + tc) * D;
+    float* gxb = gx + ((size_t)b * T + tc) * D;
     for (int k = tid; k < D; k += 256) {
         float wd[HC_MAX], ws[HC_MAX], ad[HC_MAX], as[HC_MAX];
 #pragma unroll
@@ -162,14 +160,13 @@ heads_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dw, cons
             ws[c] = c < C ? sw[c * D + k] : 0.f;
             ad[c] = as[c] = 0.f;
         }
-        for (int t = 0; t < T; t++) {
+        for (int t = 0; t < nt; t++) {
             const float xv = xb[(size_t)t * D + k];
-            const float* g = gl + t * 2 * C;
             float acc = 0.f;
 #pragma unroll
             for (int c = 0; c < HC_MAX; c++) {
                 if (c < C) {
-                    const float g1 = g[c], g2 = g[C + c];
+                    const float g1 = gl[t][c], g2 = gl[t][HC_MAX + c];
                     acc = fmaf(g1, wd[c], acc);
                     acc = fmaf(g2, ws[c], acc);
                     ad[c] = fmaf(g1, xv, ad[c]);
@@ -187,10 +184,11 @@ heads_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dw, cons
         }
     }
     for (int c = tid; c < 2 * C; c += 256) {
-        float s = 0.f;
-        for (int t = 0; t < T; t++) s += gl[t * 2 * C + c];
-        if (c < C) atomicAdd(&gdb[c], s);
-        else atomicAdd(&gsb[c - C], s);
+        float sacc = 0.f;
+        const int col = c < C ? c : HC_MAX + (c - C);
+        for (int t = 0; t < nt; t++) sacc += gl[t][col];
+        if (c < C) atomicAdd(&gdb[c], sacc);
+        else atomicAdd(&gsb[c - C], sacc);
     }
 }
 
@@ -367,11 +365,12 @@ emb_concat_bwd_kernel(const float* __restrict__ gcat, const int32_t* __restrict_
 }  // namespace
 
 int launch_heads_fwd(const float* x, const float* dw, const float* db, const float* sw, const float* sb,
-                     const uint8_t* cmask, float* strong, float* weak, float* sof, int B, int T, int D, int C,
-                     cudaStream_t s) {
+                     const uint8_t* cmask, float* strong, float* weak, float* sof, float* hsum, int B, int T, int D,
+                     int C, cudaStream_t s) {
     SEDK_PROF("heads_fwd", s);
     SEDK_REQUIRE(C >= 1 && C <= HC_MAX, "heads: nclass %d must be in [1, %d]", C, HC_MAX);
-    size_t smem = (size_t)(2 * C * (D + 1) + HT * (D + 1) + HT * 2 * HC_MAX + 2 * HC_MAX) * sizeof(float);
+    SEDK_REQUIRE(hsum != nullptr, "heads: hsum workspace missing");
+    size_t smem = (size_t)(2 * C * (D + 1) + HT * (D + 1) + HT * 2 * HC_MAX) * sizeof(float);
     SEDK_REQUIRE(smem <= 227 * 1024, "heads: feature width %d too large", D);
     static size_t configured = 0;
     if (smem > configured) {
@@ -379,26 +378,23 @@ int launch_heads_fwd(const float* x, const float* dw, const float* db, const flo
         if (rc) return rc;
         configured = smem;
     }
-    heads_fwd_kernel<<<B, 256, smem, s>>>(x, dw, db, sw, sb, cmask, strong, weak, sof, T, D, C);
+    SEDK_CUDA(cudaMemsetAsync(hsum, 0, (size_t)B * 2 * C * sizeof(float), s));
+    dim3 grid(cdiv(T, HT), B);
+    heads_fwd_kernel<<<grid, 256, smem, s>>>(x, dw, db, sw, sb, cmask, strong, hsum, sof, T, D, C);
     SEDK_LAUNCH_CHECK("heads_fwd_kernel");
+    heads_weak_kernel<<<cdiv(B * C, 128), 128, 0, s>>>(hsum, cmask, weak, B, C);
+    SEDK_LAUNCH_CHECK("heads_weak_kernel");
     return SEDK_OK;
 }
 
 int launch_heads_bwd(const float* x, const float* dw, const float* sw, const uint8_t* cmask, const float* strong,
-                     const float* weak, const float* sof, const float* gstrong, const float* gweak, float* gx,
+                     const float* hsum, const float* sof, const float* gstrong, const float* gweak, float* gx,
                      float* gdw, float* gdb, float* gsw, float* gsb, int B, int T, int D, int C, cudaStream_t s) {
     SEDK_PROF("heads_bwd", s);
     SEDK_REQUIRE(C >= 1 && C <= HC_MAX, "heads: nclass %d must be in [1, %d]", C, HC_MAX);
-    size_t smem = (size_t)(T * 2 * C + 2 * HC_MAX) * sizeof(float);
-    SEDK_REQUIRE(smem <= 227 * 1024, "heads: sequence of %d frames too long", T);
-    static size_t configured = 0;
-    if (smem > configured) {
-        int rc = opt_in_smem(heads_bwd_kernel, smem);
-        if (rc) return rc;
-        configured = smem;
-    }
-    heads_bwd_kernel<<<B, 256, smem, s>>>(x, dw, sw, cmask, strong, weak, sof, gstrong, gweak, gx, gdw, gdb, gsw, gsb, T,
-                                          D, C);
+    dim3 grid(cdiv(T, HT), B);
+    heads_bwd_kernel<<<grid, 256, 0, s>>>(x, dw, sw, cmask, strong, hsum, sof, gstrong, gweak, gx, gdw, gdb, gsw, gsb, T, D,
+                                          C);
     SEDK_LAUNCH_CHECK("heads_bwd_kernel");
     return SEDK_OK;
 }

@@ -50,6 +50,10 @@ int launch_bn_bwd_apply(float* gy, const float* z, const float* bn, const double
 // ---- gemm.cu ------------------------------------------------------------------------------------------------
 int launch_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
                 int ldb, float beta, float* C, int ldc, const float* bias, int precision, cudaStream_t s);
+// up to 4 problems of identical shape in one launch (blockIdx.z); pointer arrays live on the host
+int launch_gemm_batched(int transA, int transB, int M, int N, int K, float alpha, const float* const* A, int lda,
+                        const float* const* B, int ldb, float beta, float* const* C, int ldc, const float* const* bias,
+                        int nprob, int precision, cudaStream_t s);
 // column sums: out[n] (+)= sum_m A[m*lda + n]
 int launch_colsum(const float* A, int M, int N, int lda, float* out, int accumulate, cudaStream_t s);
 
@@ -64,10 +68,10 @@ int launch_gru_seq_bwd(const float* gout, const float* const w_hh[2], const floa
 
 // ---- heads.cu -----------------------------------------------------------------------------------------------
 int launch_heads_fwd(const float* x, const float* dw, const float* db, const float* sw, const float* sb,
-                     const uint8_t* cmask, float* strong, float* weak, float* sof, int B, int T, int D, int C,
-                     cudaStream_t s);
+                     const uint8_t* cmask, float* strong, float* weak, float* sof, float* hsum, int B, int T, int D,
+                     int C, cudaStream_t s);
 int launch_heads_bwd(const float* x, const float* dw, const float* sw, const uint8_t* cmask, const float* strong,
-                     const float* weak, const float* sof, const float* gstrong, const float* gweak, float* gx,
+                     const float* hsum, const float* sof, const float* gstrong, const float* gweak, float* gx,
                      float* gdw, float* gdb, float* gsw, float* gsb, int B, int T, int D, int C, cudaStream_t s);
 // y = keep ? x/(1-p) : 0 (stream-indexed Philox mask); used forward and backward
 int launch_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev,

@@ -131,6 +131,8 @@ class _Workspace:
         self.rnn_drop = new(B, T, in_dim)
         self.grnn_drop = new(B, T, in_dim)
         self.sof = new(B, T, model.nclass)
+        self.hsum = new(B, 2, model.nclass)
+        plan.hsum = _vp(self.hsum)
         plan.rnn_drop, plan.grnn_drop, plan.sof = _vp(self.rnn_drop), _vp(self.grnn_drop), _vp(self.sof)
         plan.gdense_w, plan.gdense_b = _vp(self.gviews["dense.weight"]), _vp(self.gviews["dense.bias"])
         plan.gsoft_w, plan.gsoft_b = _vp(self.gviews["dense_softmax.weight"]), _vp(self.gviews["dense_softmax.bias"])

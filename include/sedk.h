@@ -227,7 +227,8 @@ typedef struct {
     float* grnn_drop;
     float* strong;                  /* out: [B, C, T'] */
     float* weak;                    /* out: [B, C]     */
-    float* sof;                     /* [B, T', C] workspace: clamped attention                 */
+    float* sof;                     /* [B, T', C] workspace: class-softmax attention (unclamped) */
+    float* hsum;                    /* [B, 2, C] workspace: sum_t strong*att, sum_t att        */
     float* gstrong;                 /* in (backward): [B, C, T'] */
     float* gweak;                   /* in (backward): [B, C]     */
 } sedk_crnn_plan;

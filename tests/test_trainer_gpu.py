@@ -68,7 +68,13 @@ def oracle_step(P, cfg, audio, labels, seed, step_num=1):
     return out, dict(zip(names, grads)), Ps, Pt, mix
 
 
-@pytest.mark.parametrize("seed", [0, 1])          # seed 0 -> mixup branch taken, seed 1 -> not (random.random())
+def _noise_param(n):
+    # conv biases in front of a train-mode BatchNorm have an exactly-zero gradient; the oracle's fp32 noise gradient is
+    # normalised by Adam into an O(lr) random move, so these tensors are compared only through the forward results
+    return ".conv" in n and n.endswith(".bias")
+
+
+@pytest.mark.parametrize("seed", [0, 1])          # seed 1 -> mixup branch taken, seed 0 -> not (random.random())
 def test_training_step_autograd_path(dev, seed):
     mod, P, cfg = make(dev)
     audio, labels = data()
@@ -84,12 +90,17 @@ def test_training_step_autograd_path(dev, seed):
     loss.backward()
     gscale = max(g.abs().max().item() for g in rgrads.values())
     for n, p in mod.sed_student.named_parameters():
+        if ".conv" in n and n.endswith(".bias"):
+            # exact value 0 (the bias cancels in train-mode BN): the kernel writes 0, the oracle holds fp32 noise
+            assert p.grad.abs().max().item() == 0.0 and rgrads[n].abs().max().item() < 1e-3 * gscale, n
+            continue
         err = (p.grad.cpu() - rgrads[n]).abs().max().item() / max(rgrads[n].abs().max().item(), 1e-2 * gscale)
         assert err < 2e-3, (n, err)
     mod.opt.step()
     mod.lr_scheduler_step(mod.scheduler["scheduler"], 0, None)
     for n, p in mod.sed_student.named_parameters():
-        assert maxdiff(p, Ps[n]) < 2e-5, n                 # Adam moves each weight by ~lr: compare absolutely
+        if not _noise_param(n):
+            assert maxdiff(p, Ps[n]) < 2e-5, n             # Adam moves each weight by ~lr: compare absolutely
     for n, p in mod.sed_teacher.named_parameters():
         assert maxdiff(p, Pt[n]) < 1e-6, n
     assert mod.scheduler["scheduler"].step_num == 2
@@ -104,7 +115,7 @@ def test_fused_engine_matches_oracle_over_three_steps(dev, use_graph):
     Ps = {k: (v.clone().requires_grad_(True) if ocrnn.is_float_param(k) else v.clone()) for k, v in P.items()}
     Pt = {k: v.clone() for k, v in P.items()}
     state = {}
-    random.seed(4); np.random.seed(4); torch.manual_seed(4)
+    random.seed(3); np.random.seed(3); torch.manual_seed(3)
     ref_losses, mixes = [], []
     for step in range(1, 4):
         mix = None
@@ -126,7 +137,7 @@ def test_fused_engine_matches_oracle_over_three_steps(dev, use_graph):
                 Pt[k] = v
         ref_losses.append(out["tot_loss"].item())
     assert any(mixes) and not all(mixes)
-    random.seed(4); np.random.seed(4); torch.manual_seed(4)
+    random.seed(3); np.random.seed(3); torch.manual_seed(3)
     a_pin, l_pin = audio.pin_memory(), labels.pin_memory()
     got = []
     for step in range(3):
@@ -135,9 +146,11 @@ def test_fused_engine_matches_oracle_over_three_steps(dev, use_graph):
     for a, b in zip(got, ref_losses):
         assert abs(a - b) < 5e-5, (got, ref_losses)
     for n, p in mod.sed_student.named_parameters():
-        assert maxdiff(p, Ps[n]) < 5e-5, n
+        if not _noise_param(n):
+            assert maxdiff(p, Ps[n]) < 5e-5, n
     for n, p in mod.sed_teacher.named_parameters():
-        assert maxdiff(p, Pt[n]) < 5e-6, n
+        if not _noise_param(n):
+            assert maxdiff(p, Pt[n]) < 5e-6, n
     sd = mod.sed_student.state_dict()
     assert maxdiff(sd["cnn.cnn.batchnorm2.running_var"], Ps["cnn.cnn.batchnorm2.running_var"]) < 1e-4
     assert int(sd["cnn.cnn.batchnorm0.num_batches_tracked"]) == 3
