@@ -122,11 +122,15 @@ bnglu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
             for (int j = 0; j < NF; j++)
 #pragma unroll
                 for (int q = 0; q < 4; q++) acc[i][j][q] = 0.f;
+        {
+            const uint32_t ya = smem_u32(Y) + 4u * (uint32_t)((wm0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * YS + 4 * (lane >> 4));
+            const uint32_t wb = smem_u32(W) + 4u * (uint32_t)((wn0 + (lane >> 4) * 8 + (lane & 7)) * YS + 4 * ((lane >> 3) & 1));
 #pragma unroll 4
-        for (int k8 = 0; k8 < C / 8; k8++) {
-            auto fa = [&](int i, int rr, int c) { return Y[(wm0 + i * 16 + g + 8 * rr) * YS + k8 * 8 + t4 + 4 * c]; };
-            auto fb = [&](int j, int c) { return W[(wn0 + j * 8 + g) * YS + k8 * 8 + t4 + 4 * c]; };
-            warp_mma_k8<MF, NF, X3>(acc, fa, fb);
+            for (int k8 = 0; k8 < C / 8; k8++) {
+                auto fa = [&](int i) { return ya + 4u * (uint32_t)(i * 16 * YS + k8 * 8); };
+                auto fb = [&](int jp) { return wb + 4u * (uint32_t)(jp * 16 * YS + k8 * 8); };
+                warp_mma_k8_ldsm<MF, NF, X3>(acc, fa, fb);
+            }
         }
         __syncthreads();
 #pragma unroll
@@ -141,8 +145,8 @@ bnglu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
                 for (int j = 0; j < NF; j++) {
                     const int n = wn0 + j * 8 + 2 * t4;
                     float2 y = *reinterpret_cast<float2*>(Y + m * YS + n);
-                    float a0 = (acc[i][j][2 * rr] + vec[2 * C + n]) * sigmoidf_(y.x);
-                    float a1 = (acc[i][j][2 * rr + 1] + vec[2 * C + n + 1]) * sigmoidf_(y.y);
+                    float a0 = (acc[i][j][2 * rr] + vec[2 * C + n]) * fast_sigmoidf_(y.x);
+                    float a1 = (acc[i][j][2 * rr + 1] + vec[2 * C + n + 1]) * fast_sigmoidf_(y.y);
                     if (thresh != 0u) {
                         if ((j & 1) == 0) rnd = philox_frag_pair(ph, pix, C / 16, (wn0 >> 4) + (j >> 1), t4, dstream);
                         const bool k0 = ((j & 1) ? rnd.z : rnd.x) >= thresh, k1 = ((j & 1) ? rnd.w : rnd.y) >= thresh;
@@ -245,11 +249,15 @@ bnglu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
             for (int j = 0; j < NF; j++)
 #pragma unroll
                 for (int q = 0; q < 4; q++) acc[i][j][q] = 0.f;
+        {
+            const uint32_t ya = smem_u32(Y) + 4u * (uint32_t)((wm0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * YS + 4 * (lane >> 4));
+            const uint32_t wb = smem_u32(W) + 4u * (uint32_t)((wn0 + (lane >> 4) * 8 + (lane & 7)) * YS + 4 * ((lane >> 3) & 1));
 #pragma unroll 4
-        for (int k8 = 0; k8 < C / 8; k8++) {
-            auto fa = [&](int i, int rr, int c) { return Y[(wm0 + i * 16 + g + 8 * rr) * YS + k8 * 8 + t4 + 4 * c]; };
-            auto fb = [&](int j, int c) { return W[(wn0 + j * 8 + g) * YS + k8 * 8 + t4 + 4 * c]; };
-            warp_mma_k8<MF, NF, X3>(acc, fa, fb);
+            for (int k8 = 0; k8 < C / 8; k8++) {
+                auto fa = [&](int i) { return ya + 4u * (uint32_t)(i * 16 * YS + k8 * 8); };
+                auto fb = [&](int jp) { return wb + 4u * (uint32_t)(jp * 16 * YS + k8 * 8); };
+                warp_mma_k8_ldsm<MF, NF, X3>(acc, fa, fb);
+            }
         }
         // ---- epilogue 1: g_lin -> G, elementwise part of g_y -> acc
         float cs[NF][2];
@@ -282,7 +290,7 @@ bnglu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
                         }
                     }
                     float2 y = *reinterpret_cast<float2*>(Y + m * YS + n);
-                    float s0 = sigmoidf_(y.x), s1 = sigmoidf_(y.y);
+                    float s0 = fast_sigmoidf_(y.x), s1 = fast_sigmoidf_(y.y);
                     float l0 = acc[i][j][2 * rr] + vec[2 * C + n], l1 = acc[i][j][2 * rr + 1] + vec[2 * C + n + 1];
                     float gl0 = ga0 * s0, gl1 = ga1 * s1;
                     *reinterpret_cast<float2*>(G + m * YS + n) = make_float2(gl0, gl1);

@@ -116,6 +116,8 @@ __device__ __forceinline__ float warp_min(float v) {
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// MUFU-based variant (ex2 + rcp): abs error ~1e-7, used inside the fused CNN block kernels and the recurrence
+__device__ __forceinline__ float fast_sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------
 // cp.async (LDGSTS) 16-byte copies with zero fill
@@ -211,6 +213,56 @@ __device__ __forceinline__ void warp_mma_k8(float (&acc)[MF][NF][4], FA fa, FB f
             }
             mma_tf32(acc[i][j], ah[i], bh);
         }
+    }
+}
+
+// Same step with the fragments fetched by ldmatrix (one LDSM.x4 per A fragment / per pair of B fragments instead of
+// 4 + 4 scalar LDS).  Valid when BOTH operands are K-major in shared memory with 16-byte aligned rows: a 16x8 TF32 A
+// fragment is four 8x8 b16 matrices whose 32-bit words are exactly (row g, k t), (g+8, t), (g, t+4), (g+8, t+4).
+// a_addr(i): shared byte address THIS lane contributes for m-fragment i, i.e. of row (lane&7) + 8*((lane>>3)&1), k-offset
+// 4*(lane>>4);  b_addr(jp): for the fragment pair (2jp, 2jp+1): row n = (2jp + (lane>>4))*8 + (lane&7), k-offset
+// 4*((lane>>3)&1).
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+template <int MF, int NF, bool X3, class FA, class FB>
+__device__ __forceinline__ void warp_mma_k8_ldsm(float (&acc)[MF][NF][4], FA a_addr, FB b_addr) {
+    static_assert(NF % 2 == 0, "fragment pairs");
+    uint32_t ah[MF][4], al[MF][4];
+#pragma unroll
+    for (int i = 0; i < MF; i++) {
+        uint32_t raw[4];
+        ldsm_x4(raw, a_addr(i));
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float v = __uint_as_float(raw[q]);
+            ah[i][q] = to_tf32(v);
+            if (X3) al[i][q] = to_tf32(v - __uint_as_float(ah[i][q]));
+        }
+    }
+#pragma unroll
+    for (int jp = 0; jp < NF / 2; jp++) {
+        uint32_t raw[4];
+        ldsm_x4(raw, b_addr(jp));
+        uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float v = __uint_as_float(raw[q]);
+            bh[q >> 1][q & 1] = to_tf32(v);
+            if (X3) bl[q >> 1][q & 1] = to_tf32(v - __uint_as_float(bh[q >> 1][q & 1]));
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int i = 0; i < MF; i++) {
+                if (X3) {
+                    mma_tf32(acc[i][2 * jp + h], al[i], bh[h]);
+                    mma_tf32(acc[i][2 * jp + h], ah[i], bl[h]);
+                }
+                mma_tf32(acc[i][2 * jp + h], ah[i], bh[h]);
+            }
     }
 }
 

@@ -301,15 +301,16 @@ conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ wp, const
     load_B(0, 0);
     cp_async_commit();
 
-    int hb[MF][2];
+    // ldmatrix row bases of this lane: A row (lane&7) + 8*((lane>>3)&1) of each m-fragment, k-offset 4*(lane>>4);
+    // B row (lane&7) of fragment 2jp + (lane>>4), k-offset 4*((lane>>3)&1)
+    uint32_t a_base[MF];
 #pragma unroll
-    for (int i = 0; i < MF; i++)
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            int m = wm0 + i * 16 + g + 8 * r;
-            int ty = m / TF, tx = m - ty * TF;
-            hb[i][r] = (ty * HW + tx) * HS;
-        }
+    for (int i = 0; i < MF; i++) {
+        int m = wm0 + i * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+        int ty = m / TF, tx = m - ty * TF;
+        a_base[i] = smem_u32(halo) + 4u * (uint32_t)((ty * HW + tx) * HS + 4 * (lane >> 4));
+    }
+    const uint32_t b_lane = 4u * (uint32_t)((wn0 + (lane >> 4) * 8 + (lane & 7)) * BS + 4 * ((lane >> 3) & 1));
     float acc[MF][NF][4];
 #pragma unroll
     for (int i = 0; i < MF; i++)
@@ -326,12 +327,12 @@ conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ wp, const
         const int tap = it / NCH, c0 = (it - tap * NCH) * KC;
         const int dy = tap / 3, dx = tap - dy * 3;
         const int toff = (dy * HW + dx) * HS + c0;
-        const float* Bb = Bs + (it & 1) * NT * BS;
+        const uint32_t bb = smem_u32(Bs + (it & 1) * NT * BS) + b_lane;
 #pragma unroll
         for (int k8 = 0; k8 < KC / 8; k8++) {
-            auto fa = [&](int i, int r, int c) { return halo[hb[i][r] + toff + k8 * 8 + t4 + 4 * c]; };
-            auto fb = [&](int j, int c) { return Bb[(wn0 + j * 8 + g) * BS + k8 * 8 + t4 + 4 * c]; };
-            warp_mma_k8<MF, NF, X3>(acc, fa, fb);
+            auto fa = [&](int i) { return a_base[i] + 4u * (uint32_t)(toff + k8 * 8); };
+            auto fb = [&](int jp) { return bb + 4u * (uint32_t)(jp * 16 * BS + k8 * 8); };
+            warp_mma_k8_ldsm<MF, NF, X3>(acc, fa, fb);
         }
         __syncthreads();
     }

@@ -24,15 +24,29 @@ constexpr int SEG = 64;
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
-// dot product of 64 register-resident weights with 64 shared-memory values using packed FP32 FMA (FFMA2, sm_100+)
-__device__ __forceinline__ float dot64_ffma2(const float2 (&w)[SEG / 2], const float* __restrict__ v) {
+// The register file cannot hold all of W_hh next to the loop state (49 152 of 65 536 registers at H = 128: the first
+// version spilled inside the recurrence), so each thread keeps WR = 48 of its 64 weights in registers and the last 16 in
+// shared memory, laid out [chunk][thread] so that a warp's 16-byte reads are contiguous.
+constexpr int WR = 48;                    // weights per thread held in registers
+constexpr int WS4 = (SEG - WR) / 4;       // float4 chunks per thread held in shared memory
+
+// dot product of 64 weights (48 registers + 16 shared) with 64 shared-memory values; packed FP32 FMA (FFMA2, sm_100+)
+__device__ __forceinline__ float dot64_ffma2(const float2 (&w)[WR / 2], const float4* __restrict__ ws, int nthreads,
+                                             const float* __restrict__ v) {
     const float4* v4 = reinterpret_cast<const float4*>(v);
     float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k4 = 0; k4 < SEG / 4; k4++) {
+    for (int k4 = 0; k4 < WR / 4; k4++) {
         const float4 hh = v4[k4];
         a0 = __ffma2_rn(w[2 * k4], make_float2(hh.x, hh.y), a0);
         a1 = __ffma2_rn(w[2 * k4 + 1], make_float2(hh.z, hh.w), a1);
+    }
+#pragma unroll
+    for (int c = 0; c < WS4; c++) {
+        const float4 hh = v4[WR / 4 + c];
+        const float4 ww = ws[c * nthreads];
+        a0 = __ffma2_rn(make_float2(ww.x, ww.y), make_float2(hh.x, hh.y), a0);
+        a1 = __ffma2_rn(make_float2(ww.z, ww.w), make_float2(hh.z, hh.w), a1);
     }
     return (a0.x + a0.y) + (a1.x + a1.y);
 }
@@ -64,8 +78,10 @@ gru_fwd_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, con
                float* __restrict__ hprev0, float* __restrict__ hprev1, int B, int T, int save) {
     using Cfg = GruCfg<H, CS>;
     constexpr int HU = Cfg::HU, R = Cfg::R, SEGS = Cfg::SEGS, NT = Cfg::NT_F;
-    __shared__ __align__(16) float h_s[2][NB][H];          // double-buffered when CS > 1 (remote writes)
-    __shared__ float part[SEGS][NB][R];
+    extern __shared__ __align__(16) float gru_smem[];
+    float4* ws4 = reinterpret_cast<float4*>(gru_smem);                                  // [WS4][NT] float4
+    float (*h_s)[NB][H] = reinterpret_cast<float (*)[NB][H]>(gru_smem + WS4 * NT * 4);  // [2][NB][H]
+    float (*part)[NB][R] = reinterpret_cast<float (*)[NB][R]>(gru_smem + WS4 * NT * 4 + 2 * NB * H);   // [SEGS][NB][R]
     const int tid = threadIdx.x;
     const int dir = blockIdx.y;
     int crank = 0;
@@ -81,10 +97,13 @@ gru_fwd_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, con
     const int seg = tid / R, row = tid - seg * R;           // row in [0, R): gate = row / HU, unit = row % HU
     const int gate = row / HU, unit = row - gate * HU;
     const int grow = gate * H + u0 + unit;                  // row of W_hh [3H, H]
-    float2 w[SEG / 2];
+    float2 w[WR / 2];
 #pragma unroll
-    for (int k = 0; k < SEG / 2; k++)
+    for (int k = 0; k < WR / 2; k++)
         w[k] = *reinterpret_cast<const float2*>(whh + (size_t)grow * H + seg * SEG + 2 * k);
+#pragma unroll
+    for (int c = 0; c < WS4; c++)
+        ws4[c * NT + tid] = *reinterpret_cast<const float4*>(whh + (size_t)grow * H + seg * SEG + WR + 4 * c);
 
     for (int i = tid; i < 2 * NB * H; i += NT) (&h_s[0][0][0])[i] = 0.f;
     const bool is_gate = tid < NB * HU;
@@ -119,7 +138,7 @@ gru_fwd_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, con
             nin = gp[2 * H];
         }
 #pragma unroll
-        for (int nb = 0; nb < NB; nb++) part[seg][nb][row] = dot64_ffma2(w, &h_s[cur][nb][seg * SEG]);
+        for (int nb = 0; nb < NB; nb++) part[seg][nb][row] = dot64_ffma2(w, ws4 + tid, NT, &h_s[cur][nb][seg * SEG]);
         __syncthreads();
         const int nxt = CS > 1 ? cur ^ 1 : cur;
         if (is_gate) {
@@ -175,8 +194,11 @@ gru_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ whh0, c
                float* __restrict__ dghn0, float* __restrict__ dghn1, int B, int T) {
     using Cfg = GruCfg<H, CS>;
     constexpr int HU = Cfg::HU, JSEGS = Cfg::JSEGS, NT = Cfg::NT_B;
-    __shared__ __align__(16) float dgh_s[2][NB][3 * H];     // recurrent pre-activation grads (r, z, hn), all units
-    __shared__ float part[JSEGS][NB][HU];
+    extern __shared__ __align__(16) float gru_smem[];
+    float4* ws4 = reinterpret_cast<float4*>(gru_smem);                                  // [WS4][NT] float4
+    // recurrent pre-activation grads (r, z, hn) of all units, double-buffered: [2][NB][3H]
+    float (*dgh_s)[NB][3 * H] = reinterpret_cast<float (*)[NB][3 * H]>(gru_smem + WS4 * NT * 4);
+    float (*part)[NB][HU] = reinterpret_cast<float (*)[NB][HU]>(gru_smem + WS4 * NT * 4 + 2 * NB * 3 * H);  // [JSEGS][NB][HU]
     const int tid = threadIdx.x;
     const int dir = blockIdx.y;
     int crank = 0;
@@ -190,11 +212,16 @@ gru_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ whh0, c
     float* dghn = dir ? dghn1 : dghn0;
 
     const int jseg = tid / HU, col = tid - jseg * HU;        // column u0+col of W_hh, rows jseg*64 .. +64
-    float2 w[SEG / 2];
+    float2 w[WR / 2];
 #pragma unroll
-    for (int k = 0; k < SEG / 2; k++)
+    for (int k = 0; k < WR / 2; k++)
         w[k] = make_float2(whh[(size_t)(jseg * SEG + 2 * k) * H + u0 + col],
                            whh[(size_t)(jseg * SEG + 2 * k + 1) * H + u0 + col]);
+#pragma unroll
+    for (int c = 0; c < WS4; c++) {
+        const size_t r0 = (size_t)(jseg * SEG + WR + 4 * c) * H + u0 + col;
+        ws4[c * NT + tid] = make_float4(whh[r0], whh[r0 + H], whh[r0 + 2 * H], whh[r0 + 3 * H]);
+    }
 
     for (int i = tid; i < 2 * NB * 3 * H; i += NT) (&dgh_s[0][0][0])[i] = 0.f;
     const bool is_gate = tid < NB * HU;
@@ -263,7 +290,7 @@ gru_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ whh0, c
         if (CS > 1) cg::this_cluster().sync(); else __syncthreads();
         // dh_prev[u] += sum_j W_hh[j][u] * dgh[j]
 #pragma unroll
-        for (int nb = 0; nb < NB; nb++) part[jseg][nb][col] = dot64_ffma2(w, &dgh_s[cur][nb][jseg * SEG]);
+        for (int nb = 0; nb < NB; nb++) part[jseg][nb][col] = dot64_ffma2(w, ws4 + tid, NT, &dgh_s[cur][nb][jseg * SEG]);
         __syncthreads();
         if (is_gate) {
             float s = dh_direct;
@@ -283,10 +310,17 @@ int run_fwd(const float* const gi[2], const float* const w_hh[2], const float* c
     static_assert(GruNbOk<H, CS, NB>::ok, "");
     auto kern = gru_fwd_kernel<H, CS, NB>;
     dim3 grid(cdiv(B, NB) * CS, 2);
+    const size_t smem = (size_t)(WS4 * Cfg::NT_F * 4 + 2 * NB * H + Cfg::SEGS * NB * Cfg::R) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        int rc = opt_in_smem(kern, smem);
+        if (rc) return rc;
+        configured = true;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(Cfg::NT_F);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -307,10 +341,17 @@ int run_bwd(const float* gout, const float* const w_hh[2], const float* const ga
     using Cfg = GruCfg<H, CS>;
     auto kern = gru_bwd_kernel<H, CS, NB>;
     dim3 grid(cdiv(B, NB) * CS, 2);
+    const size_t smem = (size_t)(WS4 * Cfg::NT_B * 4 + 2 * NB * 3 * H + Cfg::JSEGS * NB * Cfg::HU) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        int rc = opt_in_smem(kern, smem);
+        if (rc) return rc;
+        configured = true;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(Cfg::NT_B);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
