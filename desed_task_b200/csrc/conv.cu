@@ -589,10 +589,13 @@ static int run_conv_tiles(const float* in, const float* wp, const float* bias, f
 
 int launch_conv3x3(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T, int F,
                    int cin, int cout, int precision, cudaStream_t s) {
+    if (cin == 128 && cout == 128 && precision == 0 && tc5_enabled())
+        return launch_conv3x3_tc5(in, wp, bias, out, stats, B, T, F, s);
     char pname[64];
     snprintf(pname, sizeof(pname), "conv3x3_%dto%d_F%d", cin, cout, F);
     SEDK_PROF(pname, s);
-    const int nt = cout >= 128 ? 128 : cout;
+    // 128-wide inputs: two 64-channel output tiles per pixel tile -> 113 KB of shared memory, 2 CTAs (16 warps) per SM
+    const int nt = cout >= 128 ? (cin >= 128 ? 64 : 128) : cout;
     SEDK_REQUIRE(cout % nt == 0, "conv3x3: cout %d must be a multiple of %d", cout, nt);
 #define SEDK_CONV(CI, NTV) \
     if (cin == CI && nt == NTV) return run_conv_tiles<CI, NTV>(in, wp, bias, out, stats, B, T, F, cout, precision, s);

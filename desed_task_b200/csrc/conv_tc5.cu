@@ -1,0 +1,297 @@
+// 3x3 convolution 128 -> 128 channels on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a.
+//
+// Implicit GEMM per CTA: D[128 pixels x 128 out-channels] (fp32 accumulator in TMEM, 128 columns) =
+//   sum over 9 taps x 4 channel chunks of  A_tap,chunk[128 px x 32 ch] * W_tap,chunk[128 co x 32 ci]^T   (kind::tf32).
+// * A tiles come straight from the channels-last activation tensor through a 4-D TMA tensor map
+//   {C, F, T, B} with box {32, TF, TT, 1}: the tap shift is a coordinate offset (f0+dx-1, t0+dy-1) and the zero padding of
+//   the convolution is TMA's out-of-bounds zero fill - there is no im2col and no halo bookkeeping in the kernel.
+// * W tiles come from the packed weights [tap][co][ci] through a 3-D map, box {32, 128, 1}.
+// * Both land in shared memory as K-major rows of 128 bytes with the 128-byte swizzle the UMMA descriptors expect.
+// * Warp-specialised: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane issues
+//   tcgen05.mma, tcgen05.commit releases pipeline stages through mbarriers), warps 2-5 = epilogue (tcgen05.ld of their
+//   TMEM lane quadrant -> bias -> global store + per-channel sum / sum^2 for train-mode BatchNorm).
+// The same kernel is the data-gradient when given the flipped/transposed weight pack.
+#include "kernels.h"
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace sedk {
+namespace {
+
+constexpr int TC_STAGES = 6;
+constexpr int TC_A_BYTES = 128 * 128;                 // 128 rows x 32 fp32
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES;
+constexpr int TC_THREADS = 192;
+constexpr int TC_C = 128;                             // channels in and out
+constexpr uint32_t TC_TMEM_COLS = 128;
+constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*stats*/;
+
+// instruction descriptor: D fp32, A/B tf32, both K-major, N = 128, M = 128 (cute::UMMA::InstrDescriptor bit layout)
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    // K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO = 16 B, descriptor version 1
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t (&v)[32], uint32_t taddr) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+template <int TT, int TF>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const float* __restrict__ bias, float* __restrict__ out, double* __restrict__ stats, int T, int F) {
+    static_assert(TT * TF == 128, "tile must hold 128 pixels");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;         // 1024-byte aligned (128B swizzle atoms)
+    uint8_t* aligned = smem_raw + (base - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(aligned + (size_t)TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* full = bars;                       // [TC_STAGES]
+    uint64_t* empty = bars + TC_STAGES;          // [TC_STAGES]
+    uint64_t* accum = bars + 2 * TC_STAGES;      // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+    float* s_stat = reinterpret_cast<float*>(aligned + (size_t)TC_STAGES * TC_STAGE_BYTES + 256);   // [2][128]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nTf = (F + TF - 1) / TF, nTt = (T + TT - 1) / TT;
+    int tile = blockIdx.x;
+    const int b = tile / (nTt * nTf);
+    tile -= b * nTt * nTf;
+    const int t0 = (tile / nTf) * TT, f0 = (tile % nTf) * TF;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accum, 1);
+        fence_mbar_init();
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB) : "memory");
+    }
+    for (int i = tid; i < 2 * TC_C; i += TC_THREADS) s_stat[i] = 0.f;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    constexpr int NIT = 9 * 4;     // taps x 32-channel chunks
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < NIT; it++) {
+                const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                mbar_wait_u32(smem_u32(&empty[s]), ph ^ 1);
+                const int tap = it >> 2, chunk = it & 3;
+                const int dy = tap / 3, dx = tap - dy * 3;
+                const uint32_t a_dst = base + s * TC_STAGE_BYTES, b_dst = a_dst + TC_A_BYTES;
+                mbar_expect_tx(&full[s], TC_STAGE_BYTES);
+                tma_load_4d(a_dst, &tmA, smem_u32(&full[s]), chunk * 32, f0 + dx - 1, t0 + dy - 1, b);
+                tma_load_3d(b_dst, &tmB, smem_u32(&full[s]), chunk * 32, 0, tap);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int it = 0; it < NIT; it++) {
+                const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                mbar_wait_u32(smem_u32(&full[s]), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint32_t a_src = base + s * TC_STAGE_BYTES, b_src = a_src + TC_A_BYTES;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {       // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
+                    umma_tf32(tmem, umma_desc_sw128(a_src + k * 32), umma_desc_sw128(b_src + k * 32), TC_IDESC,
+                              (it | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&empty[s]));   // frees the stage once these MMAs have read it
+            }
+            umma_commit(smem_u32(accum));           // accumulator complete
+        }
+    } else {
+        // ---- epilogue: warp q owns TMEM lanes [32q, 32q+32) = accumulator rows (pixels)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int ty = row / TF, tx = row - ty * TF;
+        const int t = t0 + ty, f = f0 + tx;
+        const bool valid = (t < T) && (f < F);
+        mbar_wait_u32(smem_u32(accum), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        float* orow = out + (((size_t)b * T + t) * F + f) * TC_C;
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+            uint32_t v[32];
+            tmem_ld32(v, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32));
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                x[j] = __uint_as_float(v[j]);
+                if (bias != nullptr) x[j] += bias[c * 32 + j];
+            }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    reinterpret_cast<float4*>(orow + c * 32)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            }
+            if (stats != nullptr) {
+                float mys = 0.f, myq = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const float xv = valid ? x[j] : 0.f;
+                    const float s1 = warp_sum(xv), s2 = warp_sum(xv * xv);
+                    if (lane == j) { mys = s1; myq = s2; }
+                }
+                atomicAdd(&s_stat[c * 32 + lane], mys);
+                atomicAdd(&s_stat[TC_C + c * 32 + lane], myq);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (stats != nullptr) {
+        for (int i = tid; i < 2 * TC_C; i += TC_THREADS) atomicAdd(&stats[i], (double)s_stat[i]);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+template <int TT, int TF>
+int run_tc5(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, float* out, double* stats, int B, int T,
+            int F, cudaStream_t s) {
+    auto kern = conv3x3_tc5_kernel<TT, TF>;
+    static bool cfg = false;
+    if (!cfg) {
+        int rc = opt_in_smem(kern, TC_SMEM);
+        if (rc) return rc;
+        cfg = true;
+    }
+    dim3 grid(B * cdiv(T, TT) * cdiv(F, TF));
+    kern<<<grid, TC_THREADS, TC_SMEM, s>>>(tmA, tmB, bias, out, stats, T, F);
+    SEDK_LAUNCH_CHECK("conv3x3_tc5_kernel");
+    return SEDK_OK;
+}
+
+}  // namespace
+
+bool tc5_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("SEDK_DISABLE_TCGEN05");
+        on = (e != nullptr && e[0] == '1') ? 0 : 1;
+    }
+    return on == 1;
+}
+
+int launch_conv3x3_tc5(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T,
+                       int F, cudaStream_t s) {
+    char pname[64];
+    snprintf(pname, sizeof(pname), "conv3x3_tc5_128to128_F%d", F);
+    SEDK_PROF(pname, s);
+    EncodeTiledFn enc = encode_fn();
+    SEDK_REQUIRE(enc != nullptr, "conv3x3_tc5: cuTensorMapEncodeTiled is not available from the driver");
+    SEDK_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0,
+                 "conv3x3_tc5: operands must be 16-byte aligned");
+    int TT, TF;
+    if (F > 8) { TT = 8; TF = 16; }
+    else if (F > 4) { TT = 16; TF = 8; }
+    else if (F > 2) { TT = 32; TF = 4; }
+    else { TT = 64; TF = 2; }
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)TC_C, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)TC_C * 4, (cuuint64_t)F * TC_C * 4, (cuuint64_t)T * F * TC_C * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)TF, (cuuint32_t)TT, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SEDK_REQUIRE(r == CUDA_SUCCESS, "conv3x3_tc5: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)TC_C, (cuuint64_t)TC_C, 9};
+        cuuint64_t strides[2] = {(cuuint64_t)TC_C * 4, (cuuint64_t)TC_C * TC_C * 4};
+        cuuint32_t box[3] = {32, 128, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(wp), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SEDK_REQUIRE(r == CUDA_SUCCESS, "conv3x3_tc5: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+    }
+    if (TF == 16) return run_tc5<8, 16>(tmA, tmB, bias, out, stats, B, T, F, s);
+    if (TF == 8) return run_tc5<16, 8>(tmA, tmB, bias, out, stats, B, T, F, s);
+    if (TF == 4) return run_tc5<32, 4>(tmA, tmB, bias, out, stats, B, T, F, s);
+    return run_tc5<64, 2>(tmA, tmB, bias, out, stats, B, T, F, s);
+}
+
+}  // namespace sedk

@@ -23,6 +23,10 @@ int launch_conv0_wgrad(const float* x0, const float* gz, float* gw, int B, int T
 // The same kernel computes dgrad when given the flipped/transposed pack (wpack[1]).
 int launch_conv3x3(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T, int F,
                    int cin, int cout, int precision, cudaStream_t s);
+// tcgen05 / TMEM / TMA implicit-GEMM variant for 128 -> 128 channels (TF32); conv_tc5.cu
+bool tc5_enabled();
+int launch_conv3x3_tc5(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T,
+                       int F, cudaStream_t s);
 // gwpack[tap][co][ci] += sum_pix gz[pix][co] * x[pix + shift(tap)][ci]   (gwpack zeroed by the caller)
 int launch_conv_wgrad(const float* x, const float* gz, float* gwpack, int B, int T, int F, int cin, int cout,
                       int precision, cudaStream_t s);
