@@ -68,6 +68,32 @@ __device__ __forceinline__ uint4 philox_frag_pair(const Philox& ph, uint64_t pix
     return ph((pix * (uint64_t)pairs_per_pixel + (uint64_t)pair) * 4ull + (uint64_t)t4, stream);
 }
 
+// L2 prefetch of the z rows (and, backward, the pooled gout rows) of the tile this CTA will process NEXT: the persistent
+// loop is otherwise synchronous (load tile -> compute), which exposes HBM latency once per tile.
+template <int C>
+__device__ __forceinline__ void prefetch_tile(const float* __restrict__ z, const float* __restrict__ gout,
+                                              const TileGeom& gm, int tile, int total_tiles, int tid) {
+    if (tile >= total_tiles) return;
+    int r = tile;
+    const int b = r / (gm.nTt * gm.nTf);
+    r -= b * gm.nTt * gm.nTf;
+    const int t0 = (r / gm.nTf) * gm.TT, f0 = (r % gm.nTf) * gm.TF;
+    constexpr int LINES = 128 * C / 32;            // 128-byte lines of a 128-pixel tile
+    for (int i = tid; i < LINES; i += 256) {
+        const int p = (i * 32) / C, ch = (i * 32) % C;
+        const int ty = p >> gm.tf_shift, tx = p & (gm.TF - 1);
+        const int t = t0 + ty, f = f0 + tx;
+        if (t < gm.Te && f < gm.Fe) {
+            const float* a = z + (((size_t)b * gm.T + t) * gm.F + f) * C + ch;
+            asm volatile("prefetch.global.L2 [%0];\n" ::"l"(a));
+            if (gout != nullptr && (t % gm.pt) == 0 && (f % gm.pf) == 0) {
+                const float* g = gout + (((size_t)b * gm.To + t / gm.pt) * gm.Fo + f / gm.pf) * C + ch;
+                asm volatile("prefetch.global.L2 [%0];\n" ::"l"(g));
+            }
+        }
+    }
+}
+
 template <int C, bool X3>
 __global__ void __launch_bounds__(256)
 bnglu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, const float* __restrict__ glu_w,
@@ -114,6 +140,7 @@ bnglu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
             }
             *reinterpret_cast<float4*>(Y + p * YS + q * 4) = v;
         }
+        prefetch_tile<C>(z, nullptr, gm, tile + gridDim.x, total_tiles, tid);
         __syncthreads();
         float acc[MF][NF][4];
 #pragma unroll
@@ -240,6 +267,7 @@ bnglu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
             }
             *reinterpret_cast<float4*>(Y + p * YS + q * 4) = v;
         }
+        prefetch_tile<C>(z, gout, gm, tile + gridDim.x, total_tiles, tid);
         __syncthreads();
         // ---- GEMM 1: lin = y Wg^T
         float acc[MF][NF][4];

@@ -589,8 +589,8 @@ static int run_conv_tiles(const float* in, const float* wp, const float* bias, f
 
 int launch_conv3x3(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T, int F,
                    int cin, int cout, int precision, cudaStream_t s) {
-    if (cin == 128 && cout == 128 && precision == 0 && tc5_enabled())
-        return launch_conv3x3_tc5(in, wp, bias, out, stats, B, T, F, s);
+    if (precision == 0 && tc5_enabled() && tc5_supports(cin, cout))
+        return launch_conv3x3_tc5(in, wp, bias, out, stats, B, T, F, cin, cout, s);
     char pname[64];
     snprintf(pname, sizeof(pname), "conv3x3_%dto%d_F%d", cin, cout, F);
     SEDK_PROF(pname, s);

@@ -1,11 +1,11 @@
-// 3x3 convolution 128 -> 128 channels on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a.
+// 3x3 convolution (Cin, Cout in {32, 64, 128}) on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a.
 //
-// Implicit GEMM per CTA: D[128 pixels x 128 out-channels] (fp32 accumulator in TMEM, 128 columns) =
-//   sum over 9 taps x 4 channel chunks of  A_tap,chunk[128 px x 32 ch] * W_tap,chunk[128 co x 32 ci]^T   (kind::tf32).
+// Implicit GEMM per CTA: D[128 pixels x Cout] (fp32 accumulator in TMEM, Cout columns) =
+//   sum over 9 taps x Cin/32 channel chunks of  A_tap,chunk[128 px x 32 ch] * W_tap,chunk[Cout x 32 ci]^T   (kind::tf32).
 // * A tiles come straight from the channels-last activation tensor through a 4-D TMA tensor map
 //   {C, F, T, B} with box {32, TF, TT, 1}: the tap shift is a coordinate offset (f0+dx-1, t0+dy-1) and the zero padding of
 //   the convolution is TMA's out-of-bounds zero fill - there is no im2col and no halo bookkeeping in the kernel.
-// * W tiles come from the packed weights [tap][co][ci] through a 3-D map, box {32, 128, 1}.
+// * W tiles come from the packed weights [tap][co][ci] through a 3-D map, box {32, Cout, 1}.
 // * Both land in shared memory as K-major rows of 128 bytes with the 128-byte swizzle the UMMA descriptors expect.
 // * Warp-specialised: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane issues
 //   tcgen05.mma, tcgen05.commit releases pipeline stages through mbarriers), warps 2-5 = epilogue (tcgen05.ld of their
@@ -22,12 +22,27 @@ constexpr int TC_STAGES = 6;
 constexpr int TC_A_BYTES = 128 * 128;                 // 128 rows x 32 fp32
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES;
 constexpr int TC_THREADS = 192;
-constexpr int TC_C = 128;                             // channels in and out
-constexpr uint32_t TC_TMEM_COLS = 128;
 constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*stats*/;
 
-// instruction descriptor: D fp32, A/B tf32, both K-major, N = 128, M = 128 (cute::UMMA::InstrDescriptor bit layout)
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D fp32, A/B tf32, both K-major, N = n, M = 128 (cute::UMMA::InstrDescriptor bit layout)
+__host__ __device__ constexpr uint32_t tc_idesc(uint32_t n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// column sums over the 32 lanes of a warp for 32 per-lane values: after the call v[0] of lane l holds sum_lanes v[l]
+// (recursive halving: 31 shuffles instead of 32 x 5)
+__device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; j++) {
+            const float send = upper ? v[j] : v[j + off];
+            const float keep = upper ? v[j + off] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
 
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     // K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO = 16 B, descriptor version 1
@@ -85,7 +100,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t (&v)[32], uint32_t taddr) {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-template <int TT, int TF>
+template <int CIN, int COUT, int TT, int TF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const float* __restrict__ bias, float* __restrict__ out, double* __restrict__ stats, int T, int F) {
@@ -98,7 +113,12 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint64_t* empty = bars + TC_STAGES;          // [TC_STAGES]
     uint64_t* accum = bars + 2 * TC_STAGES;      // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
-    float* s_stat = reinterpret_cast<float*>(aligned + (size_t)TC_STAGES * TC_STAGE_BYTES + 256);   // [2][128]
+    float* s_stat = reinterpret_cast<float*>(aligned + (size_t)TC_STAGES * TC_STAGE_BYTES + 256);   // [2][COUT]
+    constexpr int TC_C = COUT;
+    constexpr uint32_t TC_TMEM_COLS = COUT < 32 ? 32 : COUT;
+    constexpr uint32_t TC_IDESC = tc_idesc(COUT);
+    constexpr int NCHUNK = CIN / 32;
+    constexpr uint32_t STAGE_TX = TC_A_BYTES + COUT * 128;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nTf = (F + TF - 1) / TF, nTt = (T + TT - 1) / TT;
@@ -129,16 +149,16 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = *tmem_slot;
 
-    constexpr int NIT = 9 * 4;     // taps x 32-channel chunks
+    constexpr int NIT = 9 * NCHUNK;     // taps x 32-channel chunks
     if (warp == 0) {
         if (lane == 0) {
             for (int it = 0; it < NIT; it++) {
                 const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
                 mbar_wait_u32(smem_u32(&empty[s]), ph ^ 1);
-                const int tap = it >> 2, chunk = it & 3;
+                const int tap = it / NCHUNK, chunk = it - tap * NCHUNK;
                 const int dy = tap / 3, dx = tap - dy * 3;
                 const uint32_t a_dst = base + s * TC_STAGE_BYTES, b_dst = a_dst + TC_A_BYTES;
-                mbar_expect_tx(&full[s], TC_STAGE_BYTES);
+                mbar_expect_tx(&full[s], STAGE_TX);
                 tma_load_4d(a_dst, &tmA, smem_u32(&full[s]), chunk * 32, f0 + dx - 1, t0 + dy - 1, b);
                 tma_load_3d(b_dst, &tmB, smem_u32(&full[s]), chunk * 32, 0, tap);
             }
@@ -170,7 +190,7 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         float* orow = out + (((size_t)b * T + t) * F + f) * TC_C;
 #pragma unroll 1
-        for (int c = 0; c < 4; c++) {
+        for (int c = 0; c < COUT / 32; c++) {
             uint32_t v[32];
             tmem_ld32(v, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32));
             float x[32];
@@ -185,15 +205,16 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     reinterpret_cast<float4*>(orow + c * 32)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
             }
             if (stats != nullptr) {
-                float mys = 0.f, myq = 0.f;
+                float x2[32];
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
-                    const float xv = valid ? x[j] : 0.f;
-                    const float s1 = warp_sum(xv), s2 = warp_sum(xv * xv);
-                    if (lane == j) { mys = s1; myq = s2; }
+                    x[j] = valid ? x[j] : 0.f;
+                    x2[j] = x[j] * x[j];
                 }
-                atomicAdd(&s_stat[c * 32 + lane], mys);
-                atomicAdd(&s_stat[TC_C + c * 32 + lane], myq);
+                warp_transpose_reduce32(x, lane);
+                warp_transpose_reduce32(x2, lane);
+                atomicAdd(&s_stat[c * 32 + lane], x[0]);
+                atomicAdd(&s_stat[TC_C + c * 32 + lane], x2[0]);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -226,10 +247,10 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-template <int TT, int TF>
+template <int CIN, int COUT, int TT, int TF>
 int run_tc5(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, float* out, double* stats, int B, int T,
             int F, cudaStream_t s) {
-    auto kern = conv3x3_tc5_kernel<TT, TF>;
+    auto kern = conv3x3_tc5_kernel<CIN, COUT, TT, TF>;
     static bool cfg = false;
     if (!cfg) {
         int rc = opt_in_smem(kern, TC_SMEM);
@@ -240,6 +261,45 @@ int run_tc5(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, f
     kern<<<grid, TC_THREADS, TC_SMEM, s>>>(tmA, tmB, bias, out, stats, T, F);
     SEDK_LAUNCH_CHECK("conv3x3_tc5_kernel");
     return SEDK_OK;
+}
+
+template <int CIN, int COUT>
+int run_tc5_tiles(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T, int F,
+                  cudaStream_t s) {
+    EncodeTiledFn enc = encode_fn();
+    SEDK_REQUIRE(enc != nullptr, "conv3x3_tc5: cuTensorMapEncodeTiled is not available from the driver");
+    SEDK_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0,
+                 "conv3x3_tc5: operands must be 16-byte aligned");
+    int TT, TF;
+    if (F > 8) { TT = 8; TF = 16; }
+    else if (F > 4) { TT = 16; TF = 8; }
+    else if (F > 2) { TT = 32; TF = 4; }
+    else { TT = 64; TF = 2; }
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)CIN, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)CIN * 4, (cuuint64_t)F * CIN * 4, (cuuint64_t)T * F * CIN * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)TF, (cuuint32_t)TT, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SEDK_REQUIRE(r == CUDA_SUCCESS, "conv3x3_tc5: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)CIN, (cuuint64_t)COUT, 9};
+        cuuint64_t strides[2] = {(cuuint64_t)CIN * 4, (cuuint64_t)COUT * CIN * 4};
+        cuuint32_t box[3] = {32, (cuuint32_t)COUT, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(wp), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SEDK_REQUIRE(r == CUDA_SUCCESS, "conv3x3_tc5: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+    }
+    if (TF == 16) return run_tc5<CIN, COUT, 8, 16>(tmA, tmB, bias, out, stats, B, T, F, s);
+    if (TF == 8) return run_tc5<CIN, COUT, 16, 8>(tmA, tmB, bias, out, stats, B, T, F, s);
+    if (TF == 4) return run_tc5<CIN, COUT, 32, 4>(tmA, tmB, bias, out, stats, B, T, F, s);
+    return run_tc5<CIN, COUT, 64, 2>(tmA, tmB, bias, out, stats, B, T, F, s);
 }
 
 }  // namespace
@@ -253,45 +313,21 @@ bool tc5_enabled() {
     return on == 1;
 }
 
+bool tc5_supports(int cin, int cout) {
+    return (cin == 32 || cin == 64 || cin == 128) && (cout == 32 || cout == 64 || cout == 128);
+}
+
 int launch_conv3x3_tc5(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T,
-                       int F, cudaStream_t s) {
+                       int F, int cin, int cout, cudaStream_t s) {
     char pname[64];
-    snprintf(pname, sizeof(pname), "conv3x3_tc5_128to128_F%d", F);
+    snprintf(pname, sizeof(pname), "conv3x3_tc5_%dto%d_F%d", cin, cout, F);
     SEDK_PROF(pname, s);
-    EncodeTiledFn enc = encode_fn();
-    SEDK_REQUIRE(enc != nullptr, "conv3x3_tc5: cuTensorMapEncodeTiled is not available from the driver");
-    SEDK_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0,
-                 "conv3x3_tc5: operands must be 16-byte aligned");
-    int TT, TF;
-    if (F > 8) { TT = 8; TF = 16; }
-    else if (F > 4) { TT = 16; TF = 8; }
-    else if (F > 2) { TT = 32; TF = 4; }
-    else { TT = 64; TF = 2; }
-    CUtensorMap tmA, tmB;
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)TC_C, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)TC_C * 4, (cuuint64_t)F * TC_C * 4, (cuuint64_t)T * F * TC_C * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)TF, (cuuint32_t)TT, 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        SEDK_REQUIRE(r == CUDA_SUCCESS, "conv3x3_tc5: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
-    }
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)TC_C, (cuuint64_t)TC_C, 9};
-        cuuint64_t strides[2] = {(cuuint64_t)TC_C * 4, (cuuint64_t)TC_C * TC_C * 4};
-        cuuint32_t box[3] = {32, 128, 1};
-        cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(wp), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        SEDK_REQUIRE(r == CUDA_SUCCESS, "conv3x3_tc5: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
-    }
-    if (TF == 16) return run_tc5<8, 16>(tmA, tmB, bias, out, stats, B, T, F, s);
-    if (TF == 8) return run_tc5<16, 8>(tmA, tmB, bias, out, stats, B, T, F, s);
-    if (TF == 4) return run_tc5<32, 4>(tmA, tmB, bias, out, stats, B, T, F, s);
-    return run_tc5<64, 2>(tmA, tmB, bias, out, stats, B, T, F, s);
+#define SEDK_TC5(CI, CO) \
+    if (cin == CI && cout == CO) return run_tc5_tiles<CI, CO>(in, wp, bias, out, stats, B, T, F, s);
+    SEDK_TC5(128, 128) SEDK_TC5(64, 128) SEDK_TC5(128, 64) SEDK_TC5(32, 64) SEDK_TC5(64, 32) SEDK_TC5(64, 64)
+    SEDK_TC5(32, 32) SEDK_TC5(128, 32) SEDK_TC5(32, 128)
+#undef SEDK_TC5
+    SEDK_UNSUPPORTED("conv3x3_tc5: (cin=%d, cout=%d) has no tcgen05 instantiation", cin, cout);
 }
 
 }  // namespace sedk

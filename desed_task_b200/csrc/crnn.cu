@@ -165,7 +165,8 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
         const sedk_gru_layer& G = p->gru[l];
         const int H = G.hidden, in_dim = G.in_dim;
         SEDK_REQUIRE(G.gout && G.dghn[0] && G.dghn[1], "crnn backward: GRU layer %d gradient workspace missing", l);
-        rc = launch_gru_seq_bwd(G.gout, G.w_hh, G.gates, G.hprev, G.gi, G.dghn, B, Tp, H, s);
+        SEDK_REQUIRE(G.gb_ih[0] && G.gb_ih[1] && G.gb_hh[0] && G.gb_hh[1], "crnn backward: GRU bias grads null");
+        rc = launch_gru_seq_bwd(G.gout, G.w_hh, G.gates, G.hprev, G.gi, G.dghn, G.gb_ih, G.gb_hh, B, Tp, H, s);
         if (rc) return rc;
         const float* xin = l > 0 ? p->gru[l - 1].out : (p->emb ? p->fused : last.out);
         float* gin = l > 0 ? p->gru[l - 1].gout : (p->emb ? p->gfused : last.gout);
@@ -193,12 +194,6 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
             if (rc) return rc;
         }
         for (int d = 0; d < 2; d++) {
-            rc = launch_colsum(G.gi[d], BT, 3 * H, 3 * H, G.gb_ih[d], 0, s);
-            if (rc) return rc;
-            rc = launch_colsum(G.gi[d], BT, 2 * H, 3 * H, G.gb_hh[d], 0, s);
-            if (rc) return rc;
-            rc = launch_colsum(G.dghn[d], BT, H, H, G.gb_hh[d] + 2 * H, 0, s);
-            if (rc) return rc;
             // dx (+)= dgi W_ih
             rc = launch_gemm(0, 0, BT, in_dim, 3 * H, 1.f, G.gi[d], 3 * H, G.w_ih[d], in_dim, d == 0 ? 0.f : 1.f, gin,
                              in_dim, nullptr, p->precision, s);

@@ -25,30 +25,36 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f,
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
 // The register file cannot hold all of W_hh next to the loop state (49 152 of 65 536 registers at H = 128: the first
-// version spilled inside the recurrence), so each thread keeps WR = 48 of its 64 weights in registers and the last 16 in
+// version spilled inside the recurrence), so each thread keeps WR = 40 of its 64 weights in registers and the last 24 in
 // shared memory, laid out [chunk][thread] so that a warp's 16-byte reads are contiguous.
-constexpr int WR = 48;                    // weights per thread held in registers
+constexpr int WR = 40;                    // weights per thread held in registers
 constexpr int WS4 = (SEG - WR) / 4;       // float4 chunks per thread held in shared memory
 
-// dot product of 64 weights (48 registers + 16 shared) with 64 shared-memory values; packed FP32 FMA (FFMA2, sm_100+)
+// dot product of 64 weights (40 registers + 24 shared) with 64 shared-memory values; packed FP32 FMA (FFMA2, sm_100+)
 __device__ __forceinline__ float dot64_ffma2(const float2 (&w)[WR / 2], const float4* __restrict__ ws, int nthreads,
                                              const float* __restrict__ v) {
     const float4* v4 = reinterpret_cast<const float4*>(v);
-    float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+    // four independent accumulator chains (the packed FMA has ~4-cycle dependent latency) and the shared-memory operands
+    // of a whole group are fetched before they are consumed
+    float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f), a3 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k4 = 0; k4 < WR / 4; k4++) {
-        const float4 hh = v4[k4];
-        a0 = __ffma2_rn(w[2 * k4], make_float2(hh.x, hh.y), a0);
-        a1 = __ffma2_rn(w[2 * k4 + 1], make_float2(hh.z, hh.w), a1);
+    for (int k8 = 0; k8 < WR / 8; k8++) {
+        const float4 h0 = v4[2 * k8], h1 = v4[2 * k8 + 1];
+        a0 = __ffma2_rn(w[4 * k8], make_float2(h0.x, h0.y), a0);
+        a1 = __ffma2_rn(w[4 * k8 + 1], make_float2(h0.z, h0.w), a1);
+        a2 = __ffma2_rn(w[4 * k8 + 2], make_float2(h1.x, h1.y), a2);
+        a3 = __ffma2_rn(w[4 * k8 + 3], make_float2(h1.z, h1.w), a3);
     }
 #pragma unroll
-    for (int c = 0; c < WS4; c++) {
-        const float4 hh = v4[WR / 4 + c];
-        const float4 ww = ws[c * nthreads];
-        a0 = __ffma2_rn(make_float2(ww.x, ww.y), make_float2(hh.x, hh.y), a0);
-        a1 = __ffma2_rn(make_float2(ww.z, ww.w), make_float2(hh.z, hh.w), a1);
+    for (int c = 0; c < WS4; c += 2) {
+        const float4 h0 = v4[WR / 4 + c], h1 = v4[WR / 4 + c + 1];
+        const float4 w0 = ws[c * nthreads], w1 = ws[(c + 1) * nthreads];
+        a0 = __ffma2_rn(make_float2(w0.x, w0.y), make_float2(h0.x, h0.y), a0);
+        a1 = __ffma2_rn(make_float2(w0.z, w0.w), make_float2(h0.z, h0.w), a1);
+        a2 = __ffma2_rn(make_float2(w1.x, w1.y), make_float2(h1.x, h1.y), a2);
+        a3 = __ffma2_rn(make_float2(w1.z, w1.w), make_float2(h1.z, h1.w), a3);
     }
-    return (a0.x + a0.y) + (a1.x + a1.y);
+    return ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
 }
 
 template <int H, int CS>
@@ -191,7 +197,8 @@ __global__ void __launch_bounds__(GruCfg<H, CS>::NT_B, 1)
 gru_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ whh0, const float* __restrict__ whh1,
                const float* __restrict__ gates0, const float* __restrict__ gates1, const float* __restrict__ hprev0,
                const float* __restrict__ hprev1, float* __restrict__ dgi0, float* __restrict__ dgi1,
-               float* __restrict__ dghn0, float* __restrict__ dghn1, int B, int T) {
+               float* __restrict__ dghn0, float* __restrict__ dghn1, float* __restrict__ gbih0,
+               float* __restrict__ gbih1, float* __restrict__ gbhh0, float* __restrict__ gbhh1, int B, int T) {
     using Cfg = GruCfg<H, CS>;
     constexpr int HU = Cfg::HU, JSEGS = Cfg::JSEGS, NT = Cfg::NT_B;
     extern __shared__ __align__(16) float gru_smem[];
@@ -210,6 +217,9 @@ gru_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ whh0, c
     const float* hprev = dir ? hprev1 : hprev0;
     float* dgi = dir ? dgi1 : dgi0;
     float* dghn = dir ? dghn1 : dghn0;
+    float* gbih = dir ? gbih1 : gbih0;
+    float* gbhh = dir ? gbhh1 : gbhh0;
+    float sb_r = 0.f, sb_z = 0.f, sb_n = 0.f, sb_hn = 0.f;      // bias gradients = sums over time of the gate grads
 
     const int jseg = tid / HU, col = tid - jseg * HU;        // column u0+col of W_hh, rows jseg*64 .. +64
     float2 w[WR / 2];
@@ -270,6 +280,10 @@ gru_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ whh0, c
             dp[H] = dz_pre;
             dp[2 * H] = dn_pre;
             dghn[bt * H + u0 + gu] = dhn;
+            sb_r += dr_pre;
+            sb_z += dz_pre;
+            sb_n += dn_pre;
+            sb_hn += dhn;
         }
         if (is_gate) {
             if (CS > 1) {
@@ -300,6 +314,15 @@ gru_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ whh0, c
         }
         p_go = n_go; p_r = n_r; p_z = n_z; p_n = n_n; p_ghn = n_ghn; p_hp = n_hp;
         if (CS > 1) cur ^= 1;      // next step's remote writes must not race with slower CTAs still reading
+    }
+    if (active && gbih != nullptr) {
+        // b_ih and b_hh share the r and z gradients; the n gate differs (d n_pre vs d(hn) = d n_pre * r)
+        atomicAdd(&gbih[u0 + gu], sb_r);
+        atomicAdd(&gbih[H + u0 + gu], sb_z);
+        atomicAdd(&gbih[2 * H + u0 + gu], sb_n);
+        atomicAdd(&gbhh[u0 + gu], sb_r);
+        atomicAdd(&gbhh[H + u0 + gu], sb_z);
+        atomicAdd(&gbhh[2 * H + u0 + gu], sb_hn);
     }
 }
 
@@ -337,7 +360,8 @@ int run_fwd(const float* const gi[2], const float* const w_hh[2], const float* c
 
 template <int H, int CS, int NB>
 int run_bwd(const float* gout, const float* const w_hh[2], const float* const gates[2], const float* const hprev[2],
-            float* const dgi[2], float* const dghn[2], int B, int T, cudaStream_t s) {
+            float* const dgi[2], float* const dghn[2], float* const gb_ih[2], float* const gb_hh[2], int B, int T,
+            cudaStream_t s) {
     using Cfg = GruCfg<H, CS>;
     auto kern = gru_bwd_kernel<H, CS, NB>;
     dim3 grid(cdiv(B, NB) * CS, 2);
@@ -360,8 +384,12 @@ int run_bwd(const float* gout, const float* const w_hh[2], const float* const ga
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    for (int d = 0; d < 2; d++) {
+        SEDK_CUDA(cudaMemsetAsync(gb_ih[d], 0, (size_t)3 * H * sizeof(float), s));
+        SEDK_CUDA(cudaMemsetAsync(gb_hh[d], 0, (size_t)3 * H * sizeof(float), s));
+    }
     SEDK_CUDA(cudaLaunchKernelEx(&cfg, kern, gout, w_hh[0], w_hh[1], gates[0], gates[1], hprev[0], hprev[1], dgi[0],
-                                 dgi[1], dghn[0], dghn[1], B, T));
+                                 dgi[1], dghn[0], dghn[1], gb_ih[0], gb_ih[1], gb_hh[0], gb_hh[1], B, T));
     count_launch();
     return SEDK_OK;
 }
@@ -398,22 +426,22 @@ int launch_gru_seq_fwd(const float* const gi[2], const float* const w_hh[2], con
 }
 
 int launch_gru_seq_bwd(const float* gout, const float* const w_hh[2], const float* const gates[2],
-                       const float* const hprev[2], float* const dgi[2], float* const dghn[2], int B, int T, int H,
-                       cudaStream_t s) {
+                       const float* const hprev[2], float* const dgi[2], float* const dghn[2], float* const gb_ih[2],
+                       float* const gb_hh[2], int B, int T, int H, cudaStream_t s) {
     SEDK_PROF("gru_seq_bwd", s);
     if (H == 128) {
         switch (pick_nb(B, 1)) {
-            case 1: return run_bwd<128, 1, 1>(gout, w_hh, gates, hprev, dgi, dghn, B, T, s);
-            case 2: return run_bwd<128, 1, 2>(gout, w_hh, gates, hprev, dgi, dghn, B, T, s);
-            default: return run_bwd<128, 1, 4>(gout, w_hh, gates, hprev, dgi, dghn, B, T, s);
+            case 1: return run_bwd<128, 1, 1>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
+            case 2: return run_bwd<128, 1, 2>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
+            default: return run_bwd<128, 1, 4>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
         }
     }
-    if (H == 64) return run_bwd<64, 1, 2>(gout, w_hh, gates, hprev, dgi, dghn, B, T, s);
+    if (H == 64) return run_bwd<64, 1, 2>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
     if (H == 192) {
         switch (pick_nb(B, 3)) {
-            case 1: return run_bwd<192, 3, 1>(gout, w_hh, gates, hprev, dgi, dghn, B, T, s);
-            case 2: return run_bwd<192, 3, 2>(gout, w_hh, gates, hprev, dgi, dghn, B, T, s);
-            default: return run_bwd<192, 3, 4>(gout, w_hh, gates, hprev, dgi, dghn, B, T, s);
+            case 1: return run_bwd<192, 3, 1>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
+            case 2: return run_bwd<192, 3, 2>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
+            default: return run_bwd<192, 3, 4>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
         }
     }
     SEDK_UNSUPPORTED("GRU hidden size %d has no sm_100a instantiation (supported: 64, 128, 192)", H);

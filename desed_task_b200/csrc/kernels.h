@@ -25,8 +25,9 @@ int launch_conv3x3(const float* in, const float* wp, const float* bias, float* o
                    int cin, int cout, int precision, cudaStream_t s);
 // tcgen05 / TMEM / TMA implicit-GEMM variant for 128 -> 128 channels (TF32); conv_tc5.cu
 bool tc5_enabled();
+bool tc5_supports(int cin, int cout);
 int launch_conv3x3_tc5(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T,
-                       int F, cudaStream_t s);
+                       int F, int cin, int cout, cudaStream_t s);
 // gwpack[tap][co][ci] += sum_pix gz[pix][co] * x[pix + shift(tap)][ci]   (gwpack zeroed by the caller)
 int launch_conv_wgrad(const float* x, const float* gz, float* gwpack, int B, int T, int F, int cin, int cout,
                       int precision, cudaStream_t s);
@@ -65,10 +66,10 @@ int launch_colsum(const float* A, int M, int N, int lda, float* out, int accumul
 // one direction-pair launch: gi[dir] [B,T,3H] (= x W_ih^T + b_ih), out [B,T,2H]; saves gates/hprev when training
 int launch_gru_seq_fwd(const float* const gi[2], const float* const w_hh[2], const float* const b_hh[2], float* out,
                        float* const gates[2], float* const hprev[2], int B, int T, int H, int save, cudaStream_t s);
-// BPTT: gout [B,T,2H] -> dgi[dir] [B,T,3H] (written over gi) and dghn[dir] [B,T,H]
+// BPTT: gout [B,T,2H] -> dgi[dir] [B,T,3H] (written over gi), dghn[dir] [B,T,H] and the bias gradients gb_ih / gb_hh [3H]
 int launch_gru_seq_bwd(const float* gout, const float* const w_hh[2], const float* const gates[2],
-                       const float* const hprev[2], float* const dgi[2], float* const dghn[2], int B, int T, int H,
-                       cudaStream_t s);
+                       const float* const hprev[2], float* const dgi[2], float* const dghn[2], float* const gb_ih[2],
+                       float* const gb_hh[2], int B, int T, int H, cudaStream_t s);
 
 // ---- heads.cu -----------------------------------------------------------------------------------------------
 int launch_heads_fwd(const float* x, const float* dw, const float* db, const float* sw, const float* sb,
