@@ -65,6 +65,8 @@ _SIGS = {
     "sedk_device_cc": (i32, []),
     "sedk_sizeof_crnn_plan": (i32, []),
     "sedk_launch_count": (C.c_longlong, []),
+    "sedk_set_tcgen05": (i32, [i32]),
+    "sedk_get_tcgen05": (i32, []),
     "sedk_profile_enable": (i32, [i32]),
     "sedk_profile_report": (i32, [C.c_char_p, i32]),
     "sedk_logmel_fwd": (i32, [vp, i32, i32, C.POINTER(MelTables), vp, i64, i64, i64, i32, f32, f32, f32, vp, vp]),

@@ -304,14 +304,15 @@ int run_tc5_tiles(const float* in, const float* wp, const float* bias, float* ou
 
 }  // namespace
 
+static int g_tc5_on = -1;
 bool tc5_enabled() {
-    static int on = -1;
-    if (on < 0) {
+    if (g_tc5_on < 0) {
         const char* e = getenv("SEDK_DISABLE_TCGEN05");
-        on = (e != nullptr && e[0] == '1') ? 0 : 1;
+        g_tc5_on = (e != nullptr && e[0] == '1') ? 0 : 1;
     }
-    return on == 1;
+    return g_tc5_on == 1;
 }
+void tc5_set(int on) { g_tc5_on = on ? 1 : 0; }
 
 bool tc5_supports(int cin, int cout) {
     return (cin == 32 || cin == 64 || cin == 128) && (cout == 32 || cout == 64 || cout == 128);
@@ -331,3 +332,9 @@ int launch_conv3x3_tc5(const float* in, const float* wp, const float* bias, floa
 }
 
 }  // namespace sedk
+
+extern "C" int sedk_set_tcgen05(int on) {
+    sedk::tc5_set(on);
+    return SEDK_OK;
+}
+extern "C" int sedk_get_tcgen05(void) { return sedk::tc5_enabled() ? 1 : 0; }

@@ -25,6 +25,7 @@ int launch_conv3x3(const float* in, const float* wp, const float* bias, float* o
                    int cin, int cout, int precision, cudaStream_t s);
 // tcgen05 / TMEM / TMA implicit-GEMM variant for 128 -> 128 channels (TF32); conv_tc5.cu
 bool tc5_enabled();
+void tc5_set(int on);
 bool tc5_supports(int cin, int cout);
 int launch_conv3x3_tc5(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T,
                        int F, int cin, int cout, cudaStream_t s);

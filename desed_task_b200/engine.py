@@ -23,7 +23,7 @@ from .optim import FusedAdam, ema_alpha, flatten_parameters
 class TrainEngine:
     def __init__(self, student, mel_spec, batch_sizes, n_samples, opt=None, scheduler=None, teacher=None,
                  ema_factor=0.999, const_max=2.0, mixup_type=None, use_graph=True, process_group=None,
-                 grad_clip=0.0, emb_shape=None, class_masks=None):
+                 grad_clip=0.0, emb_shape=None, class_masks=None, distributed=True):
         self.student, self.teacher, self.mel_spec = student, teacher, mel_spec
         self.batch_sizes = list(batch_sizes)
         self.n_s, self.n_w = self.batch_sizes[0], self.batch_sizes[1]
@@ -39,7 +39,8 @@ class TrainEngine:
         self.use_graph = use_graph
         self.pg = process_group
         self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if distributed and (process_group is not None or
+                            (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
         self.grad_clip = grad_clip
         self.emb_shape = emb_shape
@@ -235,7 +236,8 @@ class TrainEngine:
             self._restore(snap)
             g = torch.cuda.CUDAGraph()
             n0 = lib().sedk_launch_count()
-            with torch.cuda.graph(g):
+            # thread_local: other threads (e.g. the NCCL watchdog polling events) must not invalidate the capture
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._device_part(mixing_graph)
             self.graph_kernels = int(lib().sedk_launch_count() - n0)
             self.graph = g

@@ -39,6 +39,11 @@ SEDK_API const char* sedk_last_error(void);
 SEDK_API int sedk_version(void);
 /* compute capability of the current device as major*10+minor (100 on B200); <0 on error */
 SEDK_API int sedk_device_cc(void);
+/* The convolutions with 32/64/128 channels run on tcgen05 (TMEM accumulators, TMA-fed) in the TF32 precision mode; this
+ * switch (default on; env SEDK_DISABLE_TCGEN05=1 turns it off) selects the legacy mma.sync kernels instead - kept for
+ * A/B parity tests. */
+SEDK_API int sedk_set_tcgen05(int on);
+SEDK_API int sedk_get_tcgen05(void);
 /* number of kernels this library has launched (or captured into a CUDA graph) so far in this process */
 SEDK_API long long sedk_launch_count(void);
 /* Optional eager-mode kernel timing: between sedk_profile_enable(1) and sedk_profile_report every launcher is bracketed by

@@ -109,6 +109,34 @@ def test_train_forward_backward_matches_oracle(dev, feats, tag, precision, tol_o
     assert np.abs(net.dense.weight.grad.cpu().numpy() - g["grad_dense_w_" + key]).max() < tol_grad * gscale
 
 
+def test_tcgen05_conv_matches_legacy_mma_path(dev, feats):
+    """A/B: the tcgen05/TMEM/TMA convolutions (layers with 32/64/128 channels, TF32 mode) against the mma.sync kernels of
+    the same layers - forward posteriors, BN statistics and every gradient.  Both are TF32 (the tcgen05 unit truncates the
+    fp32 operands, the legacy path rounds them), so they agree to TF32 noise, and both sit inside the 1e-3 budget."""
+    from desed_task_b200._lib import lib
+    cfg = dataclasses.replace(ocrnn.CFG_2023, dropout=0.0)
+    P = ocrnn.init_params(cfg, seed=42, trained_like=True)
+    res = {}
+    for on in (1, 0):
+        lib().sedk_set_tcgen05(on)
+        try:
+            assert lib().sedk_get_tcgen05() == on
+            net = build(cfg, P, dev, 0, specaugm_t_p=0.0, specaugm_f_p=0.0)
+            net.train()
+            s, w = net(feats.to(dev))
+            (s.mean() + w.mean()).backward()
+            res[on] = (s.detach().clone(), w.detach().clone(), {n: p.grad.clone() for n, p in net.named_parameters()},
+                       net.state_dict()["cnn.cnn.batchnorm5.running_var"].clone())
+        finally:
+            lib().sedk_set_tcgen05(1)
+    assert maxdiff(res[1][0], res[0][0]) < 5e-4 and maxdiff(res[1][1], res[0][1]) < 5e-4
+    assert maxdiff(res[1][3], res[0][3]) < 1e-3
+    gscale = max(g.abs().max().item() for g in res[0][2].values())
+    for n, g in res[0][2].items():
+        err = (res[1][2][n] - g).abs().max().item() / max(g.abs().max().item(), 1e-2 * gscale)
+        assert err < 2e-2, (n, err)
+
+
 def test_dropout_and_specaugment_statistics(dev, feats):
     """Train mode with the shipped dropout 0.5 + SpecAugment: outputs stay finite, differ run to run, backward runs, the
     same seed reproduces the same masks in backward (finite-difference check on one weight)."""
