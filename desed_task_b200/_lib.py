@@ -66,6 +66,7 @@ _SIGS = {
     "sedk_sizeof_crnn_plan": (i32, []),
     "sedk_launch_count": (C.c_longlong, []),
     "sedk_set_tcgen05": (i32, [i32]),
+    "sedk_set_gru_cluster": (i32, [i32]),
     "sedk_get_tcgen05": (i32, []),
     "sedk_profile_enable": (i32, [i32]),
     "sedk_profile_report": (i32, [C.c_char_p, i32]),
@@ -88,6 +89,8 @@ _SIGS = {
     "sedk_crnn_backward": (i32, [C.POINTER(CrnnPlan), vp]),
     "sedk_sed_loss": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp]),
     "sedk_sed_loss_dev": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "sedk_conv3x3": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "sedk_conv_wgrad": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "sedk_gemm": (i32, [i32, i32, i32, i32, i32, f32, vp, i32, vp, i32, f32, vp, i32, vp, i32, vp]),
 }
 

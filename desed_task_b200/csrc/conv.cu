@@ -639,6 +639,8 @@ static int run_wgrad_tiles(const float* x, const float* gz, float* gwp, int B, i
 
 int launch_conv_wgrad(const float* x, const float* gz, float* gwpack, int B, int T, int F, int cin, int cout,
                       int precision, cudaStream_t s) {
+    if (precision == 0 && tc5_enabled() && tc5_wgrad_supports(cin, cout))
+        return launch_conv_wgrad_tc5(x, gz, gwpack, B, T, F, cin, cout, s);
     char pname[64];
     snprintf(pname, sizeof(pname), "conv_wgrad_%dto%d_F%d", cin, cout, F);
     SEDK_PROF(pname, s);
@@ -652,3 +654,17 @@ int launch_conv_wgrad(const float* x, const float* gz, float* gwpack, int B, int
 }
 
 }  // namespace sedk
+
+extern "C" int sedk_conv3x3(const float* in, const float* wpack, const float* bias, float* out, double* stats, int B, int T,
+                            int F, int cin, int cout, int precision, void* stream) {
+    using namespace sedk;
+    SEDK_REQUIRE(in && wpack && out && B > 0 && T > 0 && F > 0, "sedk_conv3x3: bad arguments");
+    return launch_conv3x3(in, wpack, bias, out, stats, B, T, F, cin, cout, precision, (cudaStream_t)stream);
+}
+
+extern "C" int sedk_conv_wgrad(const float* x, const float* gz, float* gwpack, int B, int T, int F, int cin, int cout,
+                               int precision, void* stream) {
+    using namespace sedk;
+    SEDK_REQUIRE(x && gz && gwpack && B > 0 && T > 0 && F > 0, "sedk_conv_wgrad: bad arguments");
+    return launch_conv_wgrad(x, gz, gwpack, B, T, F, cin, cout, precision, (cudaStream_t)stream);
+}

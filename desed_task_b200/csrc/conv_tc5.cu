@@ -229,6 +229,154 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Weight gradient on tcgen05:  dW[tap][co][ci] = sum_pixels gz[pix][co] * x[pix + tap][ci]   (Cout = 128, Cin in {64, 128}).
+// UMMA with BOTH operands MN-major (the reduction index = pixels is the slow axis of the channels-last tensors; TF32
+// MN-major operands use the 32-byte-atom flavour of the 128-byte swizzle on both the TMA and the descriptor side):
+//   D[128 co x Cin] (+)= A^T B with A = gz tile [32 px x 128 co], B = shifted x tile [32 px x Cin], K = 8 pixels per MMA.
+// One CTA owns one kernel row (3 taps: dx = 0,1,2 at a fixed dy) and keeps the 3 accumulators (3 x Cin TMEM columns) resident
+// while it streams its share of the pixel tiles through a 3-stage TMA ring; gz is loaded once per stage and reused by the 3
+// taps.  The epilogue adds the accumulators into the packed gradient with 16-byte vector atomics.
+constexpr int WG_STAGES = 3;
+constexpr int WG_KPIX = 32;                           // pixels per stage
+constexpr int WG_CHUNK_BYTES = WG_KPIX * 128;         // one 32-channel chunk of one stage: 32 rows x 128 B
+constexpr int WG_THREADS = 192;
+
+// MN-major TF32 operands must use the "128B swizzle with 32B atoms" layout (UMMA LayoutType::SWIZZLE_128B_BASE32B = 1; TMA
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 B along MN, 32-byte chunks XOR-ed with (row % 4), 4-row K atoms.
+// LBO = stride between 32-element MN chunks, SBO = stride between 4-row K groups (512 B for consecutive rows).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+           (1ull << 46) | (1ull << 61);
+}
+
+template <int CIN, int TT, int TF>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_wgrad_tc5_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
+                      float* __restrict__ gwp, int T, int F, int total_tiles, int dbg) {
+    static_assert(TT * TF == WG_KPIX, "K tile must hold 32 pixels");
+    constexpr int COUT = 128;
+    constexpr int NCH = CIN / 32;                                   // 32-channel chunks of x
+    constexpr int A_BYTES = 4 * WG_CHUNK_BYTES;                     // 128 co
+    constexpr int B_BYTES = 3 * NCH * WG_CHUNK_BYTES;               // 3 taps
+    constexpr int STAGE = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = 3 * CIN <= 256 ? 256 : 512;
+    // D fp32, A/B tf32, A and B MN-major (bits 15, 16), N = CIN, M = 128
+    constexpr uint32_t IDESC = tc_idesc(CIN) | (1u << 15) | (1u << 16);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* aligned = smem_raw + (base - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(aligned + (size_t)WG_STAGES * STAGE);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + WG_STAGES;
+    uint64_t* accum = bars + 2 * WG_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dy = blockIdx.y;                                      // kernel row handled by this CTA
+    const int nTf = (F + TF - 1) / TF, nTt = (T + TT - 1) / TT;
+    if (tid == 0) {
+        for (int s = 0; s < WG_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accum, 1);
+        fence_mbar_init();
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmG) : "memory");
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmX) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+                const int s = it % WG_STAGES, ph = (it / WG_STAGES) & 1;
+                int r = tile;
+                const int b = r / (nTt * nTf);
+                r -= b * nTt * nTf;
+                const int t0 = (r / nTf) * TT, f0 = (r % nTf) * TF;
+                mbar_wait_u32(smem_u32(&empty[s]), ph ^ 1);
+                const uint32_t a_dst = base + s * STAGE, b_dst = a_dst + A_BYTES;
+                mbar_expect_tx(&full[s], STAGE);
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    tma_load_4d(a_dst + c * WG_CHUNK_BYTES, &tmG, smem_u32(&full[s]), c * 32, f0, t0, b);
+#pragma unroll
+                for (int dx = 0; dx < 3; dx++)
+#pragma unroll
+                    for (int c = 0; c < NCH; c++)
+                        tma_load_4d(b_dst + (dx * NCH + c) * WG_CHUNK_BYTES, &tmX, smem_u32(&full[s]), c * 32, f0 + dx - 1,
+                                    t0 + dy - 1, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int it = 0; it < my_tiles; it++) {
+                const int s = it % WG_STAGES, ph = (it / WG_STAGES) & 1;
+                mbar_wait_u32(smem_u32(&full[s]), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint32_t a_src = base + s * STAGE, b_src = a_src + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < WG_KPIX / 8; k++) {             // 8 pixels = one 1024-byte swizzle atom per MMA
+                    const uint64_t da = umma_desc_mn_sw128(a_src + k * 1024, WG_CHUNK_BYTES);
+#pragma unroll
+                    for (int dx = 0; dx < 3; dx++) {
+                        const uint64_t db = umma_desc_mn_sw128(b_src + dx * NCH * WG_CHUNK_BYTES + k * 1024, WG_CHUNK_BYTES);
+                        umma_tf32(tmem + (uint32_t)(dx * CIN), da, db, IDESC, (it | k) != 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(smem_u32(&empty[s]));
+            }
+            umma_commit(smem_u32(accum));
+        }
+    } else if (my_tiles > 0) {
+        const int q = warp & 3;
+        const int co = q * 32 + lane;
+        mbar_wait_u32(smem_u32(accum), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll 1
+        for (int dx = 0; dx < 3; dx++) {
+            float* grow = gwp + ((size_t)(dy * 3 + dx) * COUT + co) * CIN;
+#pragma unroll 1
+            for (int c = 0; c < NCH; c++) {
+                uint32_t v[32];
+                tmem_ld32(v, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(dx * CIN + c * 32));
+                if (dbg == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = __float_as_uint(1.0f);
+                }
+                if (dbg == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) atomicAdd(grow + c * 32 + j, __uint_as_float(v[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        atomicAdd(reinterpret_cast<float4*>(grow + c * 32) + j,
+                                  make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -302,6 +450,61 @@ int run_tc5_tiles(const float* in, const float* wp, const float* bias, float* ou
     return run_tc5<CIN, COUT, 64, 2>(tmA, tmB, bias, out, stats, B, T, F, s);
 }
 
+template <int CIN, int TT, int TF>
+int run_wgrad_tc5(const CUtensorMap& tmG, const CUtensorMap& tmX, float* gwp, int B, int T, int F, cudaStream_t s) {
+    auto kern = conv_wgrad_tc5_kernel<CIN, TT, TF>;
+    constexpr size_t smem = (size_t)WG_STAGES * (4 + 3 * (CIN / 32)) * WG_CHUNK_BYTES + 1024 + 256;
+    static bool cfg = false;
+    if (!cfg) {
+        int rc = opt_in_smem(kern, smem);
+        if (rc) return rc;
+        cfg = true;
+    }
+    const int tiles = B * cdiv(T, TT) * cdiv(F, TF);
+    int gx = num_sms() / 3;
+    if (gx > tiles) gx = tiles;
+    dim3 grid(gx, 3);
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("SEDK_WG_DBG"); dbg = e ? atoi(e) : 0; }
+    kern<<<grid, WG_THREADS, smem, s>>>(tmG, tmX, gwp, T, F, tiles, dbg);
+    SEDK_LAUNCH_CHECK("conv_wgrad_tc5_kernel");
+    return SEDK_OK;
+}
+
+template <int CIN>
+int run_wgrad_tc5_tiles(const float* x, const float* gz, float* gwp, int B, int T, int F, cudaStream_t s) {
+    EncodeTiledFn enc = encode_fn();
+    SEDK_REQUIRE(enc != nullptr, "conv_wgrad_tc5: cuTensorMapEncodeTiled is not available from the driver");
+    int TT, TF;
+    if (F >= 16) { TT = 2; TF = 16; }
+    else if (F > 4) { TT = 4; TF = 8; }
+    else if (F > 2) { TT = 8; TF = 4; }
+    else { TT = 16; TF = 2; }
+    CUtensorMap tmG, tmX;
+    cuuint32_t box[4] = {32, (cuuint32_t)TF, (cuuint32_t)TT, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    {
+        cuuint64_t dims[4] = {128, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
+        cuuint64_t strides[3] = {128 * 4, (cuuint64_t)F * 128 * 4, (cuuint64_t)T * F * 128 * 4};
+        CUresult r = enc(&tmG, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(gz), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SEDK_REQUIRE(r == CUDA_SUCCESS, "conv_wgrad_tc5: cuTensorMapEncodeTiled(gz) failed with %d", (int)r);
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)CIN, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)CIN * 4, (cuuint64_t)F * CIN * 4, (cuuint64_t)T * F * CIN * 4};
+        CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SEDK_REQUIRE(r == CUDA_SUCCESS, "conv_wgrad_tc5: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
+    }
+    if (TF == 16) return run_wgrad_tc5<CIN, 2, 16>(tmG, tmX, gwp, B, T, F, s);
+    if (TF == 8) return run_wgrad_tc5<CIN, 4, 8>(tmG, tmX, gwp, B, T, F, s);
+    if (TF == 4) return run_wgrad_tc5<CIN, 8, 4>(tmG, tmX, gwp, B, T, F, s);
+    return run_wgrad_tc5<CIN, 16, 2>(tmG, tmX, gwp, B, T, F, s);
+}
+
 }  // namespace
 
 static int g_tc5_on = -1;
@@ -329,6 +532,18 @@ int launch_conv3x3_tc5(const float* in, const float* wp, const float* bias, floa
     SEDK_TC5(32, 32) SEDK_TC5(128, 32) SEDK_TC5(32, 128)
 #undef SEDK_TC5
     SEDK_UNSUPPORTED("conv3x3_tc5: (cin=%d, cout=%d) has no tcgen05 instantiation", cin, cout);
+}
+
+bool tc5_wgrad_supports(int cin, int cout) { return cout == 128 && (cin == 64 || cin == 128); }
+
+int launch_conv_wgrad_tc5(const float* x, const float* gz, float* gwpack, int B, int T, int F, int cin, int cout,
+                          cudaStream_t s) {
+    char pname[64];
+    snprintf(pname, sizeof(pname), "conv_wgrad_tc5_%dto%d_F%d", cin, cout, F);
+    SEDK_PROF(pname, s);
+    SEDK_REQUIRE(tc5_wgrad_supports(cin, cout), "conv_wgrad_tc5: (cin=%d, cout=%d) not supported", cin, cout);
+    if (cin == 128) return run_wgrad_tc5_tiles<128>(x, gz, gwpack, B, T, F, s);
+    return run_wgrad_tc5_tiles<64>(x, gz, gwpack, B, T, F, s);
 }
 
 }  // namespace sedk

@@ -12,6 +12,7 @@
 // through distributed shared memory each step.
 #include "kernels.h"
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
@@ -27,12 +28,18 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2
 // The register file cannot hold all of W_hh next to the loop state (49 152 of 65 536 registers at H = 128: the first
 // version spilled inside the recurrence), so each thread keeps WR = 40 of its 64 weights in registers and the last 24 in
 // shared memory, laid out [chunk][thread] so that a warp's 16-byte reads are contiguous.
-constexpr int WR = 40;                    // weights per thread held in registers
-constexpr int WS4 = (SEG - WR) / 4;       // float4 chunks per thread held in shared memory
+// (with >= 768 threads per CTA; smaller CTAs - the cluster variants - keep all 64 in registers)
+template <int NT>
+struct WSplit {
+    static constexpr int WR = NT >= 700 ? 40 : 64;      // weights per thread held in registers
+    static constexpr int WS4 = (SEG - WR) / 4;          // float4 chunks per thread held in shared memory
+};
 
 // dot product of 64 weights (40 registers + 24 shared) with 64 shared-memory values; packed FP32 FMA (FFMA2, sm_100+)
+template <int WR>
 __device__ __forceinline__ float dot64_ffma2(const float2 (&w)[WR / 2], const float4* __restrict__ ws, int nthreads,
                                              const float* __restrict__ v) {
+    constexpr int WS4 = (SEG - WR) / 4;
     const float4* v4 = reinterpret_cast<const float4*>(v);
     // four independent accumulator chains (the packed FMA has ~4-cycle dependent latency) and the shared-memory operands
     // of a whole group are fetched before they are consumed
@@ -84,6 +91,7 @@ gru_fwd_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, con
                float* __restrict__ hprev0, float* __restrict__ hprev1, int B, int T, int save) {
     using Cfg = GruCfg<H, CS>;
     constexpr int HU = Cfg::HU, R = Cfg::R, SEGS = Cfg::SEGS, NT = Cfg::NT_F;
+    constexpr int WR = WSplit<NT>::WR, WS4 = WSplit<NT>::WS4;
     extern __shared__ __align__(16) float gru_smem[];
     float4* ws4 = reinterpret_cast<float4*>(gru_smem);                                  // [WS4][NT] float4
     float (*h_s)[NB][H] = reinterpret_cast<float (*)[NB][H]>(gru_smem + WS4 * NT * 4);  // [2][NB][H]
@@ -144,7 +152,7 @@ gru_fwd_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, con
             nin = gp[2 * H];
         }
 #pragma unroll
-        for (int nb = 0; nb < NB; nb++) part[seg][nb][row] = dot64_ffma2(w, ws4 + tid, NT, &h_s[cur][nb][seg * SEG]);
+        for (int nb = 0; nb < NB; nb++) part[seg][nb][row] = dot64_ffma2<WR>(w, ws4 + tid, NT, &h_s[cur][nb][seg * SEG]);
         __syncthreads();
         const int nxt = CS > 1 ? cur ^ 1 : cur;
         if (is_gate) {
@@ -201,6 +209,7 @@ gru_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ whh0, c
                float* __restrict__ gbih1, float* __restrict__ gbhh0, float* __restrict__ gbhh1, int B, int T) {
     using Cfg = GruCfg<H, CS>;
     constexpr int HU = Cfg::HU, JSEGS = Cfg::JSEGS, NT = Cfg::NT_B;
+    constexpr int WR = WSplit<NT>::WR, WS4 = WSplit<NT>::WS4;
     extern __shared__ __align__(16) float gru_smem[];
     float4* ws4 = reinterpret_cast<float4*>(gru_smem);                                  // [WS4][NT] float4
     // recurrent pre-activation grads (r, z, hn) of all units, double-buffered: [2][NB][3H]
@@ -304,7 +313,7 @@ gru_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ whh0, c
         if (CS > 1) cg::this_cluster().sync(); else __syncthreads();
         // dh_prev[u] += sum_j W_hh[j][u] * dgh[j]
 #pragma unroll
-        for (int nb = 0; nb < NB; nb++) part[jseg][nb][col] = dot64_ffma2(w, ws4 + tid, NT, &dgh_s[cur][nb][jseg * SEG]);
+        for (int nb = 0; nb < NB; nb++) part[jseg][nb][col] = dot64_ffma2<WR>(w, ws4 + tid, NT, &dgh_s[cur][nb][jseg * SEG]);
         __syncthreads();
         if (is_gate) {
             float s = dh_direct;
@@ -333,7 +342,7 @@ int run_fwd(const float* const gi[2], const float* const w_hh[2], const float* c
     static_assert(GruNbOk<H, CS, NB>::ok, "");
     auto kern = gru_fwd_kernel<H, CS, NB>;
     dim3 grid(cdiv(B, NB) * CS, 2);
-    const size_t smem = (size_t)(WS4 * Cfg::NT_F * 4 + 2 * NB * H + Cfg::SEGS * NB * Cfg::R) * sizeof(float);
+    const size_t smem = (size_t)(WSplit<Cfg::NT_F>::WS4 * Cfg::NT_F * 4 + 2 * NB * H + Cfg::SEGS * NB * Cfg::R) * sizeof(float);
     static bool configured = false;
     if (!configured) {
         int rc = opt_in_smem(kern, smem);
@@ -365,7 +374,7 @@ int run_bwd(const float* gout, const float* const w_hh[2], const float* const ga
     using Cfg = GruCfg<H, CS>;
     auto kern = gru_bwd_kernel<H, CS, NB>;
     dim3 grid(cdiv(B, NB) * CS, 2);
-    const size_t smem = (size_t)(WS4 * Cfg::NT_B * 4 + 2 * NB * 3 * H + Cfg::JSEGS * NB * Cfg::HU) * sizeof(float);
+    const size_t smem = (size_t)(WSplit<Cfg::NT_B>::WS4 * Cfg::NT_B * 4 + 2 * NB * 3 * H + Cfg::JSEGS * NB * Cfg::HU) * sizeof(float);
     static bool configured = false;
     if (!configured) {
         int rc = opt_in_smem(kern, smem);
@@ -394,6 +403,20 @@ int run_bwd(const float* gout, const float* const w_hh[2], const float* const ga
     return SEDK_OK;
 }
 
+// H = 128 can also run as a 2-CTA cluster (all weights in registers, half the issue work per SM, one DSMEM exchange
+// + cluster barrier per step); selected with sedk_set_gru_cluster(2) / env SEDK_GRU_CLUSTER=2 for A/B measurements
+int gru_cluster();
+}  // namespace
+int g_gru_cluster = -1;
+namespace {
+int gru_cluster() {
+    if (g_gru_cluster < 0) {
+        const char* e = getenv("SEDK_GRU_CLUSTER");
+        g_gru_cluster = (e != nullptr && e[0] == '2') ? 2 : 1;
+    }
+    return g_gru_cluster;
+}
+
 // batch rows per CTA: keep every (row, direction) pair on its own SM while they fit, then double up
 inline int pick_nb(int B, int CS) {
     const int sms = num_sms();
@@ -407,6 +430,8 @@ inline int pick_nb(int B, int CS) {
 int launch_gru_seq_fwd(const float* const gi[2], const float* const w_hh[2], const float* const b_hh[2], float* out,
                        float* const gates[2], float* const hprev[2], int B, int T, int H, int save, cudaStream_t s) {
     SEDK_PROF("gru_seq_fwd", s);
+    if (H == 128 && gru_cluster() == 2 && pick_nb(B, 2) == 1)
+        return run_fwd<128, 2, 1>(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
     if (H == 128) {
         switch (pick_nb(B, 1)) {
             case 1: return run_fwd<128, 1, 1>(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
@@ -429,6 +454,8 @@ int launch_gru_seq_bwd(const float* gout, const float* const w_hh[2], const floa
                        const float* const hprev[2], float* const dgi[2], float* const dghn[2], float* const gb_ih[2],
                        float* const gb_hh[2], int B, int T, int H, cudaStream_t s) {
     SEDK_PROF("gru_seq_bwd", s);
+    if (H == 128 && gru_cluster() == 2 && pick_nb(B, 2) == 1)
+        return run_bwd<128, 2, 1>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
     if (H == 128) {
         switch (pick_nb(B, 1)) {
             case 1: return run_bwd<128, 1, 1>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
@@ -448,3 +475,8 @@ int launch_gru_seq_bwd(const float* gout, const float* const w_hh[2], const floa
 }
 
 }  // namespace sedk
+
+extern "C" int sedk_set_gru_cluster(int cs) {
+    sedk::g_gru_cluster = (cs == 2) ? 2 : 1;
+    return SEDK_OK;
+}

@@ -27,6 +27,9 @@ int launch_conv3x3(const float* in, const float* wp, const float* bias, float* o
 bool tc5_enabled();
 void tc5_set(int on);
 bool tc5_supports(int cin, int cout);
+bool tc5_wgrad_supports(int cin, int cout);
+int launch_conv_wgrad_tc5(const float* x, const float* gz, float* gwpack, int B, int T, int F, int cin, int cout,
+                          cudaStream_t s);
 int launch_conv3x3_tc5(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T,
                        int F, int cin, int cout, cudaStream_t s);
 // gwpack[tap][co][ci] += sum_pix gz[pix][co] * x[pix + shift(tap)][ci]   (gwpack zeroed by the caller)

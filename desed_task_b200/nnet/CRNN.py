@@ -397,6 +397,9 @@ class CRNN(nn.Module):
 
     def _launch_backward(self, ws, gstrong, gweak):
         plan = ws.plan
+        # parameters may have been re-pointed since the forward (flatten_parameters on the first EMA/optimizer call
+        # copies them into one flat buffer and frees the old storages): never read weights through stale pointers
+        ws.bind_params(self)
         gs = gstrong.float().contiguous() if gstrong is not None else None
         gw = gweak.float().contiguous() if gweak is not None else None
         plan.gstrong, plan.gweak = _vp(gs), _vp(gw)
@@ -458,6 +461,7 @@ class CRNN(nn.Module):
     def backward_direct(self, ws, gstrong, gweak):
         """Runs sedk_crnn_backward; returns the flat gradient buffer (parameters() order, overwritten each call)."""
         plan = ws.plan
+        ws.bind_params(self)
         plan.gstrong, plan.gweak = _vp(gstrong), _vp(gweak)
         ws.keep_g = (gstrong, gweak)
         check(lib().sedk_crnn_backward(ctypes.byref(plan), stream_ptr()), "sedk_crnn_backward")

@@ -44,6 +44,8 @@ SEDK_API int sedk_device_cc(void);
  * A/B parity tests. */
 SEDK_API int sedk_set_tcgen05(int on);
 SEDK_API int sedk_get_tcgen05(void);
+/* H = 128 GRU recurrence as a 2-CTA cluster (cs = 2) instead of one CTA per (row, direction) (cs = 1, default) */
+SEDK_API int sedk_set_gru_cluster(int cs);
 /* number of kernels this library has launched (or captured into a CUDA graph) so far in this process */
 SEDK_API long long sedk_launch_count(void);
 /* Optional eager-mode kernel timing: between sedk_profile_enable(1) and sedk_profile_report every launcher is bracketed by
@@ -255,6 +257,16 @@ SEDK_API int sedk_sed_loss(const float* strong, const float* weak, const float* 
 SEDK_API int sedk_sed_loss_dev(const float* strong, const float* weak, const float* t_strong, const float* t_weak,
                       const float* labels, const float* labels_weak, int B, int C, int T, int n_strong, int n_weak,
                       const float* cons_weight_dev, float* losses, float* gstrong, float* gweak, void* stream);
+
+/* Stand-alone entry points of the two convolution building blocks (channels-last tensors, 3x3 / pad 1 / stride 1), used by the
+ * unit tests and micro-benchmarks; inside the network they are driven through sedk_crnn_forward / backward.
+ *   sedk_conv3x3   : out[B,T,F,cout] = bias + conv(in[B,T,F,cin], wpack[9][cout][cin]);  stats (double[2*cout], may be NULL)
+ *                    accumulates per-channel sum and sum of squares (BatchNorm statistics).
+ *   sedk_conv_wgrad: gwpack[9][cout][cin] += sum_pixels gz[pix][cout] * x[pix + tap][cin]   (gwpack pre-zeroed by the caller) */
+SEDK_API int sedk_conv3x3(const float* in, const float* wpack, const float* bias, float* out, double* stats, int B, int T,
+                 int F, int cin, int cout, int precision, void* stream);
+SEDK_API int sedk_conv_wgrad(const float* x, const float* gz, float* gwpack, int B, int T, int F, int cin, int cout,
+                    int precision, void* stream);
 
 /* plain GEMM building block (TF32 / 3xTF32 mma): C[M,N] = alpha*op(A)op(B) + beta*C + bias[n]
  * transA 0: A is [M,K] (lda), 1: A is [K,M];  transB 0: B is [K,N] (ldb), 1: B is [N,K]. */

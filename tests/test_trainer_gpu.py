@@ -87,7 +87,11 @@ def test_training_step_autograd_path(dev, seed):
     assert abs(mod.logged["train/weight"] - ref["weight"]) < 1e-9
     mod.on_before_zero_grad()
     mod.opt.zero_grad()
+    # the first EMA call flattens the student's parameters into one buffer and frees their old storages: poison what the
+    # caching allocator hands back, so a backward that still read weights through the forward's pointers cannot pass
+    junk = [torch.full_like(p, float("nan")) for p in mod.sed_student.parameters()]
     loss.backward()
+    del junk
     gscale = max(g.abs().max().item() for g in rgrads.values())
     for n, p in mod.sed_student.named_parameters():
         if ".conv" in n and n.endswith(".bias"):
