@@ -68,6 +68,8 @@ _SIGS = {
     "sedk_set_tcgen05": (i32, [i32]),
     "sedk_set_gru_cluster": (i32, [i32]),
     "sedk_get_tcgen05": (i32, []),
+    "sedk_set_option": (i32, [C.c_char_p, i32]),
+    "sedk_get_option": (i32, [C.c_char_p, i32]),
     "sedk_profile_enable": (i32, [i32]),
     "sedk_profile_report": (i32, [C.c_char_p, i32]),
     "sedk_logmel_fwd": (i32, [vp, i32, i32, C.POINTER(MelTables), vp, i64, i64, i64, i32, f32, f32, f32, vp, vp]),

@@ -550,6 +550,9 @@ int launch_bnglu_pool_fwd(const float* z, const float* bn, const float* glu_w, c
     char pname[64];
     snprintf(pname, sizeof(pname), "bnglu_pool_fwd_c%d", C);
     SEDK_PROF(pname, s);
+    if (bnglu_small_supports(B, T, F, C, pt, pf))
+        return launch_bnglu_small_fwd(z, bn, glu_w, glu_b, out, B, T, F, C, pt, pf, drop_p, seed, seed_dev, drop_stream,
+                                      precision, s);
     TileGeom gm = make_geom(T, F, pt, pf);
     SEDK_REQUIRE(geom_ok(gm), "bnglu_pool: pooling (%d,%d) on a %dx%d map is not supported", pt, pf, T, F);
     switch (C) {
@@ -571,6 +574,9 @@ int launch_bnglu_pool_bwd(const float* z, const float* bn, const float* glu_w, c
     TileGeom gm = make_geom(T, F, pt, pf);
     SEDK_REQUIRE(geom_ok(gm), "bnglu_pool: pooling (%d,%d) on a %dx%d map is not supported", pt, pf, T, F);
     if (gm.Te != T || gm.Fe != F) SEDK_CUDA(cudaMemsetAsync(gy, 0, (size_t)B * T * F * C * sizeof(float), s));
+    if (bnglu_small_supports(B, T, F, C, pt, pf))
+        return launch_bnglu_small_bwd(z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, B, T, F, C, pt, pf, drop_p, seed,
+                                      seed_dev, drop_stream, precision, s);
     switch (C) {
         case 16: return run_bwd<16>(z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, B, gm, drop_p, seed, seed_dev, drop_stream, precision, s);
         case 32: return run_bwd<32>(z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, B, gm, drop_p, seed, seed_dev, drop_stream, precision, s);

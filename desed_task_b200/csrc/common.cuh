@@ -14,6 +14,9 @@ namespace sedk {
 void set_error(const char* fmt, ...);
 int  check_launch(const char* what);
 void count_launch();
+// named kernel-variant switches (sedk_set_option / env SEDK_<NAME>)
+int  get_option(const char* name, int dflt);
+void set_option(const char* name, int value);
 // RAII device-timing scope around one launcher (no-op unless sedk_profile_enable(1) and the stream is not capturing)
 struct ProfScope {
     ProfScope(const char* name, cudaStream_t s);

@@ -2,6 +2,8 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
+#include <ctype.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -19,6 +21,21 @@ void set_error(const char* fmt, ...) {
 
 static long long g_launches = 0;
 void count_launch() { g_launches++; }
+
+// ---- named integer options (kernel-variant switches for A/B measurements and parity tests); default from the environment
+// variable SEDK_<NAME> (upper case) on first use, else the caller's default
+static std::map<std::string, int> g_opts;
+int get_option(const char* name, int dflt) {
+    auto it = g_opts.find(name);
+    if (it != g_opts.end()) return it->second;
+    std::string env = "SEDK_";
+    for (const char* c = name; *c; c++) env += (char)toupper(*c);
+    const char* e = getenv(env.c_str());
+    int v = (e != nullptr && e[0] != 0) ? atoi(e) : dflt;
+    g_opts[name] = v;
+    return v;
+}
+void set_option(const char* name, int value) { g_opts[name] = value; }
 
 // ---- optional per-launcher device timing (eager mode only; never enabled inside a timed benchmark region)
 struct ProfEntry { std::string name; cudaEvent_t a, b; };
@@ -64,6 +81,13 @@ extern "C" int sedk_device_cc(void) {
 }
 extern "C" int sedk_sizeof_crnn_plan(void) { return (int)sizeof(sedk_crnn_plan); }
 extern "C" long long sedk_launch_count(void) { return sedk::g_launches; }
+
+extern "C" int sedk_set_option(const char* name, int value) {
+    if (name == nullptr) return SEDK_ERR_INVALID;
+    sedk::set_option(name, value);
+    return SEDK_OK;
+}
+extern "C" int sedk_get_option(const char* name, int dflt) { return name ? sedk::get_option(name, dflt) : dflt; }
 
 extern "C" int sedk_profile_enable(int on) {
     using namespace sedk;

@@ -335,6 +335,321 @@ gru_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ whh0, c
     }
 }
 
+// ================================================================================================================
+// Second-generation recurrence for H = 128 ("v2"), one batch row per CTA.  ncu on the first-generation kernel: 1460
+// shared-memory wavefronts per time step (h broadcast + smem-resident weights + partial sums) and two barriers, ~2100
+// cycles per step.  v2:
+//   forward : 512 threads = 128 hidden units x 4 k-lanes.  A quad owns the r, z, n rows of one unit; lane kl holds the
+//             3 x 32 weights of k in [32 kl, 32 kl + 32) (80 in registers, 16 in shared memory), reads its 32 h values as
+//             8 LDS.128 (h is stored with 4 floats of padding per 32 so the four lanes of a quad hit different banks),
+//             reduces the three partial sums over the quad with 6 shuffles and finishes the cell redundantly in all four
+//             lanes.  The new h goes to the other half of a double buffer: ONE __syncthreads per step.
+//   backward: 512 threads = 64 unit pairs x 8 j-lanes.  An octet owns columns (2o, 2o+1) of W_hh; lane l8 holds the
+//             2 x 48 weights of rows j in [48 l8, 48 l8 + 48) and reads dgh[j] as 12 LDS.128 (padding 4 per 48);
+//             a 3-shuffle exchange/reduce leaves d h_prev of unit 2o in lanes 0-3 and of unit 2o+1 in lanes 4-7, where
+//             the gate gradients of the next (earlier) step are computed - no shared-memory partials, one barrier per step.
+// Per-step integer work is kept to pointer increments: every global array is walked with a per-lane pointer and a
+// per-lane stride, and each lane of a quad owns two of the six stores of its unit.
+constexpr int V2_H = 128;
+constexpr int V2_NT = 512;
+constexpr int V2_WS4 = 4;            // float4 chunks of weights per thread kept in shared memory (16 of 96 weights)
+constexpr int V2_HPAD = 36 * 4;      // padded h buffer: k -> k + 4 (k / 32)
+constexpr int V2_DPAD = 52 * 8;      // padded dgh buffer: j -> j + 4 (j / 48)
+
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+// MUFU-only gate nonlinearities without the range-check code of __expf / __fdividef (inf / 0 propagate to the right limits)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lean_sigmoid(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float lean_tanh(float x) {
+    return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * x)), 1.0f);
+}
+
+__global__ void __launch_bounds__(V2_NT, 1)
+gru_fwd_v2_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, const float* __restrict__ whh0,
+                  const float* __restrict__ whh1, const float* __restrict__ bhh0, const float* __restrict__ bhh1,
+                  float* __restrict__ out, float* __restrict__ gates0, float* __restrict__ gates1,
+                  float* __restrict__ hprev0, float* __restrict__ hprev1, int T, int save) {
+    constexpr int H = V2_H, NT = V2_NT;
+    extern __shared__ __align__(16) float gru_smem[];
+    float4* ws4 = reinterpret_cast<float4*>(gru_smem);            // [V2_WS4][NT]
+    float* h_s = gru_smem + V2_WS4 * NT * 4;                      // [2][V2_HPAD]
+    const int tid = threadIdx.x;
+    const int dir = blockIdx.y;
+    const int b = blockIdx.x;
+    const int u = tid >> 2, kl = tid & 3;
+    const float* whh = dir ? whh1 : whh0;
+    const float* bhh = dir ? bhh1 : bhh0;
+
+    float2 wr[16], wz[16], wn[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const int k = 32 * kl + 4 * c;
+        const float4 a = *reinterpret_cast<const float4*>(whh + (size_t)u * H + k);
+        const float4 bz = *reinterpret_cast<const float4*>(whh + (size_t)(H + u) * H + k);
+        const float4 n = *reinterpret_cast<const float4*>(whh + (size_t)(2 * H + u) * H + k);
+        wr[2 * c] = lo2(a); wr[2 * c + 1] = hi2(a);
+        wz[2 * c] = lo2(bz); wz[2 * c + 1] = hi2(bz);
+        if (c < 4) { wn[2 * c] = lo2(n); wn[2 * c + 1] = hi2(n); }
+        else ws4[(c - 4) * NT + tid] = n;
+    }
+    for (int i = tid; i < 2 * V2_HPAD; i += NT) h_s[i] = 0.f;
+    const float bhr = bhh[u], bhz = bhh[H + u], bhn = bhh[2 * H + u];
+
+    // per-lane walking pointers (time stride +-1 step)
+    const int t0 = dir ? T - 1 : 0;
+    const ptrdiff_t ts = dir ? -1 : 1;
+    const size_t bt0 = (size_t)b * T + t0;
+    const float* gp = (dir ? gi1 : gi0) + bt0 * 3 * H + u;
+    const ptrdiff_t gstep = ts * 3 * H;
+    // lane 0: out <- h_new, hprev <- h_old;  lane 1: gates r, z;  lane 2: gates n, hn;  lane 3: nothing
+    float* gbase = (dir ? gates1 : gates0) + bt0 * 4 * H + u;
+    float* pa = kl == 0 ? out + bt0 * 2 * H + dir * H + u : (kl == 1 ? gbase : gbase + 2 * H);
+    float* pb = kl == 0 ? (dir ? hprev1 : hprev0) + bt0 * H + u : (kl == 1 ? gbase + H : gbase + 3 * H);
+    const ptrdiff_t sa = ts * (kl == 0 ? 2 * H : 4 * H), sb = ts * (kl == 0 ? H : 4 * H);
+    const bool do_a = kl == 0 || (save != 0 && kl < 3);
+    const bool do_b = save != 0 && kl < 3;
+    const float* hrd = h_s + 36 * kl;                             // this lane's 32 h values (padded layout), buffer 0
+    float* hwr = h_s + V2_HPAD + u + 4 * (u >> 5);                // where lane 0 of the quad publishes h_new, buffer 1
+    float hval = 0.f;
+    float gir = gp[0] + bhr, giz = gp[H] + bhz, gin = gp[2 * H];
+    __syncthreads();
+
+    for (int step = 0; step < T; step++) {
+        float nir = 0.f, niz = 0.f, nin = 0.f;
+        if (step + 1 < T) {
+            gp += gstep;
+            nir = gp[0]; niz = gp[H]; nin = gp[2 * H];
+        }
+        float2 ar0 = make_float2(0.f, 0.f), ar1 = ar0, az0 = ar0, az1 = ar0, an0 = ar0, an1 = ar0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const float4 h4 = *reinterpret_cast<const float4*>(hrd + 4 * c);
+            const float2 hl = lo2(h4), hh = hi2(h4);
+            ar0 = __ffma2_rn(wr[2 * c], hl, ar0);
+            ar1 = __ffma2_rn(wr[2 * c + 1], hh, ar1);
+            az0 = __ffma2_rn(wz[2 * c], hl, az0);
+            az1 = __ffma2_rn(wz[2 * c + 1], hh, az1);
+            if (c < 4) {
+                an0 = __ffma2_rn(wn[2 * c], hl, an0);
+                an1 = __ffma2_rn(wn[2 * c + 1], hh, an1);
+            } else {
+                const float4 w4 = ws4[(c - 4) * NT + tid];
+                an0 = __ffma2_rn(lo2(w4), hl, an0);
+                an1 = __ffma2_rn(hi2(w4), hh, an1);
+            }
+        }
+        float sr = (ar0.x + ar0.y) + (ar1.x + ar1.y);
+        float sz = (az0.x + az0.y) + (az1.x + az1.y);
+        float sn = (an0.x + an0.y) + (an1.x + an1.y);
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            sr += __shfl_xor_sync(0xffffffffu, sr, o);
+            sz += __shfl_xor_sync(0xffffffffu, sz, o);
+            sn += __shfl_xor_sync(0xffffffffu, sn, o);
+        }
+        const float ghn = sn + bhn;
+        const float r = lean_sigmoid(gir + sr);
+        const float zg = lean_sigmoid(giz + sz);
+        const float n = lean_tanh(fmaf(r, ghn, gin));
+        const float hnew = fmaf(zg, hval - n, n);                 // (1 - z) n + z h
+        if (kl == 0) *hwr = hnew;
+        if (do_a) *pa = kl == 0 ? hnew : (kl == 1 ? r : n);
+        if (do_b) *pb = kl == 0 ? hval : (kl == 1 ? zg : ghn);
+        pa += sa;
+        pb += sb;
+        hval = hnew;
+        gir = nir + bhr; giz = niz + bhz; gin = nin;
+        // swap the double buffer: readers move to the buffer just written
+        const ptrdiff_t flip = (step & 1) ? -V2_HPAD : V2_HPAD;
+        hrd += flip;
+        hwr -= flip;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(V2_NT, 1)
+gru_bwd_v2_kernel(const float* __restrict__ gout, const float* __restrict__ whh0, const float* __restrict__ whh1,
+                  const float* __restrict__ gates0, const float* __restrict__ gates1, const float* __restrict__ hprev0,
+                  const float* __restrict__ hprev1, float* __restrict__ dgi0, float* __restrict__ dgi1,
+                  float* __restrict__ dghn0, float* __restrict__ dghn1, float* __restrict__ gbih0,
+                  float* __restrict__ gbih1, float* __restrict__ gbhh0, float* __restrict__ gbhh1, int T) {
+    constexpr int H = V2_H, NT = V2_NT;
+    extern __shared__ __align__(16) float gru_smem[];
+    float4* ws4 = reinterpret_cast<float4*>(gru_smem);            // [V2_WS4][NT]
+    float* dgh_s = gru_smem + V2_WS4 * NT * 4;                    // [2][V2_DPAD]: d(r_pre), d(z_pre), d(hn), padded
+    const int tid = threadIdx.x;
+    const int dir = blockIdx.y;
+    const int b = blockIdx.x;
+    const int o = tid >> 3, l8 = tid & 7;
+    const int ua = 2 * o;                       // columns ua, ua + 1 of W_hh
+    const int um = ua + (l8 >> 2);              // the unit whose cell gradient this lane computes
+    const int sub = l8 & 3;
+    const float* whh = dir ? whh1 : whh0;
+    float* gbih = dir ? gbih1 : gbih0;
+    float* gbhh = dir ? gbhh1 : gbhh0;
+
+    float2 wa[24], wb[16];
+#pragma unroll
+    for (int c = 0; c < 12; c++) {
+        const float* wp = whh + (size_t)(48 * l8 + 4 * c) * H + ua;
+        const float2 r0 = *reinterpret_cast<const float2*>(wp);
+        const float2 r1 = *reinterpret_cast<const float2*>(wp + H);
+        const float2 r2 = *reinterpret_cast<const float2*>(wp + 2 * H);
+        const float2 r3 = *reinterpret_cast<const float2*>(wp + 3 * H);
+        wa[2 * c] = make_float2(r0.x, r1.x);
+        wa[2 * c + 1] = make_float2(r2.x, r3.x);
+        if (c < 8) {
+            wb[2 * c] = make_float2(r0.y, r1.y);
+            wb[2 * c + 1] = make_float2(r2.y, r3.y);
+        } else {
+            ws4[(c - 8) * NT + tid] = make_float4(r0.y, r1.y, r2.y, r3.y);
+        }
+    }
+    for (int i = tid; i < 2 * V2_DPAD; i += NT) dgh_s[i] = 0.f;
+    float sb_r = 0.f, sb_z = 0.f, sb_n = 0.f, sb_hn = 0.f;
+
+    // processing order: time index t = dir ? T-1-step : step for step = T-1 .. 0
+    const int t0 = dir ? 0 : T - 1;
+    const ptrdiff_t ts = dir ? 1 : -1;
+    const size_t bt0 = (size_t)b * T + t0;
+    const float* gop = gout + bt0 * 2 * H + dir * H + um;
+    const float* gsp = (dir ? gates1 : gates0) + bt0 * 4 * H + um;
+    const float* hpp = (dir ? hprev1 : hprev0) + bt0 * H + um;
+    // lane sub 0: dgi r, z;  sub 1: dgi n, dghn;  sub 2: the three shared-memory values;  sub 3: nothing
+    float* dgb = (dir ? dgi1 : dgi0) + bt0 * 3 * H + um;
+    float* pa = sub == 0 ? dgb : dgb + 2 * H;
+    float* pb = sub == 0 ? dgb + H : (dir ? dghn1 : dghn0) + bt0 * H + um;
+    const ptrdiff_t sa = ts * 3 * H, sbs = ts * (sub == 0 ? 3 * H : H);
+    const bool do_g = sub < 2;
+    // padded positions of (r, z, hn) of unit um in the dgh buffer, and of this lane's 48-row slice
+    const int jr = um, jz = H + um, jn = 2 * H + um;
+    float* dwr = dgh_s + jr + 4 * (jr / 48);
+    const int offz = (jz + 4 * (jz / 48)) - (jr + 4 * (jr / 48)), offn = (jn + 4 * (jn / 48)) - (jr + 4 * (jr / 48));
+    const float* drd = dgh_s + 52 * l8;
+    float dh = 0.f;
+    float p_go = gop[0], p_r = gsp[0], p_z = gsp[H], p_n = gsp[2 * H], p_ghn = gsp[3 * H], p_hp = hpp[0];
+    __syncthreads();
+
+    for (int step = T - 1; step >= 0; step--) {
+        // saved activations of the next processed step, one step ahead of their use
+        float n_go = 0.f, n_r = 0.f, n_z = 0.f, n_n = 0.f, n_ghn = 0.f, n_hp = 0.f;
+        if (step > 0) {
+            gop += ts * 2 * H;
+            gsp += ts * 4 * H;
+            hpp += ts * H;
+            n_go = gop[0];
+            n_r = gsp[0]; n_z = gsp[H]; n_n = gsp[2 * H]; n_ghn = gsp[3 * H];
+            n_hp = hpp[0];
+        }
+        const float g = p_go + dh;
+        const float dn = g * (1.0f - p_z);
+        const float dz = g * (p_hp - p_n);
+        const float dh_direct = g * p_z;
+        const float dn_pre = dn * (1.0f - p_n * p_n);
+        const float dz_pre = dz * p_z * (1.0f - p_z);
+        const float dr_pre = dn_pre * p_ghn * p_r * (1.0f - p_r);
+        const float dhn = dn_pre * p_r;
+        if (do_g) {
+            *pa = sub == 0 ? dr_pre : dn_pre;
+            *pb = sub == 0 ? dz_pre : dhn;
+        } else if (sub == 2) {
+            dwr[0] = dr_pre;
+            dwr[offz] = dz_pre;
+            dwr[offn] = dhn;
+        }
+        pa += sa;
+        pb += sbs;
+        sb_r += dr_pre; sb_z += dz_pre; sb_n += dn_pre; sb_hn += dhn;
+        p_go = n_go; p_r = n_r; p_z = n_z; p_n = n_n; p_ghn = n_ghn; p_hp = n_hp;
+        __syncthreads();
+        // d h_prev[u] = dh_direct[u] + sum_j W_hh[j][u] * dgh[j]
+        float2 aa0 = make_float2(0.f, 0.f), aa1 = aa0, ab0 = aa0, ab1 = aa0;
+#pragma unroll
+        for (int c = 0; c < 12; c++) {
+            const float4 d4 = *reinterpret_cast<const float4*>(drd + 4 * c);
+            const float2 dl = lo2(d4), dhh = hi2(d4);
+            aa0 = __ffma2_rn(wa[2 * c], dl, aa0);
+            aa1 = __ffma2_rn(wa[2 * c + 1], dhh, aa1);
+            if (c < 8) {
+                ab0 = __ffma2_rn(wb[2 * c], dl, ab0);
+                ab1 = __ffma2_rn(wb[2 * c + 1], dhh, ab1);
+            } else {
+                const float4 w4 = ws4[(c - 8) * NT + tid];
+                ab0 = __ffma2_rn(lo2(w4), dl, ab0);
+                ab1 = __ffma2_rn(hi2(w4), dhh, ab1);
+            }
+        }
+        const float sa_ = (aa0.x + aa0.y) + (aa1.x + aa1.y);
+        const float sb_ = (ab0.x + ab0.y) + (ab1.x + ab1.y);
+        const bool upper = (l8 & 4) != 0;
+        float keep = upper ? sb_ : sa_;
+        keep += __shfl_xor_sync(0xffffffffu, upper ? sa_ : sb_, 4);
+        keep += __shfl_xor_sync(0xffffffffu, keep, 2);
+        keep += __shfl_xor_sync(0xffffffffu, keep, 1);
+        dh = dh_direct + keep;
+        // the next step's gate writes go to the other buffer: no second barrier needed
+        const ptrdiff_t flip = ((T - 1 - step) & 1) ? -V2_DPAD : V2_DPAD;
+        drd += flip;
+        dwr += flip;
+    }
+    if (sub == 0 && gbih != nullptr) {
+        // b_ih and b_hh share the r and z gradients; the n gate differs (d n_pre vs d(hn) = d n_pre * r)
+        atomicAdd(&gbih[um], sb_r);
+        atomicAdd(&gbih[H + um], sb_z);
+        atomicAdd(&gbih[2 * H + um], sb_n);
+        atomicAdd(&gbhh[um], sb_r);
+        atomicAdd(&gbhh[H + um], sb_z);
+        atomicAdd(&gbhh[2 * H + um], sb_hn);
+    }
+}
+
+int run_fwd_v2(const float* const gi[2], const float* const w_hh[2], const float* const b_hh[2], float* out,
+               float* const gates[2], float* const hprev[2], int B, int T, int save, cudaStream_t s) {
+    auto kern = gru_fwd_v2_kernel;
+    const size_t smem = (size_t)(V2_WS4 * V2_NT * 4 + 2 * V2_HPAD) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        int rc = opt_in_smem(kern, smem);
+        if (rc) return rc;
+        configured = true;
+    }
+    kern<<<dim3(B, 2), V2_NT, smem, s>>>(gi[0], gi[1], w_hh[0], w_hh[1], b_hh[0], b_hh[1], out, gates[0], gates[1],
+                                         hprev[0], hprev[1], T, save);
+    SEDK_LAUNCH_CHECK("gru_fwd_v2_kernel");
+    return SEDK_OK;
+}
+
+int run_bwd_v2(const float* gout, const float* const w_hh[2], const float* const gates[2], const float* const hprev[2],
+               float* const dgi[2], float* const dghn[2], float* const gb_ih[2], float* const gb_hh[2], int B, int T,
+               cudaStream_t s) {
+    auto kern = gru_bwd_v2_kernel;
+    const size_t smem = (size_t)(V2_WS4 * V2_NT * 4 + 2 * V2_DPAD) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        int rc = opt_in_smem(kern, smem);
+        if (rc) return rc;
+        configured = true;
+    }
+    for (int d = 0; d < 2; d++) {
+        SEDK_CUDA(cudaMemsetAsync(gb_ih[d], 0, (size_t)3 * V2_H * sizeof(float), s));
+        SEDK_CUDA(cudaMemsetAsync(gb_hh[d], 0, (size_t)3 * V2_H * sizeof(float), s));
+    }
+    kern<<<dim3(B, 2), V2_NT, smem, s>>>(gout, w_hh[0], w_hh[1], gates[0], gates[1], hprev[0], hprev[1], dgi[0], dgi[1],
+                                         dghn[0], dghn[1], gb_ih[0], gb_ih[1], gb_hh[0], gb_hh[1], T);
+    SEDK_LAUNCH_CHECK("gru_bwd_v2_kernel");
+    return SEDK_OK;
+}
+
 template <int H, int CS, int NB>
 int run_fwd(const float* const gi[2], const float* const w_hh[2], const float* const b_hh[2], float* out,
             float* const gates[2], float* const hprev[2], int B, int T, int save, cudaStream_t s) {
@@ -432,6 +747,9 @@ int launch_gru_seq_fwd(const float* const gi[2], const float* const w_hh[2], con
     SEDK_PROF("gru_seq_fwd", s);
     if (H == 128 && gru_cluster() == 2 && pick_nb(B, 2) == 1)
         return run_fwd<128, 2, 1>(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
+    // v2 holds 80 weights + the loop state in exactly 128 registers at one batch row per CTA (two rows spill)
+    if (H == 128 && get_option("gru_v2", 1) && pick_nb(B, 1) == 1)
+        return run_fwd_v2(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
     if (H == 128) {
         switch (pick_nb(B, 1)) {
             case 1: return run_fwd<128, 1, 1>(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
@@ -456,6 +774,8 @@ int launch_gru_seq_bwd(const float* gout, const float* const w_hh[2], const floa
     SEDK_PROF("gru_seq_bwd", s);
     if (H == 128 && gru_cluster() == 2 && pick_nb(B, 2) == 1)
         return run_bwd<128, 2, 1>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
+    if (H == 128 && get_option("gru_v2", 1) && pick_nb(B, 1) == 1)
+        return run_bwd_v2(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
     if (H == 128) {
         switch (pick_nb(B, 1)) {
             case 1: return run_bwd<128, 1, 1>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);

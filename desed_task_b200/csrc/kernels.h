@@ -52,6 +52,15 @@ int launch_bnglu_pool_bwd(const float* z, const float* bn, const float* glu_w, c
                           float* gy, float* gglu_w, float* gglu_b, double* stats, int B, int T, int F, int C, int pt,
                           int pf, float drop_p, uint64_t seed, const uint64_t* seed_dev, uint64_t drop_stream, int precision,
                           cudaStream_t s);
+// bnglu_small.cu: register-resident warp-autonomous variants of the two kernels above for C in {16, 32} (pf == 2)
+bool bnglu_small_supports(int B, int T, int F, int C, int pt, int pf);
+int launch_bnglu_small_fwd(const float* z, const float* bn, const float* glu_w, const float* glu_b, float* out, int B,
+                           int T, int F, int C, int pt, int pf, float drop_p, uint64_t seed, const uint64_t* seed_dev,
+                           uint64_t drop_stream, int precision, cudaStream_t s);
+int launch_bnglu_small_bwd(const float* z, const float* bn, const float* glu_w, const float* glu_b, const float* gout,
+                           float* gy, float* gglu_w, float* gglu_b, double* stats, int B, int T, int F, int C, int pt,
+                           int pf, float drop_p, uint64_t seed, const uint64_t* seed_dev, uint64_t drop_stream,
+                           int precision, cudaStream_t s);
 // train-mode BN backward: gy -> gz in place; writes ggamma, gbeta (and zero conv-bias grad gb)
 int launch_bn_bwd_apply(float* gy, const float* z, const float* bn, const double* stats, float* ggamma, float* gbeta,
                         float* gb, double count, int64_t n_pix, int C, cudaStream_t s);

@@ -46,6 +46,13 @@ SEDK_API int sedk_set_tcgen05(int on);
 SEDK_API int sedk_get_tcgen05(void);
 /* H = 128 GRU recurrence as a 2-CTA cluster (cs = 2) instead of one CTA per (row, direction) (cs = 1, default) */
 SEDK_API int sedk_set_gru_cluster(int cs);
+/* Named integer switches selecting between kernel variants (A/B measurements, parity tests).  Unset options take their
+ * default from the environment variable SEDK_<NAME> (upper case), else the built-in default.  Known names:
+ *   "gru_v2"      1 (default): H = 128 recurrence with the quad-per-unit layout (shuffle reductions, one barrier per
+ *                 step); 0: first-generation kernel (row x k-segment layout, partial sums through shared memory)
+ *   "bnglu_small" 1 (default): register-resident warp-autonomous BN+GLU+pool kernels for 16 / 32 channels; 0: tiled kernel */
+SEDK_API int sedk_set_option(const char* name, int value);
+SEDK_API int sedk_get_option(const char* name, int dflt);
 /* number of kernels this library has launched (or captured into a CUDA graph) so far in this process */
 SEDK_API long long sedk_launch_count(void);
 /* Optional eager-mode kernel timing: between sedk_profile_enable(1) and sedk_profile_report every launcher is bracketed by
