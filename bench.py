@@ -281,7 +281,7 @@ def run_ours(args):
         # ---- front-end bandwidth (the second headline: mel GB/s vs HBM peak)
         lm_cnt, lm_tot = prof.get("logmel", (1, 0.0))
         mel_gbs = B * 960512 / (lm_tot / lm_cnt) / 1e6 if lm_tot > 0 else None
-        cpu = cpu_baseline(B, budget_s=20.0) if world == 1 else None
+        cpu = cpu_baseline(B, budget_s=20.0) if (world == 1 and not args.quick) else None
         out = {
             "metric": METRIC, "value": round(value, 1), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": W, "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak",
@@ -410,6 +410,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="supervised", choices=["supervised", "mean_teacher"])
     ap.add_argument("--batch", type=int, default=None, help="clips per GPU (default 24 supervised / 48 mean-teacher)")
+    ap.add_argument("--quick", action="store_true", help="development runs: skip the CPU baseline leg")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = 48 if args.workload == "mean_teacher" else 24

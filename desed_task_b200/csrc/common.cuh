@@ -14,6 +14,7 @@ namespace sedk {
 void set_error(const char* fmt, ...);
 int  check_launch(const char* what);
 void count_launch();
+bool profiling_on();
 // named kernel-variant switches (sedk_set_option / env SEDK_<NAME>)
 int  get_option(const char* name, int dflt);
 void set_option(const char* name, int value);

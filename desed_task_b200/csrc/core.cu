@@ -58,6 +58,8 @@ ProfScope::~ProfScope() {
     if (idx_ >= 0) cudaEventRecord(g_prof[idx_].b, s_);
 }
 
+bool profiling_on() { return g_prof_on; }
+
 int check_launch(const char* what) {
     g_launches++;
     cudaError_t e = cudaGetLastError();

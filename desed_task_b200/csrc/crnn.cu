@@ -14,6 +14,60 @@ namespace {
 
 constexpr uint64_t STREAM_EMB = 100, STREAM_RNN = 200;
 
+// Fork / join helper: kernels that are off the dependency chain (weight packing in forward; the weight-gradient GEMMs of
+// the GRU and of the convolutions in backward) run on a library-owned side stream so that they overlap the chain instead
+// of extending it.  Event record / wait pairs are capturable: inside a CUDA graph they become parallel branches.
+// Disabled while per-launcher profiling is on (the event brackets would time overlapped kernels) or with option
+// "side_stream" = 0.
+struct Side {
+    cudaStream_t s = nullptr;
+    cudaEvent_t ev[16];
+    int next = 0;
+    bool ok = false;
+    Side() {
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return;
+        for (int i = 0; i < 16; i++)
+            if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return;
+        ok = true;
+    }
+    cudaEvent_t event() { return ev[next++ & 15]; }
+};
+Side& side() {
+    static thread_local Side x;
+    return x;
+}
+// returns the side stream after making it wait for everything enqueued on `main` so far, or `main` itself when disabled
+struct Fork {
+    cudaStream_t main, side_s;
+    bool forked = false;
+    explicit Fork(cudaStream_t m) : main(m), side_s(m) {}
+    int begin() {
+        if (forked || profiling_on() || get_option("side_stream", 1) == 0 || !side().ok) return SEDK_OK;
+        cudaEvent_t e = side().event();
+        SEDK_CUDA(cudaEventRecord(e, main));
+        SEDK_CUDA(cudaStreamWaitEvent(side().s, e, 0));
+        side_s = side().s;
+        forked = true;
+        return SEDK_OK;
+    }
+    // side work issued so far must see what `main` has done up to now (a new dependency edge main -> side)
+    int sync_side_to_main() {
+        if (!forked) return SEDK_OK;
+        cudaEvent_t e = side().event();
+        SEDK_CUDA(cudaEventRecord(e, main));
+        SEDK_CUDA(cudaStreamWaitEvent(side_s, e, 0));
+        return SEDK_OK;
+    }
+    // main waits for all side work issued so far
+    int join() {
+        if (!forked) return SEDK_OK;
+        cudaEvent_t e = side().event();
+        SEDK_CUDA(cudaEventRecord(e, side_s));
+        SEDK_CUDA(cudaStreamWaitEvent(main, e, 0));
+        return SEDK_OK;
+    }
+};
+
 int validate(const sedk_crnn_plan* p, bool backward) {
     SEDK_REQUIRE(p != nullptr, "crnn: null plan");
     SEDK_REQUIRE(p->B > 0 && p->n_conv >= 1 && p->n_conv <= SEDK_MAX_CONV, "crnn: bad B / n_conv");
@@ -60,6 +114,18 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const int B = p->B;
     const float pdrop = p->training ? p->dropout_p : 0.f;
+    // ---------------- weight packs of every layer: off the chain, overlapped with the first conv
+    Fork fk(s);
+    rc = fk.begin();
+    if (rc) return rc;
+    for (int i = 1; i < p->n_conv; i++) {
+        rc = launch_pack_weights(p->conv[i].w, p->conv[i].wpack, p->conv[i].cin, p->conv[i].cout, fk.side_s);
+        if (rc) return rc;
+    }
+    if (p->n_conv < 2) {
+        rc = fk.join();
+        if (rc) return rc;
+    }
     // ---------------- CNN
     for (int i = 0; i < p->n_conv; i++) {
         const sedk_conv_layer& L = p->conv[i];
@@ -71,8 +137,10 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
                                   p->training ? p->specaug : nullptr, L.w, L.b, p->training ? p->x0 : nullptr, L.z, st, B,
                                   L.T, L.F, C, s);
         } else {
-            rc = launch_pack_weights(L.w, L.wpack, L.cin, C, s);
-            if (rc) return rc;
+            if (i == 1) {
+                rc = fk.join();
+                if (rc) return rc;
+            }
             rc = launch_conv3x3(p->conv[i - 1].out, L.wpack, L.b, L.z, st, B, L.T, L.F, L.cin, C, p->precision, s);
         }
         if (rc) return rc;
@@ -146,6 +214,7 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
     const int BT = B * Tp;
     const int Hl = p->gru[p->n_gru - 1].hidden;
     const int D = 2 * Hl, C = p->nclass;
+    Fork fk(s);
     // ---------------- heads
     SEDK_CUDA(cudaMemsetAsync(p->gdense_w, 0, (size_t)C * D * sizeof(float), s));
     SEDK_CUDA(cudaMemsetAsync(p->gsoft_w, 0, (size_t)C * D * sizeof(float), s));
@@ -171,10 +240,14 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
         const float* xin = l > 0 ? p->gru[l - 1].out : (p->emb ? p->fused : last.out);
         float* gin = l > 0 ? p->gru[l - 1].gout : (p->emb ? p->gfused : last.gout);
         SEDK_REQUIRE(gin, "crnn backward: input-gradient buffer of GRU layer %d missing", l);
+        // the weight-gradient GEMMs only feed the optimiser: side stream
+        rc = l == p->n_gru - 1 ? fk.begin() : fk.sync_side_to_main();
+        if (rc) return rc;
+        cudaStream_t ss = fk.side_s;
         for (int d = 0; d < 2; d++) {
             SEDK_REQUIRE(G.gw_ih[d] && G.gw_hh[d] && G.gb_ih[d] && G.gb_hh[d], "crnn backward: GRU grads null");
-            SEDK_CUDA(cudaMemsetAsync(G.gw_ih[d], 0, (size_t)3 * H * in_dim * sizeof(float), s));
-            SEDK_CUDA(cudaMemsetAsync(G.gw_hh[d], 0, (size_t)3 * H * H * sizeof(float), s));
+            SEDK_CUDA(cudaMemsetAsync(G.gw_ih[d], 0, (size_t)3 * H * in_dim * sizeof(float), ss));
+            SEDK_CUDA(cudaMemsetAsync(G.gw_hh[d], 0, (size_t)3 * H * H * sizeof(float), ss));
         }
         {
             // dW_ih = dgi^T x ; dW_hh rows [0,2H) from (dr, dz), rows [2H,3H) from d(hn) - both directions per launch
@@ -182,15 +255,15 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
             const float* xs[2] = {xin, xin};
             float* gwih[2] = {G.gw_ih[0], G.gw_ih[1]};
             rc = launch_gemm_batched(1, 0, 3 * H, in_dim, BT, 1.f, dgi, 3 * H, xs, in_dim, 1.f, gwih, in_dim, nullptr, 2,
-                                     p->precision, s);
+                                     p->precision, ss);
             if (rc) return rc;
             const float* hp[2] = {G.hprev[0], G.hprev[1]};
             float* gwhh[2] = {G.gw_hh[0], G.gw_hh[1]};
-            rc = launch_gemm_batched(1, 0, 2 * H, H, BT, 1.f, dgi, 3 * H, hp, H, 1.f, gwhh, H, nullptr, 2, p->precision, s);
+            rc = launch_gemm_batched(1, 0, 2 * H, H, BT, 1.f, dgi, 3 * H, hp, H, 1.f, gwhh, H, nullptr, 2, p->precision, ss);
             if (rc) return rc;
             const float* dhn[2] = {G.dghn[0], G.dghn[1]};
             float* gwhn[2] = {G.gw_hh[0] + (size_t)2 * H * H, G.gw_hh[1] + (size_t)2 * H * H};
-            rc = launch_gemm_batched(1, 0, H, H, BT, 1.f, dhn, H, hp, H, 1.f, gwhn, H, nullptr, 2, p->precision, s);
+            rc = launch_gemm_batched(1, 0, H, H, BT, 1.f, dhn, H, hp, H, 1.f, gwhn, H, nullptr, 2, p->precision, ss);
             if (rc) return rc;
         }
         for (int d = 0; d < 2; d++) {
@@ -232,10 +305,12 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
         if (i > 0) {
             const sedk_conv_layer& P = p->conv[i - 1];
             SEDK_REQUIRE(P.gout, "crnn backward: gout of conv layer %d missing", i - 1);
-            SEDK_CUDA(cudaMemsetAsync(L.gwpack, 0, (size_t)9 * Cc * L.cin * sizeof(float), s));
-            rc = launch_conv_wgrad(P.out, L.gy, L.gwpack, B, L.T, L.F, L.cin, Cc, p->precision, s);
+            rc = fk.forked ? fk.sync_side_to_main() : fk.begin();
             if (rc) return rc;
-            rc = launch_unpack_wgrad(L.gwpack, L.gw, L.cin, Cc, s);
+            SEDK_CUDA(cudaMemsetAsync(L.gwpack, 0, (size_t)9 * Cc * L.cin * sizeof(float), fk.side_s));
+            rc = launch_conv_wgrad(P.out, L.gy, L.gwpack, B, L.T, L.F, L.cin, Cc, p->precision, fk.side_s);
+            if (rc) return rc;
+            rc = launch_unpack_wgrad(L.gwpack, L.gw, L.cin, Cc, fk.side_s);
             if (rc) return rc;
             rc = launch_conv3x3(L.gy, L.wpack + (size_t)9 * Cc * L.cin, nullptr, P.gout, nullptr, B, L.T, L.F, Cc, L.cin,
                                 p->precision, s);
@@ -246,5 +321,5 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
             if (rc) return rc;
         }
     }
-    return SEDK_OK;
+    return fk.join();
 }
