@@ -49,12 +49,15 @@ class TrainEngine:
         self.C = student.nclass
         self.T = mel_spec.n_frames(n_samples)
         self.audio_dev = [torch.empty(B, n_samples, device=dev), torch.empty(B, n_samples, device=dev)]
-        self.mel_buf = torch.empty(B, mel_spec.n_mels, self.T, device=dev)
+        # the front end runs on its own stream into ping-pong buffers, so that step k+1's log-mel overlaps step k's graph
+        self.mel_bufs = [torch.empty(B, mel_spec.n_mels, self.T, device=dev) for _ in range(2)]
+        self.mel_buf = self.mel_bufs[0]
         self.logmel = torch.empty_like(self.mel_buf)
         self.Tp = None
         self.labels_dev = None
         self.emb_dev = torch.empty(B, *emb_shape, device=dev) if emb_shape else None
-        self.minmax = torch.empty(B, 2, dtype=torch.int32, device=dev)
+        self.minmaxs = [torch.empty(B, 2, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.minmax = self.minmaxs[0]
         self.perm = torch.arange(B, dtype=torch.int64, device=dev)
         self.coef = torch.ones(B, device=dev)
         self.perm_s = torch.arange(max(self.n_s, 1), dtype=torch.int64, device=dev)
@@ -75,6 +78,10 @@ class TrainEngine:
         self.ring_ev = [None] * self.ring
         self.slot_ev = [None, None]
         self.copy_stream = torch.cuda.Stream(device=dev)
+        self.fe_stream = torch.cuda.Stream(device=dev)
+        self.buf_free_ev = [None, None]
+        self.graphs = [None, None]      # one captured graph per ping-pong buffer
+        self.keeps = [None, None]
         self.graph = None
         self.graph_kernels = 0          # kernels captured in the graph (one replay launches all of them)
         self.replays = 0
@@ -87,11 +94,12 @@ class TrainEngine:
         self.ws = None
 
     # ------------------------------------------------------------------------------------------------------------
-    def _device_part(self, do_mix):
-        """Everything between the front end and the optimiser (graph-capturable)."""
+    def _device_part(self, do_mix, slot=0):
+        """Everything between the front end and the optimiser (graph-capturable), reading ping-pong buffer `slot`."""
         s = stream_ptr()
         L = lib()
         n_s, n_w, B = self.n_s, self.n_w, self.B
+        self.mel_buf, self.minmax = self.mel_bufs[slot], self.minmaxs[slot]
         check(L.sedk_bump_counter(ptr(self.seed_ctr), 1, s), "sedk_bump_counter")
         if do_mix:
             check(L.sedk_minmax_init(ptr(self.minmax), B, s), "sedk_minmax_init")
@@ -120,7 +128,7 @@ class TrainEngine:
             t_strong, t_weak, _ = self.teacher.forward_direct(feats, self.minmax, emb, cm)
         if self.gstrong is None:
             self.gstrong, self.gweak = torch.empty_like(strong), torch.empty_like(weak)
-        self._keep = (labels_weak, labels_strong, strong, weak, t_strong, t_weak)
+        self.keeps[slot] = (labels_weak, labels_strong, strong, weak, t_strong, t_weak)
         check(L.sedk_sed_loss_dev(ptr(strong), ptr(weak), ptr(t_strong), ptr(t_weak),
                                   ptr(labels_strong.contiguous()) if n_s > 0 else None,
                                   ptr(labels_weak) if n_w > 0 else None, B, self.C, strong.shape[2], n_s, n_w,
@@ -178,13 +186,17 @@ class TrainEngine:
         hs[4] = self.const_max * scale if self.teacher is not None else 0.0
         return do_mix, r
 
-    def step(self, audio_host, labels_host, emb_host=None):
-        """One optimisation step on a host batch (pinned fp32 tensors: audio [B, L], labels [B, C, T'])."""
+    def step(self, audio_host, labels_host, emb_host=None, inputs_ready=False):
+        """One optimisation step.  audio [B, L] / labels [B, C, T'] fp32: pinned host tensors (copied on a copy stream) or
+        device tensors.  The front end runs on its own stream into ping-pong buffers, so the log-mel of step k+1 overlaps
+        the forward/backward graph of step k.  For DEVICE inputs the front end waits for the caller's current stream unless
+        `inputs_ready=True` (the caller guarantees the batch was complete before this call)."""
         dev, B = self.dev, self.B
         k = self.step_idx
         slot = k % 2
         cur = torch.cuda.current_stream(dev)
         resident = audio_host.is_cuda
+        fe = self.fe_stream
         if not resident:
             # ---- H2D of this step's inputs on the copy stream (overlaps the previous step's compute)
             with torch.cuda.stream(self.copy_stream):
@@ -193,11 +205,30 @@ class TrainEngine:
                 self.audio_dev[slot].copy_(audio_host, non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(self.copy_stream)
+            fe.wait_event(ev_in)
+        elif not inputs_ready:
+            fe.wait_stream(cur)
         if self.labels_dev is None:
             self.labels_dev = torch.empty(labels_host.shape, device=dev)
+            fe.wait_stream(cur)                                   # first step: allocations / table uploads on `cur`
         do_mix, r = self._host_scalars()
         mixing_graph = self.mixup_type is not None
         audio_in = audio_host if resident else self.audio_dev[slot]
+        # ---- front end on its own stream (eager: reads the double-buffered audio slot, writes ping-pong buffer `slot`)
+        if self.buf_free_ev[slot] is not None:
+            fe.wait_event(self.buf_free_ev[slot])                 # the graph that last read this buffer has finished
+        with torch.cuda.stream(fe):
+            self.mel_buf, self.minmax = self.mel_bufs[slot], self.minmaxs[slot]
+            if mixing_graph:
+                self.mel_spec_run(audio_in, log=False)
+            else:
+                check(lib().sedk_minmax_init(ptr(self.minmax), B, stream_ptr()), "sedk_minmax_init")
+                self.mel_spec_run(audio_in, log=True)
+            ev_fe = torch.cuda.Event()
+            ev_fe.record(fe)
+        if not resident:
+            self.slot_ev[slot] = ev_fe
+        # ---- per-step device scalars and labels (current stream)
         self.labels_dev.copy_(labels_host, non_blocking=True)
         if emb_host is not None:
             self.emb_dev.copy_(emb_host, non_blocking=True)
@@ -213,40 +244,33 @@ class TrainEngine:
             if n_w > 0:
                 self.perm_w.copy_(self.host_perm[r][B + n_s:B + n_s + n_w], non_blocking=True)
                 self.coef_w.copy_(self.host_coef[r][B + n_s:B + n_s + n_w], non_blocking=True)
-        if not resident:
-            cur.wait_event(ev_in)
-        # ---- front end (eager: reads the double-buffered audio slot)
-        if mixing_graph:
-            self.mel_spec_run(audio_in, log=False)
-        else:
-            check(lib().sedk_minmax_init(ptr(self.minmax), B, stream_ptr()), "sedk_minmax_init")
-            self.mel_spec_run(audio_in, log=True)
-        if not resident:
-            ev_used = torch.cuda.Event()
-            ev_used.record(cur)
-            self.slot_ev[slot] = ev_used
+        cur.wait_event(ev_fe)
         # ---- forward / loss / backward
         if not self.use_graph:
-            self._device_part(mixing_graph)
-        elif self.graph is None:
+            self._device_part(mixing_graph, slot)
+        elif self.graphs[slot] is None:
             # warm-up (loads kernels, opts into shared memory, allocates workspaces), then capture
             snap = self._snapshot()
-            self._device_part(mixing_graph)
+            self._device_part(mixing_graph, slot)
             torch.cuda.synchronize(dev)
             self._restore(snap)
             g = torch.cuda.CUDAGraph()
             n0 = lib().sedk_launch_count()
             # thread_local: other threads (e.g. the NCCL watchdog polling events) must not invalidate the capture
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                self._device_part(mixing_graph)
+                self._device_part(mixing_graph, slot)
             self.graph_kernels = int(lib().sedk_launch_count() - n0)
+            self.graphs[slot] = g
             self.graph = g
             self._restore(snap)
-            self.graph.replay()
+            g.replay()
             self.replays += 1
         else:
-            self.graph.replay()
+            self.graphs[slot].replay()
             self.replays += 1
+        ev_free = torch.cuda.Event()
+        ev_free.record(cur)
+        self.buf_free_ev[slot] = ev_free
         self._optimizer_part()
         self.host_loss[r].copy_(self.losses, non_blocking=True)
         ev = torch.cuda.Event()
