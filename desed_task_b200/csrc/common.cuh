@@ -121,7 +121,13 @@ __device__ __forceinline__ float warp_min(float v) {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 // MUFU-based variant (ex2 + rcp): abs error ~1e-7, used inside the fused CNN block kernels and the recurrence
-__device__ __forceinline__ float fast_sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// (raw ex2.approx / rcp.approx: none of the range-check code __expf / __fdividef carry; ex2 -> inf gives rcp -> 0, the limit)
+__device__ __forceinline__ float fast_sigmoidf_(float x) {
+    float e, y;
+    asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(1.0f + e));
+    return y;
+}
 
 // ---------------------------------------------------------------------------------------------
 // cp.async (LDGSTS) 16-byte copies with zero fill
