@@ -34,7 +34,7 @@ class ConvLayer(C.Structure):
                 ("num_batches", vp), ("glu_w", vp), ("glu_b", vp),
                 ("gw", vp), ("gb", vp), ("ggamma", vp), ("gbeta", vp), ("gglu_w", vp), ("gglu_b", vp),
                 ("wpack", vp), ("gwpack", vp), ("z", vp), ("gy", vp), ("out", vp), ("gout", vp), ("stats", vp),
-                ("bn", vp)]
+                ("bn", vp), ("glu_pack", vp), ("lin", vp)]
 
 
 class GruLayer(C.Structure):

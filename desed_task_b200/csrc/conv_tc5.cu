@@ -12,7 +12,7 @@
 //   TMEM lane quadrant -> bias -> global store + per-channel sum / sum^2 for train-mode BatchNorm).
 // The same kernel is the data-gradient when given the flipped/transposed weight pack.
 #include "kernels.h"
-#include <cuda.h>
+#include "tc5.cuh"
 #include <stdlib.h>
 
 namespace sedk {
@@ -23,82 +23,6 @@ constexpr int TC_A_BYTES = 128 * 128;                 // 128 rows x 32 fp32
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES;
 constexpr int TC_THREADS = 192;
 constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*stats*/;
-
-// instruction descriptor: D fp32, A/B tf32, both K-major, N = n, M = 128 (cute::UMMA::InstrDescriptor bit layout)
-__host__ __device__ constexpr uint32_t tc_idesc(uint32_t n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
-}
-
-// column sums over the 32 lanes of a warp for 32 per-lane values: after the call v[0] of lane l holds sum_lanes v[l]
-// (recursive halving: 31 shuffles instead of 32 x 5)
-__device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int j = 0; j < off; j++) {
-            const float send = upper ? v[j] : v[j + off];
-            const float keep = upper ? v[j + off] : v[j];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-}
-
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    // K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO = 16 B, descriptor version 1
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-           (2ull << 61);
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n"
-        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
-        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t (&v)[32], uint32_t taddr) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-}
 
 template <int CIN, int COUT, int TT, int TF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -242,15 +166,9 @@ constexpr int WG_KPIX = 32;                           // pixels per stage
 constexpr int WG_CHUNK_BYTES = WG_KPIX * 128;         // one 32-channel chunk of one stage: 32 rows x 128 B
 constexpr int WG_THREADS = 192;
 
-// MN-major TF32 operands must use the "128B swizzle with 32B atoms" layout (UMMA LayoutType::SWIZZLE_128B_BASE32B = 1; TMA
-// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 B along MN, 32-byte chunks XOR-ed with (row % 4), 4-row K atoms.
-// LBO = stride between 32-element MN chunks, SBO = stride between 4-row K groups (512 B for consecutive rows).
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
-           (1ull << 46) | (1ull << 61);
-}
-
-template <int CIN, int TT, int TF>
+// NDX = 3: convolution (CTA row dy = blockIdx.y, taps dx = 0..2);  NDX = 1: a single un-shifted tap, i.e. the plain TN GEMM
+// D[128 x Cin] += gz^T x over all pixels (used for the GLU gate weight gradient, bnglu_tc5.cu).
+template <int CIN, int TT, int TF, int NDX = 3>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_tc5_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
                       float* __restrict__ gwp, int T, int F, int total_tiles, int dbg) {
@@ -258,9 +176,10 @@ conv_wgrad_tc5_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
     constexpr int COUT = 128;
     constexpr int NCH = CIN / 32;                                   // 32-channel chunks of x
     constexpr int A_BYTES = 4 * WG_CHUNK_BYTES;                     // 128 co
-    constexpr int B_BYTES = 3 * NCH * WG_CHUNK_BYTES;               // 3 taps
+    constexpr int B_BYTES = NDX * NCH * WG_CHUNK_BYTES;             // NDX taps
     constexpr int STAGE = A_BYTES + B_BYTES;
-    constexpr uint32_t TMEM_COLS = 3 * CIN <= 256 ? 256 : 512;
+    constexpr uint32_t TMEM_COLS = NDX * CIN <= 128 ? 128 : (NDX * CIN <= 256 ? 256 : 512);
+    constexpr int SHIFT = NDX == 3 ? 1 : 0;                         // tap offset = index - SHIFT
     // D fp32, A/B tf32, A and B MN-major (bits 15, 16), N = CIN, M = 128
     constexpr uint32_t IDESC = tc_idesc(CIN) | (1u << 15) | (1u << 16);
     extern __shared__ uint8_t smem_raw[];
@@ -313,11 +232,11 @@ conv_wgrad_tc5_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
                 for (int c = 0; c < 4; c++)
                     tma_load_4d(a_dst + c * WG_CHUNK_BYTES, &tmG, smem_u32(&full[s]), c * 32, f0, t0, b);
 #pragma unroll
-                for (int dx = 0; dx < 3; dx++)
+                for (int dx = 0; dx < NDX; dx++)
 #pragma unroll
                     for (int c = 0; c < NCH; c++)
-                        tma_load_4d(b_dst + (dx * NCH + c) * WG_CHUNK_BYTES, &tmX, smem_u32(&full[s]), c * 32, f0 + dx - 1,
-                                    t0 + dy - 1, b);
+                        tma_load_4d(b_dst + (dx * NCH + c) * WG_CHUNK_BYTES, &tmX, smem_u32(&full[s]), c * 32, f0 + dx - SHIFT,
+                                    t0 + dy - SHIFT, b);
             }
         }
     } else if (warp == 1) {
@@ -331,7 +250,7 @@ conv_wgrad_tc5_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
                 for (int k = 0; k < WG_KPIX / 8; k++) {             // 8 pixels = one 1024-byte swizzle atom per MMA
                     const uint64_t da = umma_desc_mn_sw128(a_src + k * 1024, WG_CHUNK_BYTES);
 #pragma unroll
-                    for (int dx = 0; dx < 3; dx++) {
+                    for (int dx = 0; dx < NDX; dx++) {
                         const uint64_t db = umma_desc_mn_sw128(b_src + dx * NCH * WG_CHUNK_BYTES + k * 1024, WG_CHUNK_BYTES);
                         umma_tf32(tmem + (uint32_t)(dx * CIN), da, db, IDESC, (it | k) != 0 ? 1u : 0u);
                     }
@@ -346,8 +265,8 @@ conv_wgrad_tc5_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
         mbar_wait_u32(smem_u32(accum), 0);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll 1
-        for (int dx = 0; dx < 3; dx++) {
-            float* grow = gwp + ((size_t)(dy * 3 + dx) * COUT + co) * CIN;
+        for (int dx = 0; dx < NDX; dx++) {
+            float* grow = gwp + ((size_t)(dy * NDX + dx) * COUT + co) * CIN;
 #pragma unroll 1
             for (int c = 0; c < NCH; c++) {
                 uint32_t v[32];
@@ -375,24 +294,6 @@ conv_wgrad_tc5_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
     }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
 }
 
 template <int CIN, int COUT, int TT, int TF>
@@ -450,10 +351,10 @@ int run_tc5_tiles(const float* in, const float* wp, const float* bias, float* ou
     return run_tc5<CIN, COUT, 64, 2>(tmA, tmB, bias, out, stats, B, T, F, s);
 }
 
-template <int CIN, int TT, int TF>
+template <int CIN, int TT, int TF, int NDX>
 int run_wgrad_tc5(const CUtensorMap& tmG, const CUtensorMap& tmX, float* gwp, int B, int T, int F, cudaStream_t s) {
-    auto kern = conv_wgrad_tc5_kernel<CIN, TT, TF>;
-    constexpr size_t smem = (size_t)WG_STAGES * (4 + 3 * (CIN / 32)) * WG_CHUNK_BYTES + 1024 + 256;
+    auto kern = conv_wgrad_tc5_kernel<CIN, TT, TF, NDX>;
+    constexpr size_t smem = (size_t)WG_STAGES * (4 + NDX * (CIN / 32)) * WG_CHUNK_BYTES + 1024 + 256;
     static bool cfg = false;
     if (!cfg) {
         int rc = opt_in_smem(kern, smem);
@@ -461,9 +362,9 @@ int run_wgrad_tc5(const CUtensorMap& tmG, const CUtensorMap& tmX, float* gwp, in
         cfg = true;
     }
     const int tiles = B * cdiv(T, TT) * cdiv(F, TF);
-    int gx = num_sms() / 3;
+    int gx = num_sms() / NDX;
     if (gx > tiles) gx = tiles;
-    dim3 grid(gx, 3);
+    dim3 grid(gx, NDX);
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("SEDK_WG_DBG"); dbg = e ? atoi(e) : 0; }
     kern<<<grid, WG_THREADS, smem, s>>>(tmG, tmX, gwp, T, F, tiles, dbg);
@@ -471,7 +372,7 @@ int run_wgrad_tc5(const CUtensorMap& tmG, const CUtensorMap& tmX, float* gwp, in
     return SEDK_OK;
 }
 
-template <int CIN>
+template <int CIN, int NDX>
 int run_wgrad_tc5_tiles(const float* x, const float* gz, float* gwp, int B, int T, int F, cudaStream_t s) {
     EncodeTiledFn enc = encode_fn();
     SEDK_REQUIRE(enc != nullptr, "conv_wgrad_tc5: cuTensorMapEncodeTiled is not available from the driver");
@@ -499,10 +400,10 @@ int run_wgrad_tc5_tiles(const float* x, const float* gz, float* gwp, int B, int 
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SEDK_REQUIRE(r == CUDA_SUCCESS, "conv_wgrad_tc5: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
     }
-    if (TF == 16) return run_wgrad_tc5<CIN, 2, 16>(tmG, tmX, gwp, B, T, F, s);
-    if (TF == 8) return run_wgrad_tc5<CIN, 4, 8>(tmG, tmX, gwp, B, T, F, s);
-    if (TF == 4) return run_wgrad_tc5<CIN, 8, 4>(tmG, tmX, gwp, B, T, F, s);
-    return run_wgrad_tc5<CIN, 16, 2>(tmG, tmX, gwp, B, T, F, s);
+    if (TF == 16) return run_wgrad_tc5<CIN, 2, 16, NDX>(tmG, tmX, gwp, B, T, F, s);
+    if (TF == 8) return run_wgrad_tc5<CIN, 4, 8, NDX>(tmG, tmX, gwp, B, T, F, s);
+    if (TF == 4) return run_wgrad_tc5<CIN, 8, 4, NDX>(tmG, tmX, gwp, B, T, F, s);
+    return run_wgrad_tc5<CIN, 16, 2, NDX>(tmG, tmX, gwp, B, T, F, s);
 }
 
 }  // namespace
@@ -542,8 +443,14 @@ int launch_conv_wgrad_tc5(const float* x, const float* gz, float* gwpack, int B,
     snprintf(pname, sizeof(pname), "conv_wgrad_tc5_%dto%d_F%d", cin, cout, F);
     SEDK_PROF(pname, s);
     SEDK_REQUIRE(tc5_wgrad_supports(cin, cout), "conv_wgrad_tc5: (cin=%d, cout=%d) not supported", cin, cout);
-    if (cin == 128) return run_wgrad_tc5_tiles<128>(x, gz, gwpack, B, T, F, s);
-    return run_wgrad_tc5_tiles<64>(x, gz, gwpack, B, T, F, s);
+    if (cin == 128) return run_wgrad_tc5_tiles<128, 3>(x, gz, gwpack, B, T, F, s);
+    return run_wgrad_tc5_tiles<64, 3>(x, gz, gwpack, B, T, F, s);
+}
+
+// out[n][k] += sum_pixels g[pix][n] * x[pix][k]  (both [B,T,F,128] channels-last; out pre-zeroed by the caller)
+int launch_tn_gemm_tc5_c128(const float* x, const float* g, float* out, int B, int T, int F, cudaStream_t s) {
+    SEDK_PROF("glu_wgrad_tc5_c128", s);
+    return run_wgrad_tc5_tiles<128, 1>(x, g, out, B, T, F, s);
 }
 
 }  // namespace sedk

@@ -68,6 +68,12 @@ struct Fork {
     }
 };
 
+// the tcgen05 BN+GLU path needs its two workspaces and covers C = 128, pooling (1, 2), TF32 mode; the backward of a layer
+// must take the same path as its forward (different dropout-mask mapping, lin saved), so both sides ask this one function
+bool use_glu_tc5(const sedk_crnn_plan* p, const sedk_conv_layer& L) {
+    return L.glu_pack != nullptr && L.lin != nullptr && bnglu_tc5_supports(L.T, L.F, L.cout, L.pt, L.pf, p->precision);
+}
+
 int validate(const sedk_crnn_plan* p, bool backward) {
     SEDK_REQUIRE(p != nullptr, "crnn: null plan");
     SEDK_REQUIRE(p->B > 0 && p->n_conv >= 1 && p->n_conv <= SEDK_MAX_CONV, "crnn: bad B / n_conv");
@@ -144,6 +150,15 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
             rc = launch_conv3x3(p->conv[i - 1].out, L.wpack, L.b, L.z, st, B, L.T, L.F, L.cin, C, p->precision, s);
         }
         if (rc) return rc;
+        if (use_glu_tc5(p, L)) {
+            rc = launch_glu_prep(L.stats, L.gamma, L.beta, L.running_mean, L.running_var, L.num_batches, L.bn, L.glu_w,
+                                 L.glu_b, L.glu_pack, (double)B * L.T * L.F, p->bn_eps, p->bn_momentum, p->training, C, s);
+            if (rc) return rc;
+            rc = launch_bnglu_tc5_fwd(L.z, L.bn, L.glu_pack, L.out, p->training ? L.lin : nullptr, B, L.T, L.F, L.pt, L.pf,
+                                      pdrop, p->seed, p->seed_dev, (uint64_t)i, s);
+            if (rc) return rc;
+            continue;
+        }
         rc = launch_bn_finalize(L.stats, L.gamma, L.beta, L.running_mean, L.running_var, L.num_batches, L.bn,
                                 (double)B * L.T * L.F, p->bn_eps, p->bn_momentum, p->training, C, s);
         if (rc) return rc;
@@ -295,11 +310,23 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
         const int Cc = L.cout;
         const int64_t npix = (int64_t)B * L.T * L.F;
         SEDK_CUDA(cudaMemsetAsync(L.stats + 2 * Cc, 0, 2 * Cc * sizeof(double), s));
-        SEDK_CUDA(cudaMemsetAsync(L.gglu_w, 0, (size_t)Cc * Cc * sizeof(float), s));
         SEDK_CUDA(cudaMemsetAsync(L.gglu_b, 0, (size_t)Cc * sizeof(float), s));
+        if (use_glu_tc5(p, L)) {
+            rc = launch_bnglu_tc5_bwd(L.z, L.bn, L.glu_pack, L.gout, L.lin, L.gy, L.gglu_b, L.stats, B, L.T, L.F, L.pt, L.pf,
+                                      pdrop, p->seed, p->seed_dev, (uint64_t)i, s);
+            if (rc) return rc;
+            // gate weight gradient = g_lin^T z over all pixels: off the chain
+            rc = fk.forked ? fk.sync_side_to_main() : fk.begin();
+            if (rc) return rc;
+            SEDK_CUDA(cudaMemsetAsync(L.gglu_w, 0, (size_t)Cc * Cc * sizeof(float), fk.side_s));
+            rc = launch_glu_wgrad_tc5(L.z, L.lin, L.bn, L.gglu_w, L.gglu_b, B, L.T, L.F, fk.side_s);
+            if (rc) return rc;
+        } else {
+        SEDK_CUDA(cudaMemsetAsync(L.gglu_w, 0, (size_t)Cc * Cc * sizeof(float), s));
         rc = launch_bnglu_pool_bwd(L.z, L.bn, L.glu_w, L.glu_b, L.gout, L.gy, L.gglu_w, L.gglu_b, L.stats, B, L.T, L.F, Cc,
                                    L.pt, L.pf, pdrop, p->seed, p->seed_dev, (uint64_t)i, p->precision, s);
         if (rc) return rc;
+        }
         rc = launch_bn_bwd_apply(L.gy, L.z, L.bn, L.stats, L.ggamma, L.gbeta, L.gb, (double)npix, npix, Cc, s);
         if (rc) return rc;
         if (i > 0) {

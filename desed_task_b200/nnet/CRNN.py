@@ -85,7 +85,10 @@ class _Workspace:
                 gwpack=new(9 * C * cin) if i > 0 else None,
                 z=new(B, T, F, C), gy=new(B, T, F, C),
                 out=new(B, T // pt, F // pf, C), gout=new(B, T // pt, F // pf, C),
-                stats=new(4 * C, dtype=torch.float64, zero=True), bn=new(4 * C, zero=True))
+                stats=new(4 * C, dtype=torch.float64, zero=True), bn=new(4 * C, zero=True),
+                # tcgen05 BN+GLU path of the 128-channel layers (include/sedk.h: glu_pack, lin)
+                glu_pack=new(2 * C * C + C, zero=True) if C == 128 else None,
+                lin=new(B, T, F, C) if C == 128 else None)
             for k, v in d.items():
                 setattr(L, k, _vp(v))
             pre = "cnn.cnn."

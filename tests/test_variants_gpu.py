@@ -42,7 +42,7 @@ def _compare(a, b, tol_out, tol_grad):
     assert worst[1] < tol_grad, worst
 
 
-@pytest.mark.parametrize("option", ["gru_v2", "bnglu_small"])
+@pytest.mark.parametrize("option", ["gru_v2", "bnglu_small", "bnglu_tc5"])
 @pytest.mark.parametrize("precision,tol_out,tol_grad", [(1, 2e-5, 2e-3), (0, 5e-4, 3e-2)])
 def test_kernel_generations_agree(dev, feats, option, precision, tol_out, tol_grad):
     from desed_task_b200._lib import lib
@@ -71,8 +71,8 @@ def test_gru_two_rows_per_cta_path(dev):
     assert maxdiff(s_big[:2], s_small) < 2e-5 and maxdiff(w_big[78:80], w_small) < 2e-5
 
 
-@pytest.mark.parametrize("small", [1, 0])
-def test_dropout_masks_agree_between_forward_and_backward(dev, feats, small):
+@pytest.mark.parametrize("small,precision", [(1, 1), (0, 1), (1, 0)])
+def test_dropout_masks_agree_between_forward_and_backward(dev, feats, small, precision):
     """Dropout masks are regenerated in backward from (seed, stream, counter): with the seed pinned, a central finite
     difference of the loss along the gradient direction must reproduce |grad| (a forward/backward mask mismatch in any
     layer would break this by O(1))."""
@@ -81,7 +81,8 @@ def test_dropout_masks_agree_between_forward_and_backward(dev, feats, small):
     try:
         cfg = dataclasses.replace(ocrnn.CFG_2023, dropout=0.5)
         P = ocrnn.init_params(cfg, seed=42, trained_like=True)
-        net = build(cfg, P, dev, 1, specaugm_t_p=0.0, specaugm_f_p=0.0)
+        # precision 0 also exercises the tcgen05 BN+GLU kernels of the 128-channel layers (their own mask mapping)
+        net = build(cfg, P, dev, precision, specaugm_t_p=0.0, specaugm_f_p=0.0)
         net.train()
         x = feats.to(dev)
         wgt = torch.linspace(0.5, 1.5, 156, device=dev)
@@ -108,7 +109,7 @@ def test_dropout_masks_agree_between_forward_and_backward(dev, feats, small):
                 for n in names:
                     params[n].add_(grads[n], alpha=-sign * eps)
         fd = (vals[0] - vals[1]) / (2 * eps)
-        assert abs(fd - gnorm * gnorm) / (gnorm * gnorm) < 0.08, (fd, gnorm * gnorm)
+        assert abs(fd - gnorm * gnorm) / (gnorm * gnorm) < (0.08 if precision else 0.15), (fd, gnorm * gnorm)
         # and a different seed gives different masks
         with torch.no_grad():
             assert abs(loss_at(101).item() - loss.item()) > 1e-6
