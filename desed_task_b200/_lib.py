@@ -57,7 +57,8 @@ class CrnnPlan(C.Structure):
                 ("dense_w", vp), ("dense_b", vp), ("soft_w", vp), ("soft_b", vp),
                 ("gdense_w", vp), ("gdense_b", vp), ("gsoft_w", vp), ("gsoft_b", vp),
                 ("classes_mask", vp), ("rnn_drop", vp), ("grnn_drop", vp), ("strong", vp), ("weak", vp), ("sof", vp), ("hsum", vp),
-                ("gstrong", vp), ("gweak", vp)]
+                ("gstrong", vp), ("gweak", vp),
+                ("zero_fwd", vp), ("zero_fwd_bytes", i64), ("zero_bwd", vp), ("zero_bwd_bytes", i64)]
 
 
 _SIGS = {

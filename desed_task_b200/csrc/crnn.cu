@@ -120,6 +120,8 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const int B = p->B;
     const float pdrop = p->training ? p->dropout_p : 0.f;
+    const bool zf = p->zero_fwd != nullptr && p->zero_fwd_bytes > 0;
+    if (zf && p->training) SEDK_CUDA(cudaMemsetAsync(p->zero_fwd, 0, (size_t)p->zero_fwd_bytes, s));
     // ---------------- weight packs of every layer: off the chain, overlapped with the first conv
     Fork fk(s);
     rc = fk.begin();
@@ -136,7 +138,7 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
     for (int i = 0; i < p->n_conv; i++) {
         const sedk_conv_layer& L = p->conv[i];
         const int C = L.cout;
-        if (p->training) SEDK_CUDA(cudaMemsetAsync(L.stats, 0, 4 * C * sizeof(double), s));
+        if (p->training && !zf) SEDK_CUDA(cudaMemsetAsync(L.stats, 0, 4 * C * sizeof(double), s));
         double* st = p->training ? L.stats : nullptr;
         if (i == 0) {
             rc = launch_conv0_fwd(p->x, p->x_sb, p->x_sm, p->x_st, p->minmax, p->scaler_eps,
@@ -230,11 +232,17 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
     const int Hl = p->gru[p->n_gru - 1].hidden;
     const int D = 2 * Hl, C = p->nclass;
     Fork fk(s);
+    // zb: every gradient buffer was cleared by one memset; zs: the backward halves of `stats` were cleared by the forward
+    const bool zb = p->zero_bwd != nullptr && p->zero_bwd_bytes > 0;
+    const bool zs = p->zero_fwd != nullptr && p->zero_fwd_bytes > 0;
+    if (zb) SEDK_CUDA(cudaMemsetAsync(p->zero_bwd, 0, (size_t)p->zero_bwd_bytes, s));
     // ---------------- heads
-    SEDK_CUDA(cudaMemsetAsync(p->gdense_w, 0, (size_t)C * D * sizeof(float), s));
-    SEDK_CUDA(cudaMemsetAsync(p->gsoft_w, 0, (size_t)C * D * sizeof(float), s));
-    SEDK_CUDA(cudaMemsetAsync(p->gdense_b, 0, (size_t)C * sizeof(float), s));
-    SEDK_CUDA(cudaMemsetAsync(p->gsoft_b, 0, (size_t)C * sizeof(float), s));
+    if (!zb) {
+        SEDK_CUDA(cudaMemsetAsync(p->gdense_w, 0, (size_t)C * D * sizeof(float), s));
+        SEDK_CUDA(cudaMemsetAsync(p->gsoft_w, 0, (size_t)C * D * sizeof(float), s));
+        SEDK_CUDA(cudaMemsetAsync(p->gdense_b, 0, (size_t)C * sizeof(float), s));
+        SEDK_CUDA(cudaMemsetAsync(p->gsoft_b, 0, (size_t)C * sizeof(float), s));
+    }
     const float* hx = pdrop > 0.f ? p->rnn_drop : p->gru[p->n_gru - 1].out;
     float* ghx = pdrop > 0.f ? p->grnn_drop : p->gru[p->n_gru - 1].gout;
     rc = launch_heads_bwd(hx, p->dense_w, p->soft_w, p->classes_mask, p->strong, p->hsum, p->sof, p->gstrong, p->gweak,
@@ -250,7 +258,7 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
         const int H = G.hidden, in_dim = G.in_dim;
         SEDK_REQUIRE(G.gout && G.dghn[0] && G.dghn[1], "crnn backward: GRU layer %d gradient workspace missing", l);
         SEDK_REQUIRE(G.gb_ih[0] && G.gb_ih[1] && G.gb_hh[0] && G.gb_hh[1], "crnn backward: GRU bias grads null");
-        rc = launch_gru_seq_bwd(G.gout, G.w_hh, G.gates, G.hprev, G.gi, G.dghn, G.gb_ih, G.gb_hh, B, Tp, H, s);
+        rc = launch_gru_seq_bwd(G.gout, G.w_hh, G.gates, G.hprev, G.gi, G.dghn, G.gb_ih, G.gb_hh, B, Tp, H, zb ? 1 : 0, s);
         if (rc) return rc;
         const float* xin = l > 0 ? p->gru[l - 1].out : (p->emb ? p->fused : last.out);
         float* gin = l > 0 ? p->gru[l - 1].gout : (p->emb ? p->gfused : last.gout);
@@ -261,6 +269,7 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
         cudaStream_t ss = fk.side_s;
         for (int d = 0; d < 2; d++) {
             SEDK_REQUIRE(G.gw_ih[d] && G.gw_hh[d] && G.gb_ih[d] && G.gb_hh[d], "crnn backward: GRU grads null");
+            if (zb) continue;
             SEDK_CUDA(cudaMemsetAsync(G.gw_ih[d], 0, (size_t)3 * H * in_dim * sizeof(float), ss));
             SEDK_CUDA(cudaMemsetAsync(G.gw_hh[d], 0, (size_t)3 * H * H * sizeof(float), ss));
         }
@@ -292,7 +301,7 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
     if (p->emb != nullptr) {
         SEDK_REQUIRE(p->gcat_w && p->gcat_b && p->gfused && last.gout, "crnn backward: fusion gradient buffers missing");
         const int W = nb + p->emb_dim;
-        SEDK_CUDA(cudaMemsetAsync(p->gcat_w, 0, (size_t)nb * W * sizeof(float), s));
+        if (!zb) SEDK_CUDA(cudaMemsetAsync(p->gcat_w, 0, (size_t)nb * W * sizeof(float), s));
         rc = launch_gemm(1, 0, nb, W, BT, 1.f, p->gfused, nb, p->cat_in, W, 1.f, p->gcat_w, W, nullptr, p->precision, s);
         if (rc) return rc;
         rc = launch_colsum(p->gfused, BT, nb, nb, p->gcat_b, 0, s);
@@ -309,8 +318,8 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
         const sedk_conv_layer& L = p->conv[i];
         const int Cc = L.cout;
         const int64_t npix = (int64_t)B * L.T * L.F;
-        SEDK_CUDA(cudaMemsetAsync(L.stats + 2 * Cc, 0, 2 * Cc * sizeof(double), s));
-        SEDK_CUDA(cudaMemsetAsync(L.gglu_b, 0, (size_t)Cc * sizeof(float), s));
+        if (!zs) SEDK_CUDA(cudaMemsetAsync(L.stats + 2 * Cc, 0, 2 * Cc * sizeof(double), s));
+        if (!zb) SEDK_CUDA(cudaMemsetAsync(L.gglu_b, 0, (size_t)Cc * sizeof(float), s));
         if (use_glu_tc5(p, L)) {
             rc = launch_bnglu_tc5_bwd(L.z, L.bn, L.glu_pack, L.gout, L.lin, L.gy, L.gglu_b, L.stats, B, L.T, L.F, L.pt, L.pf,
                                       pdrop, p->seed, p->seed_dev, (uint64_t)i, s);
@@ -318,11 +327,11 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
             // gate weight gradient = g_lin^T z over all pixels: off the chain
             rc = fk.forked ? fk.sync_side_to_main() : fk.begin();
             if (rc) return rc;
-            SEDK_CUDA(cudaMemsetAsync(L.gglu_w, 0, (size_t)Cc * Cc * sizeof(float), fk.side_s));
+            if (!zb) SEDK_CUDA(cudaMemsetAsync(L.gglu_w, 0, (size_t)Cc * Cc * sizeof(float), fk.side_s));
             rc = launch_glu_wgrad_tc5(L.z, L.lin, L.bn, L.gglu_w, L.gglu_b, B, L.T, L.F, fk.side_s);
             if (rc) return rc;
         } else {
-        SEDK_CUDA(cudaMemsetAsync(L.gglu_w, 0, (size_t)Cc * Cc * sizeof(float), s));
+        if (!zb) SEDK_CUDA(cudaMemsetAsync(L.gglu_w, 0, (size_t)Cc * Cc * sizeof(float), s));
         rc = launch_bnglu_pool_bwd(L.z, L.bn, L.glu_w, L.glu_b, L.gout, L.gy, L.gglu_w, L.gglu_b, L.stats, B, L.T, L.F, Cc,
                                    L.pt, L.pf, pdrop, p->seed, p->seed_dev, (uint64_t)i, p->precision, s);
         if (rc) return rc;
@@ -334,7 +343,7 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
             SEDK_REQUIRE(P.gout, "crnn backward: gout of conv layer %d missing", i - 1);
             rc = fk.forked ? fk.sync_side_to_main() : fk.begin();
             if (rc) return rc;
-            SEDK_CUDA(cudaMemsetAsync(L.gwpack, 0, (size_t)9 * Cc * L.cin * sizeof(float), fk.side_s));
+            if (!zb) SEDK_CUDA(cudaMemsetAsync(L.gwpack, 0, (size_t)9 * Cc * L.cin * sizeof(float), fk.side_s));
             rc = launch_conv_wgrad(P.out, L.gy, L.gwpack, B, L.T, L.F, L.cin, Cc, p->precision, fk.side_s);
             if (rc) return rc;
             rc = launch_unpack_wgrad(L.gwpack, L.gw, L.cin, Cc, fk.side_s);
@@ -343,7 +352,7 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
                                 p->precision, s);
             if (rc) return rc;
         } else {
-            SEDK_CUDA(cudaMemsetAsync(L.gw, 0, (size_t)9 * Cc * sizeof(float), s));
+            if (!zb) SEDK_CUDA(cudaMemsetAsync(L.gw, 0, (size_t)9 * Cc * sizeof(float), s));
             rc = launch_conv0_wgrad(p->x0, L.gy, L.gw, B, L.T, L.F, Cc, p->precision, s);
             if (rc) return rc;
         }

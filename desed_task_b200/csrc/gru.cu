@@ -631,7 +631,7 @@ int run_fwd_v2(const float* const gi[2], const float* const w_hh[2], const float
 
 int run_bwd_v2(const float* gout, const float* const w_hh[2], const float* const gates[2], const float* const hprev[2],
                float* const dgi[2], float* const dghn[2], float* const gb_ih[2], float* const gb_hh[2], int B, int T,
-               cudaStream_t s) {
+               int zeroed, cudaStream_t s) {
     auto kern = gru_bwd_v2_kernel;
     const size_t smem = (size_t)(V2_WS4 * V2_NT * 4 + 2 * V2_DPAD) * sizeof(float);
     static bool configured = false;
@@ -640,7 +640,7 @@ int run_bwd_v2(const float* gout, const float* const w_hh[2], const float* const
         if (rc) return rc;
         configured = true;
     }
-    for (int d = 0; d < 2; d++) {
+    for (int d = 0; d < 2 && !zeroed; d++) {
         SEDK_CUDA(cudaMemsetAsync(gb_ih[d], 0, (size_t)3 * V2_H * sizeof(float), s));
         SEDK_CUDA(cudaMemsetAsync(gb_hh[d], 0, (size_t)3 * V2_H * sizeof(float), s));
     }
@@ -685,7 +685,7 @@ int run_fwd(const float* const gi[2], const float* const w_hh[2], const float* c
 template <int H, int CS, int NB>
 int run_bwd(const float* gout, const float* const w_hh[2], const float* const gates[2], const float* const hprev[2],
             float* const dgi[2], float* const dghn[2], float* const gb_ih[2], float* const gb_hh[2], int B, int T,
-            cudaStream_t s) {
+            int zeroed, cudaStream_t s) {
     using Cfg = GruCfg<H, CS>;
     auto kern = gru_bwd_kernel<H, CS, NB>;
     dim3 grid(cdiv(B, NB) * CS, 2);
@@ -708,7 +708,7 @@ int run_bwd(const float* gout, const float* const w_hh[2], const float* const ga
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    for (int d = 0; d < 2; d++) {
+    for (int d = 0; d < 2 && !zeroed; d++) {
         SEDK_CUDA(cudaMemsetAsync(gb_ih[d], 0, (size_t)3 * H * sizeof(float), s));
         SEDK_CUDA(cudaMemsetAsync(gb_hh[d], 0, (size_t)3 * H * sizeof(float), s));
     }
@@ -770,25 +770,25 @@ int launch_gru_seq_fwd(const float* const gi[2], const float* const w_hh[2], con
 
 int launch_gru_seq_bwd(const float* gout, const float* const w_hh[2], const float* const gates[2],
                        const float* const hprev[2], float* const dgi[2], float* const dghn[2], float* const gb_ih[2],
-                       float* const gb_hh[2], int B, int T, int H, cudaStream_t s) {
+                       float* const gb_hh[2], int B, int T, int H, int zeroed, cudaStream_t s) {
     SEDK_PROF("gru_seq_bwd", s);
     if (H == 128 && gru_cluster() == 2 && pick_nb(B, 2) == 1)
-        return run_bwd<128, 2, 1>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
+        return run_bwd<128, 2, 1>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, zeroed, s);
     if (H == 128 && get_option("gru_v2", 1) && pick_nb(B, 1) == 1)
-        return run_bwd_v2(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
+        return run_bwd_v2(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, zeroed, s);
     if (H == 128) {
         switch (pick_nb(B, 1)) {
-            case 1: return run_bwd<128, 1, 1>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
-            case 2: return run_bwd<128, 1, 2>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
-            default: return run_bwd<128, 1, 4>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
+            case 1: return run_bwd<128, 1, 1>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, zeroed, s);
+            case 2: return run_bwd<128, 1, 2>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, zeroed, s);
+            default: return run_bwd<128, 1, 4>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, zeroed, s);
         }
     }
-    if (H == 64) return run_bwd<64, 1, 2>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
+    if (H == 64) return run_bwd<64, 1, 2>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, zeroed, s);
     if (H == 192) {
         switch (pick_nb(B, 3)) {
-            case 1: return run_bwd<192, 3, 1>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
-            case 2: return run_bwd<192, 3, 2>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
-            default: return run_bwd<192, 3, 4>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, s);
+            case 1: return run_bwd<192, 3, 1>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, zeroed, s);
+            case 2: return run_bwd<192, 3, 2>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, zeroed, s);
+            default: return run_bwd<192, 3, 4>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, zeroed, s);
         }
     }
     SEDK_UNSUPPORTED("GRU hidden size %d has no sm_100a instantiation (supported: 64, 128, 192)", H);

@@ -97,7 +97,7 @@ int launch_gru_seq_fwd(const float* const gi[2], const float* const w_hh[2], con
 // BPTT: gout [B,T,2H] -> dgi[dir] [B,T,3H] (written over gi), dghn[dir] [B,T,H] and the bias gradients gb_ih / gb_hh [3H]
 int launch_gru_seq_bwd(const float* gout, const float* const w_hh[2], const float* const gates[2],
                        const float* const hprev[2], float* const dgi[2], float* const dghn[2], float* const gb_ih[2],
-                       float* const gb_hh[2], int B, int T, int H, cudaStream_t s);
+                       float* const gb_hh[2], int B, int T, int H, int zeroed, cudaStream_t s);
 
 // ---- heads.cu -----------------------------------------------------------------------------------------------
 int launch_heads_fwd(const float* x, const float* dw, const float* db, const float* sw, const float* sb,

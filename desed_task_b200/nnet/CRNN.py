@@ -54,7 +54,19 @@ class _Workspace:
         params = list(model.named_parameters())
         self.pnames = [n for n, _ in params]
         sizes = [p.numel() for _, p in params]
-        self.gflat = new(sum(sizes), zero=True)
+        cnn = model.cnn
+        n_conv = len(cnn.nb_filters)
+        # One contiguous region holds every buffer the backward accumulates into (the flat gradient + the packed conv
+        # weight-gradient accumulators) and one holds every BatchNorm statistics array: sedk_crnn_plan.zero_bwd / zero_fwd
+        # let the library clear each with a single memset.
+        chans = [1] + list(cnn.nb_filters)
+        gw_sizes = [0] + [9 * chans[i + 1] * chans[i] for i in range(1, n_conv)]
+        n_grad = (sum(sizes) + 3) // 4 * 4
+        self.zero_bwd = new(n_grad + sum(gw_sizes), zero=True)
+        self.gflat = self.zero_bwd[:sum(sizes)]
+        gw_off = [n_grad + sum(gw_sizes[:i]) for i in range(n_conv)]
+        self.zero_fwd = new(sum(4 * c for c in cnn.nb_filters), dtype=torch.float64, zero=True)
+        st_off = [sum(4 * c for c in cnn.nb_filters[:i]) for i in range(n_conv)]
         self.gviews = {}
         off = 0
         for (n, p), sz in zip(params, sizes):
@@ -63,9 +75,9 @@ class _Workspace:
 
         plan = CrnnPlan()
         plan.B, plan.n_mels, plan.n_frames = B, n_mels, n_frames
-        cnn = model.cnn
-        n_conv = len(cnn.nb_filters)
         plan.n_conv = n_conv
+        plan.zero_bwd, plan.zero_bwd_bytes = _vp(self.zero_bwd), self.zero_bwd.numel() * 4
+        plan.zero_fwd, plan.zero_fwd_bytes = _vp(self.zero_fwd), self.zero_fwd.numel() * 8
         plan.n_gru = model.rnn.num_layers
         plan.nclass = model.nclass
         plan.bn_eps, plan.bn_momentum = 1e-3, 0.99
@@ -82,10 +94,10 @@ class _Workspace:
             L.cin, L.cout, L.T, L.F, L.pt, L.pf = cin, C, T, F, pt, pf
             d = dict(
                 wpack=new(2 * 9 * C * cin) if i > 0 else None,
-                gwpack=new(9 * C * cin) if i > 0 else None,
+                gwpack=self.zero_bwd[gw_off[i]:gw_off[i] + gw_sizes[i]] if i > 0 else None,
                 z=new(B, T, F, C), gy=new(B, T, F, C),
                 out=new(B, T // pt, F // pf, C), gout=new(B, T // pt, F // pf, C),
-                stats=new(4 * C, dtype=torch.float64, zero=True), bn=new(4 * C, zero=True),
+                stats=self.zero_fwd[st_off[i]:st_off[i] + 4 * C], bn=new(4 * C, zero=True),
                 # tcgen05 BN+GLU path of the 128-channel layers (include/sedk.h: glu_pack, lin)
                 glu_pack=new(2 * C * C + C, zero=True) if C == 128 else None,
                 lin=new(B, T, F, C) if C == 128 else None)

@@ -249,6 +249,15 @@ typedef struct {
     float* hsum;                    /* [B, 2, C] workspace: sum_t strong*att, sum_t att        */
     float* gstrong;                 /* in (backward): [B, C, T'] */
     float* gweak;                   /* in (backward): [B, C]     */
+    /* Optional bulk zeroing.  When the caller lays out every `stats` array of the conv layers contiguously it passes that
+     * region as zero_fwd: the forward clears it with ONE memset (both halves: the backward half is only written by the
+     * backward that follows).  Likewise zero_bwd covers every gradient / gradient-accumulator buffer of the plan (gw, gb,
+     * ggamma, gbeta, gglu_*, gwpack, GRU and head gradients): one memset at the start of the backward replaces ~35.
+     * NULL: each buffer is cleared individually (the default). */
+    void* zero_fwd;
+    int64_t zero_fwd_bytes;
+    void* zero_bwd;
+    int64_t zero_bwd_bytes;
 } sedk_crnn_plan;
 
 SEDK_API int sedk_crnn_forward(const sedk_crnn_plan* plan, void* stream);
