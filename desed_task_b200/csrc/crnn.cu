@@ -74,6 +74,11 @@ bool use_glu_tc5(const sedk_crnn_plan* p, const sedk_conv_layer& L) {
     return L.glu_pack != nullptr && L.lin != nullptr && bnglu_tc5_supports(L.T, L.F, L.cout, L.pt, L.pf, p->precision);
 }
 
+template <class... P>
+bool all_aligned16(P... ptrs) {
+    return ((((reinterpret_cast<uintptr_t>(ptrs)) & 15) == 0) && ...);
+}
+
 int validate(const sedk_crnn_plan* p, bool backward) {
     SEDK_REQUIRE(p != nullptr, "crnn: null plan");
     SEDK_REQUIRE(p->B > 0 && p->n_conv >= 1 && p->n_conv <= SEDK_MAX_CONV, "crnn: bad B / n_conv");
@@ -196,8 +201,11 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
             const float* Bs[2] = {G.w_ih[0], G.w_ih[1]};
             float* Cs[2] = {G.gi[0], G.gi[1]};
             const float* bs[2] = {G.b_ih[0], G.b_ih[1]};
-            rc = launch_gemm_batched(0, 1, B * Tp, 3 * H, in_dim, 1.f, As, in_dim, Bs, in_dim, 0.f, Cs, 3 * H, bs, 2,
-                                     p->precision, s);
+            if (gemm_tc5_ok(B * Tp, 3 * H, in_dim, p->precision) && all_aligned16(xr, Bs[0], Bs[1], Cs[0], Cs[1], bs[0], bs[1]))
+                rc = launch_gemm_tc5_nt2(xr, Bs, bs, Cs, B * Tp, 3 * H, in_dim, s);
+            else
+                rc = launch_gemm_batched(0, 1, B * Tp, 3 * H, in_dim, 1.f, As, in_dim, Bs, in_dim, 0.f, Cs, 3 * H, bs, 2,
+                                         p->precision, s);
             if (rc) return rc;
         }
         SEDK_REQUIRE(G.out && (!p->training || (G.gates[0] && G.gates[1] && G.hprev[0] && G.hprev[1])),
@@ -290,11 +298,19 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
             rc = launch_gemm_batched(1, 0, H, H, BT, 1.f, dhn, H, hp, H, 1.f, gwhn, H, nullptr, 2, p->precision, ss);
             if (rc) return rc;
         }
-        for (int d = 0; d < 2; d++) {
-            // dx (+)= dgi W_ih
-            rc = launch_gemm(0, 0, BT, in_dim, 3 * H, 1.f, G.gi[d], 3 * H, G.w_ih[d], in_dim, d == 0 ? 0.f : 1.f, gin,
-                             in_dim, nullptr, p->precision, s);
+        if (gemm_tc5_ok(BT, in_dim, 3 * H, p->precision) && all_aligned16(G.gi[0], G.gi[1], G.w_ih[0], G.w_ih[1], gin)) {
+            // dx = dgi_f W_ih,f + dgi_b W_ih,b : one tcgen05 launch, split-K over the two directions
+            const float* da[2] = {G.gi[0], G.gi[1]};
+            const float* wb[2] = {G.w_ih[0], G.w_ih[1]};
+            rc = launch_gemm_tc5_nn_pair(da, wb, gin, BT, in_dim, 3 * H, s);
             if (rc) return rc;
+        } else {
+            for (int d = 0; d < 2; d++) {
+                // dx (+)= dgi W_ih
+                rc = launch_gemm(0, 0, BT, in_dim, 3 * H, 1.f, G.gi[d], 3 * H, G.w_ih[d], in_dim, d == 0 ? 0.f : 1.f, gin,
+                                 in_dim, nullptr, p->precision, s);
+                if (rc) return rc;
+            }
         }
     }
     // ---------------- embedding fusion

@@ -87,6 +87,12 @@ int launch_gemm(int transA, int transB, int M, int N, int K, float alpha, const 
 int launch_gemm_batched(int transA, int transB, int M, int N, int K, float alpha, const float* const* A, int lda,
                         const float* const* B, int ldb, float beta, float* const* C, int ldc, const float* const* bias,
                         int nprob, int precision, cudaStream_t s);
+// gemm_tc5.cu: tcgen05 variants of the two GEMM shapes on the GRU's dependency chain (TF32 mode, K % 32 == 0, 16-byte
+// aligned operands): C_d = A B_d^T + bias_d for d = 0, 1 in one launch, and C = A0 B0 + A1 B1 (split-K over two pairs)
+bool gemm_tc5_ok(int M, int N, int K, int precision);
+int launch_gemm_tc5_nt2(const float* A, const float* const B[2], const float* const bias[2], float* const C[2], int M, int N,
+                        int K, cudaStream_t s);
+int launch_gemm_tc5_nn_pair(const float* const A[2], const float* const B[2], float* C, int M, int N, int K, cudaStream_t s);
 // column sums: out[n] (+)= sum_m A[m*lda + n]
 int launch_colsum(const float* A, int M, int N, int lda, float* out, int accumulate, cudaStream_t s);
 

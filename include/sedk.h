@@ -50,7 +50,10 @@ SEDK_API int sedk_set_gru_cluster(int cs);
  * default from the environment variable SEDK_<NAME> (upper case), else the built-in default.  Known names:
  *   "gru_v2"      1 (default): H = 128 recurrence with the quad-per-unit layout (shuffle reductions, one barrier per
  *                 step); 0: first-generation kernel (row x k-segment layout, partial sums through shared memory)
- *   "bnglu_small" 1 (default): register-resident warp-autonomous BN+GLU+pool kernels for 16 / 32 channels; 0: tiled kernel */
+ *   "bnglu_small" 1 (default): register-resident warp-autonomous BN+GLU+pool kernels for 16 / 32 channels; 0: tiled kernel
+ *   "bnglu_tc5"   1 (default): tcgen05 / TMEM / TMA BN+GLU+pool kernels for the 128-channel layers (TF32 mode)
+ *   "gemm_tc5"    1 (default): tcgen05 GEMMs for the GRU input projections and input gradients (TF32 mode)
+ *   "side_stream" 1 (default): weight-gradient GEMMs and weight packs on a forked side stream */
 SEDK_API int sedk_set_option(const char* name, int value);
 SEDK_API int sedk_get_option(const char* name, int dflt);
 /* number of kernels this library has launched (or captured into a CUDA graph) so far in this process */

@@ -110,9 +110,11 @@ def test_train_forward_backward_matches_oracle(dev, feats, tag, precision, tol_o
 
 
 def test_tcgen05_conv_matches_legacy_mma_path(dev, feats):
-    """A/B: the tcgen05/TMEM/TMA convolutions (layers with 32/64/128 channels, TF32 mode) against the mma.sync kernels of
-    the same layers - forward posteriors, BN statistics and every gradient.  Both are TF32 (the tcgen05 unit truncates the
-    fp32 operands, the legacy path rounds them), so they agree to TF32 noise, and both sit inside the 1e-3 budget."""
+    """A/B: every tcgen05/TMEM/TMA kernel (convolutions with 32/64/128 channels, the 128-channel BN+GLU blocks, the GRU
+    projection GEMMs; TF32 mode) against the mma.sync kernels of the same layers - forward posteriors, BN statistics and
+    every gradient.  Both are TF32 (the tcgen05 unit truncates the fp32 operands, the legacy path rounds them), so they
+    agree to TF32 noise (bounded here by the 1e-3 posterior budget; each side is held to 1e-3 against the fp32 oracle by
+    test_eval_forward_matches_golden / test_train_forward_backward_matches_oracle)."""
     from desed_task_b200._lib import lib
     cfg = dataclasses.replace(ocrnn.CFG_2023, dropout=0.0)
     P = ocrnn.init_params(cfg, seed=42, trained_like=True)
@@ -129,7 +131,7 @@ def test_tcgen05_conv_matches_legacy_mma_path(dev, feats):
                        net.state_dict()["cnn.cnn.batchnorm5.running_var"].clone())
         finally:
             lib().sedk_set_tcgen05(1)
-    assert maxdiff(res[1][0], res[0][0]) < 5e-4 and maxdiff(res[1][1], res[0][1]) < 5e-4
+    assert maxdiff(res[1][0], res[0][0]) < 1e-3 and maxdiff(res[1][1], res[0][1]) < 1e-3
     assert maxdiff(res[1][3], res[0][3]) < 1e-3
     gscale = max(g.abs().max().item() for g in res[0][2].values())
     for n, g in res[0][2].items():
