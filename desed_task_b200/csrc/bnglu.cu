@@ -197,6 +197,10 @@ bnglu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
                         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
                     }
                 s.x *= inv_pool; s.y *= inv_pool; s.z *= inv_pool; s.w *= inv_pool;
+                if (!X3) {      // TF32 mode: the pooled activation is the next convolution's MMA operand (tcgen05 truncates)
+                    s.x = __uint_as_float(to_tf32(s.x)); s.y = __uint_as_float(to_tf32(s.y));
+                    s.z = __uint_as_float(to_tf32(s.z)); s.w = __uint_as_float(to_tf32(s.w));
+                }
                 *reinterpret_cast<float4*>(out + (((size_t)b * gm.To + to) * gm.Fo + fo) * C + q * 4) = s;
             }
         }

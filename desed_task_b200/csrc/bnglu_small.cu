@@ -236,6 +236,8 @@ bnglu_small_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bn
                 for (int e = 0; e < 4; e++) {
                     s[e] = y[0][q][e] + y[1][q][e];
                     s[e] = (s[e] + __shfl_xor_sync(0xffffffffu, s[e], 4)) * inv_pool;
+                    // TF32 mode: the pooled activation is the next convolution's MMA operand (the tcgen05 unit truncates)
+                    if (!X3) s[e] = __uint_as_float(to_tf32(s[e]));
                 }
                 if ((g & 1) == 0)
                     *reinterpret_cast<float4*>(out + pool_off<C>(gm, p, 0, g) + 16 * q + 4 * t4) =
@@ -248,8 +250,10 @@ bnglu_small_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bn
                 for (int q = 0; q < Q; q++) {
                     float s[4];
 #pragma unroll
-                    for (int e = 0; e < 4; e++)
+                    for (int e = 0; e < 4; e++) {
                         s[e] = (y[rr][q][e] + __shfl_xor_sync(0xffffffffu, y[rr][q][e], 4)) * inv_pool;
+                        if (!X3) s[e] = __uint_as_float(to_tf32(s[e]));
+                    }
                     if ((g & 1) == 0)
                         *reinterpret_cast<float4*>(out + pool_off<C>(gm, p, rr, g) + 16 * q + 4 * t4) =
                             make_float4(s[0], s[1], s[2], s[3]);

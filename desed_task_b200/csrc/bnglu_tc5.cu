@@ -58,8 +58,9 @@ glu_prep_kernel(const double* __restrict__ stats, const float* __restrict__ gamm
     const float scale = gamma[k] * invstd;
     const float shift = beta[k] - mean * scale;
     const float w = glu_w[n * C + k];
-    pack[n * C + k] = w * scale;
-    pack[C * C + k * C + n] = w;
+    // rounded to the nearest TF32 value here: the tensor core truncates what it reads
+    pack[n * C + k] = __uint_as_float(to_tf32(w * scale));
+    pack[C * C + k * C + n] = __uint_as_float(to_tf32(w));
     float part = warp_sum(w * shift);
     if ((k & 31) == 0) red[k >> 5] = part;
     __syncthreads();
@@ -227,7 +228,8 @@ bnglu_tc5_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
                         r[d] = a;
                         if (lrow != nullptr && i + d < pvalid) lrow[(size_t)(i + d) * C] = lin;
                     }
-                    if (i < pvalid) orow[(size_t)(i >> 1) * C] = 0.5f * (r[0] + r[1]);
+                    // the pooled activation is the next convolution's MMA operand: store the nearest TF32 value
+                    if (i < pvalid) orow[(size_t)(i >> 1) * C] = __uint_as_float(to_tf32(0.5f * (r[0] + r[1])));
                 }
             }
             tc5_fence_before();

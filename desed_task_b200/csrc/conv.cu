@@ -15,19 +15,23 @@ namespace sedk {
 namespace {
 
 // ------------------------------------------------------------------------------------------------------------
-__global__ void pack_kernel(const float* __restrict__ w, float* __restrict__ wp, int cin, int cout) {
+// rnd: round to the nearest TF32 value while packing (TF32 mode): the tcgen05 unit TRUNCATES fp32 operands, so operands
+// that are already representable lose nothing there
+__global__ void pack_kernel(const float* __restrict__ w, float* __restrict__ wp, int cin, int cout, int rnd) {
     const int n = 9 * cin * cout;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * n) return;
     int r = i % n;
     int tap = r / (cout * cin);
+    float v;
     if (i < n) {
         int co = (r / cin) % cout, ci = r % cin;
-        wp[i] = w[((size_t)co * cin + ci) * 9 + tap];
+        v = w[((size_t)co * cin + ci) * 9 + tap];
     } else {
         int ci = (r / cout) % cin, co = r % cout;
-        wp[i] = w[((size_t)co * cin + ci) * 9 + (8 - tap)];
+        v = w[((size_t)co * cin + ci) * 9 + (8 - tap)];
     }
+    wp[i] = rnd ? __uint_as_float(to_tf32(v)) : v;
 }
 
 __global__ void unpack_kernel(const float* __restrict__ gwp, float* __restrict__ gw, int cin, int cout) {
@@ -504,10 +508,10 @@ int launch_with_smem(K kernel, dim3 grid, size_t smem, cudaStream_t s, const cha
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
-int launch_pack_weights(const float* w, float* wpack, int cin, int cout, cudaStream_t s) {
+int launch_pack_weights(const float* w, float* wpack, int cin, int cout, int round_tf32, cudaStream_t s) {
     SEDK_PROF("pack_weights", s);
     int n = 2 * 9 * cin * cout;
-    pack_kernel<<<cdiv(n, 256), 256, 0, s>>>(w, wpack, cin, cout);
+    pack_kernel<<<cdiv(n, 256), 256, 0, s>>>(w, wpack, cin, cout, round_tf32);
     SEDK_LAUNCH_CHECK("pack_kernel");
     return SEDK_OK;
 }

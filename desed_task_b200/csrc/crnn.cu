@@ -132,7 +132,8 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
     rc = fk.begin();
     if (rc) return rc;
     for (int i = 1; i < p->n_conv; i++) {
-        rc = launch_pack_weights(p->conv[i].w, p->conv[i].wpack, p->conv[i].cin, p->conv[i].cout, fk.side_s);
+        rc = launch_pack_weights(p->conv[i].w, p->conv[i].wpack, p->conv[i].cin, p->conv[i].cout, p->precision == 0 ? 1 : 0,
+                                 fk.side_s);
         if (rc) return rc;
     }
     if (p->n_conv < 2) {

@@ -6,7 +6,8 @@ namespace sedk {
 
 // ---- conv.cu ------------------------------------------------------------------------------------------------
 // wpack[0][tap][co][ci] = w[co][ci][tap];  wpack[1][tap][ci][co] = w[co][ci][8 - tap]   (tap = ky*3 + kx)
-int launch_pack_weights(const float* w, float* wpack, int cin, int cout, cudaStream_t s);
+// round_tf32: round the packed weights to the nearest TF32 value (TF32 mode; the tcgen05 unit truncates its operands)
+int launch_pack_weights(const float* w, float* wpack, int cin, int cout, int round_tf32, cudaStream_t s);
 // gw[co][ci][tap] = gwpack[tap][co][ci]
 int launch_unpack_wgrad(const float* gwpack, float* gw, int cin, int cout, cudaStream_t s);
 // first layer (Cin = 1): fused instance-minmax scaler + specaugment mask + 3x3 stencil.
