@@ -87,6 +87,7 @@ _SIGS = {
     "sedk_adam_ema_dev": (i32, [vp, vp, vp, vp, vp, i64, i32, f32, f32, f32, vp, vp]),
     "sedk_bump_counter": (i32, [vp, u64, vp]),
     "sedk_sumsq": (i32, [vp, i64, vp, vp]),
+    "sedk_mask_spans": (i32, [vp, i32, i32, i32, i32, i32, u64, vp, u64, vp]),
     "sedk_median_filter": (i32, [vp, vp, i32, i32, i32, i64, i64, i64, i64, i64, i64, vp, vp]),
     "sedk_crnn_forward": (i32, [C.POINTER(CrnnPlan), vp]),
     "sedk_crnn_backward": (i32, [C.POINTER(CrnnPlan), vp]),

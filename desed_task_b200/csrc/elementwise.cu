@@ -391,6 +391,45 @@ extern "C" int sedk_bump_counter(uint64_t* counter, uint64_t inc, void* stream) 
     return SEDK_OK;
 }
 
+// torchaudio mask_along_axis_iid draws (functional.py:857-869) for two masked axes at once, on the device:
+//   value = u * param;  min = u' * (size - value);  span = [floor(min), floor(min) + floor(value))
+// out[b] = {start_a, end_a, start_b, end_b}; param < 1 disables an axis (span 0, 0).  One Philox call per example.
+namespace sedk {
+namespace {
+__global__ void mask_spans_kernel(int32_t* __restrict__ out, int B, int size_a, int param_a, int size_b, int param_b,
+                                  uint64_t seed, const uint64_t* __restrict__ seed_dev, uint64_t stream_id) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const Philox ph(seed + (seed_dev ? *seed_dev : 0ull));
+    const uint4 r = ph((uint64_t)b, stream_id);
+    const float k = 2.3283064365386963e-10f;     // 2^-32
+    int sa = 0, ea = 0, sb = 0, eb = 0;
+    if (param_a >= 1) {
+        const float value = (float)r.x * k * (float)param_a;
+        const float mn = (float)r.y * k * ((float)size_a - value);
+        sa = (int)mn;
+        ea = sa + (int)value;
+    }
+    if (param_b >= 1) {
+        const float value = (float)r.z * k * (float)param_b;
+        const float mn = (float)r.w * k * ((float)size_b - value);
+        sb = (int)mn;
+        eb = sb + (int)value;
+    }
+    reinterpret_cast<int4*>(out)[b] = make_int4(sa, ea, sb, eb);
+}
+}  // namespace
+}  // namespace sedk
+
+extern "C" int sedk_mask_spans(int32_t* out, int B, int size_a, int param_a, int size_b, int param_b, uint64_t seed,
+                               const uint64_t* seed_dev, uint64_t stream_id, void* stream) {
+    SEDK_REQUIRE(out && B > 0, "sedk_mask_spans: bad arguments");
+    sedk::mask_spans_kernel<<<sedk::cdiv(B, 128), 128, 0, (cudaStream_t)stream>>>(out, B, size_a, param_a, size_b, param_b,
+                                                                                  seed, seed_dev, stream_id);
+    SEDK_LAUNCH_CHECK("mask_spans_kernel");
+    return SEDK_OK;
+}
+
 extern "C" int sedk_sumsq(const float* g, int64_t n, double* out, void* stream) {
     SEDK_REQUIRE(g && out && n > 0, "sedk_sumsq: bad arguments");
     SEDK_CUDA(cudaMemsetAsync(out, 0, sizeof(double), (cudaStream_t)stream));

@@ -79,6 +79,7 @@ class TrainEngine:
         self.slot_ev = [None, None]
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.fe_stream = torch.cuda.Stream(device=dev)
+        self.teacher_stream = torch.cuda.Stream(device=dev)
         self.buf_free_ev = [None, None]
         self.graphs = [None, None]      # one captured graph per ping-pong buffer
         self.keeps = [None, None]
@@ -121,11 +122,22 @@ class TrainEngine:
             feats = self.mel_buf        # the front-end kernel already wrote the log-mel and the min/max
         emb = self.emb_dev
         cm = self.class_masks
-        strong, weak, ws = self.student.forward_direct(feats, self.minmax, emb, cm)
-        self.ws = ws
         t_strong = t_weak = None
         if self.teacher is not None:
-            t_strong, t_weak, _ = self.teacher.forward_direct(feats, self.minmax, emb, cm)
+            # the teacher's (no-grad) forward is independent of the student's: fork it onto its own stream; inside a
+            # capture the event pair turns it into a parallel branch of the graph
+            cur = torch.cuda.current_stream(self.dev)
+            ev_fork = torch.cuda.Event()
+            ev_fork.record(cur)
+            self.teacher_stream.wait_event(ev_fork)
+            with torch.cuda.stream(self.teacher_stream):
+                t_strong, t_weak, _ = self.teacher.forward_direct(feats, self.minmax, emb, cm)
+                ev_join = torch.cuda.Event()
+                ev_join.record(self.teacher_stream)
+        strong, weak, ws = self.student.forward_direct(feats, self.minmax, emb, cm)
+        self.ws = ws
+        if self.teacher is not None:
+            torch.cuda.current_stream(self.dev).wait_event(ev_join)
         if self.gstrong is None:
             self.gstrong, self.gweak = torch.empty_like(strong), torch.empty_like(weak)
         self.keeps[slot] = (labels_weak, labels_strong, strong, weak, t_strong, t_weak)

@@ -143,6 +143,8 @@ class _Workspace:
                     getattr(G, "g" + nm)[di] = self.gviews[key].data_ptr()
             self.gru.append(d)
             in_dim = 2 * H
+        self.specaug_buf = new(B, 4, dtype=torch.int32, zero=True)
+        self.dropstep_buf = new(B, 4, dtype=torch.int32, zero=True)
         self.rnn_drop = new(B, T, in_dim)
         self.grnn_drop = new(B, T, in_dim)
         self.sof = new(B, T, model.nclass)
@@ -353,37 +355,28 @@ class CRNN(nn.Module):
             new.__dict__[k] = {} if k == "_ws" else copy.deepcopy(v, memo)
         return new
 
-    def _draw_spans(self, B, size, mask_param, p, device):
-        """torchaudio mask_along_axis_iid (functional.py:857-869): value = rand*param; min = rand*(size - value)."""
-        param = mask_param if p == 1.0 else min(mask_param, int(size * p))
-        if param < 1:
-            return None
-        value = torch.rand(B, device=device) * param
-        min_value = torch.rand(B, device=device) * (size - value)
-        start = min_value.long()
-        return start, start + value.long()
+    @staticmethod
+    def _span_param(size, mask_param, p):
+        """torchaudio mask_along_axis_iid (functional.py:857-859): the effective mask parameter; < 1 disables the mask."""
+        return mask_param if p == 1.0 else min(mask_param, int(size * p))
 
-    def _specaug_spans(self, B, n_mels, n_frames, device):
-        """CRNN.apply_specaugment (CRNN.py:207-219): 'freq' mask first, then time mask; same draw order."""
-        fm = self._draw_spans(B, n_mels, self.specaugm_f_l, self.specaugm_f_p, device)
-        tm = self._draw_spans(B, n_frames, self.specaugm_t_l, self.specaugm_t_p, device)
-        if fm is None and tm is None:
+    def _spans(self, buf, B, size_a, param_a, size_b, param_b, seed, stream_id):
+        """One kernel draws both spans of every example (sedk_mask_spans); None when both masks are disabled."""
+        if param_a < 1 and param_b < 1:
             return None
-        z = torch.zeros(B, dtype=torch.long, device=device)
-        fm = fm if fm is not None else (z, z)
-        tm = tm if tm is not None else (z, z)
-        return torch.stack([fm[0], fm[1], tm[0], tm[1]], 1).to(torch.int32).contiguous()
+        check(lib().sedk_mask_spans(ptr(buf), B, size_a, param_a, size_b, param_b, seed,
+                                    _vp(getattr(self, "seed_dev", None)), stream_id, stream_ptr()), "sedk_mask_spans")
+        return buf
 
-    def _dropstep_spans(self, B, frames, device):
+    def _specaug_spans(self, ws, B, n_mels, n_frames, seed):
+        """CRNN.apply_specaugment (CRNN.py:207-219): 'freq' mask first, then time mask."""
+        return self._spans(ws.specaug_buf, B, n_mels, self._span_param(n_mels, self.specaugm_f_l, self.specaugm_f_p),
+                           n_frames, self._span_param(n_frames, self.specaugm_t_l, self.specaugm_t_p), seed, 300)
+
+    def _dropstep_spans(self, ws, B, frames, seed):
         """CRNN.py:288-293: TimeMasking(dropstep_len, iid, p) on x, then on the embeddings."""
-        xm = self._draw_spans(B, frames, self.dropstep_recurrent_len, self.dropstep_recurrent, device)
-        em = self._draw_spans(B, frames, self.dropstep_recurrent_len, self.dropstep_recurrent, device)
-        if xm is None and em is None:
-            return None
-        z = torch.zeros(B, dtype=torch.long, device=device)
-        xm = xm if xm is not None else (z, z)
-        em = em if em is not None else (z, z)
-        return torch.stack([xm[0], xm[1], em[0], em[1]], 1).to(torch.int32).contiguous()
+        prm = self._span_param(frames, self.dropstep_recurrent_len, self.dropstep_recurrent)
+        return self._spans(ws.dropstep_buf, B, frames, prm, frames, prm, seed, 301)
 
     # ------------------------------------------------------------------------------------------------------------
     def _launch_forward(self, ws, x, minmax, embeddings, classes_mask, specaug, dropstep, training, seed):
@@ -449,12 +442,12 @@ class CRNN(nn.Module):
             classes_mask = classes_mask.to(torch.bool).contiguous()
         ws = self._workspace(B, n_mels, n_frames, x.device, emb_shape)
         training = self.training
-        specaug = self._specaug_spans(B, n_mels, n_frames, x.device) if training else None
-        dropstep = None
-        if training and self.use_embeddings and self.dropstep_recurrent:
-            dropstep = self._dropstep_spans(B, ws.Tp, x.device)
         self._fwd_count += 1
         seed = (torch.initial_seed() * 1000003 + self._fwd_count * 7919 + id(self) % 65521) & 0xFFFFFFFFFFFFFFFF
+        specaug = self._specaug_spans(ws, B, n_mels, n_frames, seed) if training else None
+        dropstep = None
+        if training and self.use_embeddings and self.dropstep_recurrent:
+            dropstep = self._dropstep_spans(ws, B, ws.Tp, seed)
         args = (x, minmax, embeddings, classes_mask, specaug, dropstep, training, seed)
         want_grad = torch.is_grad_enabled() and training and any(p.requires_grad for p in self.parameters())
         if autograd is not None:

@@ -143,6 +143,12 @@ SEDK_API int sedk_adam_ema_dev(float* p, const float* g, float* m, float* v, flo
                       float beta2, float eps, const float* hyper, void* stream);
 /* *counter += inc (one thread); pair with sedk_crnn_plan.seed_dev */
 SEDK_API int sedk_bump_counter(uint64_t* counter, uint64_t inc, void* stream);
+/* SpecAugment / dropstep span draws on the device (CRNN.apply_specaugment, desed_task/nnet/CRNN.py:207-219 and :288-293;
+ * torchaudio mask_along_axis_iid semantics: value = u*param, start = floor(u'*(size - value)), end = start + floor(value)):
+ * out int32 [B][4] = {start_a, end_a, start_b, end_b}; param < 1 disables an axis.  Philox keyed by (seed + *seed_dev,
+ * stream_id, example) so that a captured CUDA graph draws fresh spans on every replay. */
+SEDK_API int sedk_mask_spans(int32_t* out, int B, int size_a, int param_a, int size_b, int param_b, uint64_t seed,
+                    const uint64_t* seed_dev, uint64_t stream_id, void* stream);
 /* sum of squares of g into out[0] (double), for gradient clipping (2024 recipe gradient_clip 5.0) */
 SEDK_API int sedk_sumsq(const float* g, int64_t n, double* out, void* stream);
 

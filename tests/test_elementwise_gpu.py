@@ -156,3 +156,26 @@ def test_median_filter(dev):
     for k in (1, 2, 4, 8, 31):                               # even windows and the maximum size
         got = median_filter(torch.from_numpy(big[:2]).to(dev), k, class_dim=2).cpu().numpy()
         assert np.array_equal(got[1], opost.median_filter_time(big[1], k))
+
+
+def test_mask_spans_follow_torchaudio_iid_semantics(dev):
+    """sedk_mask_spans: value = u*param, start = floor(u'*(size - value)), end = start + floor(value) per example and axis
+    (torchaudio mask_along_axis_iid, functional.py:857-869); widths in [0, param), spans inside the axis, fresh draws per
+    seed / device counter, param < 1 disables an axis."""
+    from desed_task_b200._lib import check, lib, ptr
+    B = 4096
+    out = torch.zeros(B, 4, dtype=torch.int32, device=dev)
+    ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(lib().sedk_mask_spans(ptr(out), B, 128, 10, 626, 5, 1234, ptr(ctr), 300, None), "sedk_mask_spans")
+    a = out.cpu().numpy().astype(np.int64)
+    wf, wt = a[:, 1] - a[:, 0], a[:, 3] - a[:, 2]
+    assert (a[:, 0] >= 0).all() and (a[:, 1] <= 128).all() and (wf >= 0).all() and (wf <= 9).all()
+    assert (a[:, 2] >= 0).all() and (a[:, 3] <= 626).all() and (wt >= 0).all() and (wt <= 4).all()
+    assert abs(wf.mean() - 4.5) < 0.25 and abs(wt.mean() - 2.0) < 0.15          # floor(U[0,10)) / floor(U[0,5))
+    assert abs(a[:, 2].mean() - 0.5 * (626 - 2.5)) < 12                         # start ~ U[0, size - value)
+    ctr += 1
+    out2 = torch.zeros_like(out)
+    check(lib().sedk_mask_spans(ptr(out2), B, 128, 10, 626, 5, 1234, ptr(ctr), 300, None), "sedk_mask_spans")
+    assert (out2 != out).any()
+    check(lib().sedk_mask_spans(ptr(out2), B, 128, 0, 626, 5, 1234, ptr(ctr), 300, None), "sedk_mask_spans")
+    assert (out2[:, :2] == 0).all() and (out2[:, 3] >= out2[:, 2]).all()
