@@ -15,13 +15,18 @@
 // addressing is base + column * C.
 // Persistent CTAs; z tiles double-buffered in shared memory (2 x 64 KB) next to the resident W' (64 KB); accumulators
 // double-buffered in TMEM (2 x 128 columns) so that the MMA of tile i+1 overlaps the epilogue of tile i.
+//
+// 64-channel layers run on the SAME kernels: two row-halves of a tile are stacked on the M / K axes, i.e. MMA row
+// m = (h, n) is channel n of the pixels in half h, the weight operand is the 128 x 128 block-diagonal diag(W, W), and the
+// B operand row of pixel column px is [z(half 0, px, 0..63) | z(half 1, px, 0..63)] (two TMA boxes per K chunk pair).
+// Half the MMA work multiplies zeros - irrelevant here, the layer is bound by its element-wise work and HBM traffic.
 #include "kernels.h"
 #include "tc5.cuh"
 
 namespace sedk {
 namespace {
 
-constexpr int GT_C = 128;                        // channels (MMA M and K)
+constexpr int GT_C = 128;                        // MMA M and K: 128 channels, or 2 halves x 64 channels
 constexpr int GT_NPX = 128;                      // pixels per tile (MMA N)
 constexpr int GT_CHUNK = GT_NPX * 128;           // bytes of one 32-channel chunk of a tile: 128 rows x 128 B
 constexpr int GT_TILE = 4 * GT_CHUNK;            // 64 KB
@@ -31,24 +36,31 @@ constexpr size_t GT_SMEM_FWD = (size_t)3 * GT_TILE + 1024 + 256;
 
 // ------------------------------------------------------------------------------------------------------------------------
 // bn_finalize + gate-weight preparation: one block per gate output n, one thread per input channel k.
-//   pack[0 .. C*C)      W'[n][k] = Wg[n][k] * scale[k]        (forward A operand)
-//   pack[C*C .. 2*C*C)  WT[k][n] = Wg[n][k]                   (backward A operand: g_y^T = WT g_lin^T)
-//   pack[2*C*C .. +C)   b'[n]    = bg[n] + sum_k Wg[n][k] * shift[k]
+//   pack[0 .. 128*128)            W'[n][k] = Wg[n][k] * scale[k]       (forward A operand; block-diagonal for C = 64)
+//   pack[128*128 .. 2*128*128)    WT[k][n] = Wg[n][k]                  (backward A operand: g_y^T = WT g_lin^T)
+//   pack[2*128*128 .. +C)         b'[n]    = bg[n] + sum_k Wg[n][k] * shift[k]
+//   pack[2*128*128+128 .. +128*128)  scratch of the gate weight-gradient GEMM (C = 64 only)
+constexpr int GT_PACK_B = 2 * GT_C * GT_C;       // offset of b'
+constexpr int GT_PACK_RAW = 2 * GT_C * GT_C + GT_C;
+template <int C>
 __global__ void __launch_bounds__(GT_C)
 glu_prep_kernel(const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                 float* __restrict__ rm, float* __restrict__ rv, int64_t* __restrict__ nb, float* __restrict__ bn,
                 const float* __restrict__ glu_w, const float* __restrict__ glu_b, float* __restrict__ pack, double count,
                 float eps, float momentum, int training) {
-    constexpr int C = GT_C;
-    __shared__ float red[C / 32];
-    const int n = blockIdx.x, k = threadIdx.x;
+    constexpr int M = GT_C;
+    __shared__ float red[M / 32];
+    // pack row m = (h, n), column j = (h', k); the blocks h != h' of the two 128 x 128 operands are zero
+    const int m = blockIdx.x, j = threadIdx.x;
+    const int n = m & (C - 1), k = j & (C - 1);
+    const bool diag = (m / C) == (j / C);
     float mean, invstd;
     double unbiased = 0.0;
     if (training) {
-        const double m = stats[k] / count;
-        double var = stats[C + k] / count - m * m;
+        const double mu = stats[k] / count;
+        double var = stats[C + k] / count - mu * mu;
         if (var < 0.0) var = 0.0;
-        mean = (float)m;
+        mean = (float)mu;
         invstd = (float)(1.0 / sqrt(var + (double)eps));
         unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
     } else {
@@ -59,17 +71,18 @@ glu_prep_kernel(const double* __restrict__ stats, const float* __restrict__ gamm
     const float shift = beta[k] - mean * scale;
     const float w = glu_w[n * C + k];
     // rounded to the nearest TF32 value here: the tensor core truncates what it reads
-    pack[n * C + k] = __uint_as_float(to_tf32(w * scale));
-    pack[C * C + k * C + n] = __uint_as_float(to_tf32(w));
-    float part = warp_sum(w * shift);
-    if ((k & 31) == 0) red[k >> 5] = part;
+    pack[m * M + j] = diag ? __uint_as_float(to_tf32(w * scale)) : 0.f;
+    // WT2[(h, kk)][(h', nn)] = Wg[nn][kk]: with (m, j) = ((h, kk), (h', nn)) that is glu_w[k * C + n]
+    pack[M * M + m * M + j] = diag ? __uint_as_float(to_tf32(glu_w[k * C + n])) : 0.f;
+    float part = warp_sum(j < C ? w * shift : 0.f);
+    if ((j & 31) == 0) red[j >> 5] = part;
     __syncthreads();
-    if (k == 0) {
+    if (j == 0 && m < C) {
         float s = glu_b[n];
-        for (int i = 0; i < C / 32; i++) s += red[i];
-        pack[2 * C * C + n] = s;
+        for (int i = 0; i < M / 32; i++) s += red[i];
+        pack[2 * M * M + n] = s;
     }
-    if (n == 0) {
+    if (m == 0 && j < C) {
         // the last reader of the running statistics is this block itself (all other blocks only read stats / gamma / beta)
         if (training) {
             rm[k] = (1.0f - momentum) * rm[k] + momentum * mean;
@@ -84,8 +97,8 @@ glu_prep_kernel(const double* __restrict__ stats, const float* __restrict__ gamm
 }
 
 struct GtGeom {
-    int T, F, TT, TF, nTt, To, Fo;      // pooling (1, 2): To = T, Fo = F / 2; one tile column (TF == F)
-    int tf_shift;
+    int T, F, TTh, TT, nTt, Fo;         // pooling (1, 2): Fo = F / 2; tile = TT full rows = (128 / C) halves of TTh rows,
+                                        // TTh * F = 128 pixel columns per half
 };
 
 // byte offset of element (pixel row p, channel-in-chunk `lane`) inside a 128-byte-swizzled [128 rows x 32 fp32] chunk
@@ -107,12 +120,13 @@ __device__ __forceinline__ uint32_t gt_keep8(const Philox& ph, int tile, int g8,
     return bits;
 }
 
+template <int C>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 bnglu_tc5_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW,
                      const float* __restrict__ bn, const float* __restrict__ bprime, float* __restrict__ out,
                      float* __restrict__ lin_out, GtGeom gm, int total_tiles, uint32_t thresh16, float inv_keep,
                      uint64_t seed, const uint64_t* __restrict__ seed_dev, uint64_t dstream) {
-    constexpr int C = GT_C;
+    constexpr int CH = C / 32;                                  // 32-channel chunks per half
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* aligned = smem_raw + (base - smem_u32(smem_raw));
@@ -168,8 +182,9 @@ bnglu_tc5_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
                 const int b = tile / gm.nTt, t0 = (tile - b * gm.nTt) * gm.TT;
                 mbar_wait_u32(smem_u32(&zempty[s]), ph ^ 1);
                 mbar_expect_tx(&zfull[s], GT_TILE);
-                for (int c = 0; c < 4; c++)
-                    tma_load_4d(z_smem + s * GT_TILE + c * GT_CHUNK, &tmZ, smem_u32(&zfull[s]), c * 32, 0, t0, b);
+                for (int c = 0; c < 4; c++)     // chunk c = (half c / CH, channels 32 (c % CH) ..)
+                    tma_load_4d(z_smem + s * GT_TILE + c * GT_CHUNK, &tmZ, smem_u32(&zfull[s]), (c % CH) * 32, 0,
+                                t0 + (c / CH) * gm.TTh, b);
             }
         }
     } else if (warp == 1) {
@@ -191,16 +206,16 @@ bnglu_tc5_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
             }
         }
     } else {
-        // ---- epilogue: this thread owns channel n = 32 q + lane (TMEM lane) and the pixel columns [c0, c0 + 32)
+        // ---- epilogue: this thread owns TMEM lane m = 32 q + lane = channel n of row-half h, pixel columns [c0, c0 + 32)
         const int q = warp & 3, c0 = 32 * ((warp - 2) >> 2);
-        const int n = 32 * q + lane;
+        const int m = 32 * q + lane, n = m & (C - 1), h = m / C;
         const float sc = bn[n], sh = bn[C + n], bp = bprime[n];
         const Philox ph(seed + (seed_dev ? *seed_dev : 0ull));
         const uint32_t swz_hi = (uint32_t)(lane >> 2), swz_lo = (uint32_t)((lane & 3) << 2);
         for (int it = 0; it < my_tiles; it++) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int s = it & 1, phs = (it >> 1) & 1;
-            const int b = tile / gm.nTt, t0 = (tile - b * gm.nTt) * gm.TT;
+            const int b = tile / gm.nTt, t0 = (tile - b * gm.nTt) * gm.TT + h * gm.TTh;
             const int pvalid = (gm.T - t0) * gm.F - c0;               // columns i < pvalid of this warp's 32 are real pixels
             const size_t row0 = (size_t)b * gm.T + t0;
             float* lrow = lin_out != nullptr ? lin_out + (row0 * gm.F + c0) * C + n : nullptr;
@@ -213,7 +228,7 @@ bnglu_tc5_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
 #pragma unroll
             for (int g8 = 0; g8 < 4; g8++) {
                 uint32_t kb = 0xffu;
-                if (thresh16 != 0u) kb = gt_keep8(ph, tile, (c0 >> 3) + g8, n, dstream, thresh16);
+                if (thresh16 != 0u) kb = gt_keep8(ph, tile, (c0 >> 3) + g8, m, dstream, thresh16);
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) {
                     const int i = 8 * g8 + e;                           // even pixel of a pooling pair
@@ -263,13 +278,14 @@ bnglu_tc5_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
 //     dWg[n][k] = scale[k] * (g_lin^T z)[n][k] + shift[k] * sum_px g_lin[px][n].
 constexpr size_t GT_SMEM_BWD = (size_t)3 * GT_TILE + 1024 + 256;
 
+template <int C>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 bnglu_tc5_bwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW,
                      const float* __restrict__ bn, const float* __restrict__ gout, float* __restrict__ lin_glin,
                      float* __restrict__ gy, float* __restrict__ gglu_b, double* __restrict__ stats, GtGeom gm,
                      int total_tiles, uint32_t thresh16, float inv_keep, uint64_t seed,
                      const uint64_t* __restrict__ seed_dev, uint64_t dstream) {
-    constexpr int C = GT_C;
+    constexpr int CH = C / 32;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* aligned = smem_raw + (base - smem_u32(smem_raw));
@@ -323,7 +339,8 @@ bnglu_tc5_bwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
                 const int b = tile / gm.nTt, t0 = (tile - b * gm.nTt) * gm.TT;
                 mbar_wait_u32(smem_u32(zempty), (it & 1) ^ 1);
                 mbar_expect_tx(zfull, GT_TILE);
-                for (int c = 0; c < 4; c++) tma_load_4d(z_smem + c * GT_CHUNK, &tmZ, smem_u32(zfull), c * 32, 0, t0, b);
+                for (int c = 0; c < 4; c++)
+                    tma_load_4d(z_smem + c * GT_CHUNK, &tmZ, smem_u32(zfull), (c % CH) * 32, 0, t0 + (c / CH) * gm.TTh, b);
             }
         }
     } else if (warp == 1) {
@@ -343,7 +360,7 @@ bnglu_tc5_bwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
         }
     } else {
         const int q = warp & 3, c0 = 32 * ((warp - 2) >> 2);
-        const int n = 32 * q + lane;
+        const int m = 32 * q + lane, n = m & (C - 1), h = m / C;
         const float sc = bn[n], sh = bn[C + n], is = bn[3 * C + n], mi = -bn[2 * C + n] * bn[3 * C + n];
         const Philox ph(seed + (seed_dev ? *seed_dev : 0ull));
         const uint32_t swz_hi = (uint32_t)(lane >> 2), swz_lo = (uint32_t)((lane & 3) << 2);
@@ -352,7 +369,7 @@ bnglu_tc5_bwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
         uint8_t* gs = aligned + 2 * GT_TILE + (size_t)q * GT_CHUNK + (size_t)c0 * 128;
         for (int it = 0; it < my_tiles; it++) {
             const int tile = blockIdx.x + it * gridDim.x;
-            const int b = tile / gm.nTt, t0 = (tile - b * gm.nTt) * gm.TT;
+            const int b = tile / gm.nTt, t0 = (tile - b * gm.nTt) * gm.TT + h * gm.TTh;
             const int pvalid = (gm.T - t0) * gm.F - c0;
             const size_t row0 = (size_t)b * gm.T + t0;
             float* lrow = lin_glin + (row0 * gm.F + c0) * C + n;
@@ -371,7 +388,7 @@ bnglu_tc5_bwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
 #pragma unroll
                 for (int g8 = 0; g8 < 2; g8++) {
                     uint32_t kb = 0xffu;
-                    if (thresh16 != 0u) kb = gt_keep8(ph, tile, (c0 >> 3) + 2 * hb + g8, n, dstream, thresh16);
+                    if (thresh16 != 0u) kb = gt_keep8(ph, tile, (c0 >> 3) + 2 * hb + g8, m, dstream, thresh16);
 #pragma unroll
                     for (int e = 0; e < 8; e++) {
                         const int i = 16 * hb + 8 * g8 + e;
@@ -425,21 +442,27 @@ bnglu_tc5_bwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
     }
 }
 
-// dWg[n][k] = scale[k] * raw[n][k] + shift[k] * sum_px g_lin[px][n]   (in place; raw = g_lin^T z, gglu_b = sum g_lin)
-__global__ void glu_wgrad_fix_kernel(float* __restrict__ gglu_w, const float* __restrict__ gglu_b, const float* __restrict__ bn) {
-    constexpr int C = GT_C;
+// dWg[n][k] = scale[k] * raw[n][k] + shift[k] * sum_px g_lin[px][n]   (raw = g_lin^T z, gglu_b = sum g_lin).
+// C = 128: raw IS gglu_w (in place).  C = 64: raw is the 128 x 128 product of the pixel-pair views; its two diagonal
+// 64 x 64 blocks are the sums over even / odd pixels, the off-diagonal blocks are cross terms and are dropped.
+template <int C>
+__global__ void glu_wgrad_fix_kernel(float* __restrict__ gglu_w, const float* __restrict__ raw, const float* __restrict__ gglu_b,
+                                     const float* __restrict__ bn) {
     const int n = blockIdx.x, k = threadIdx.x;
-    gglu_w[n * C + k] = fmaf(bn[k], gglu_w[n * C + k], bn[C + k] * gglu_b[n]);
+    float r;
+    if (C == GT_C) r = raw[n * GT_C + k];
+    else r = raw[n * GT_C + k] + raw[(C + n) * GT_C + C + k];
+    gglu_w[n * C + k] = fmaf(bn[k], r, bn[C + k] * gglu_b[n]);
 }
 
-inline bool make_gtgeom(GtGeom& g, int T, int F, int pt, int pf) {
-    if (pt != 1 || pf != 2) return false;
-    if (F != 16 && F != 8 && F != 4 && F != 2) return false;
-    g.T = T; g.F = F; g.TF = F; g.TT = GT_NPX / F;
+inline bool make_gtgeom(GtGeom& g, int T, int F, int C, int pt, int pf) {
+    if (pt != 1 || pf != 2 || (C != 64 && C != 128)) return false;
+    if (F < 2 || F > 64 || (F & (F - 1)) != 0) return false;
+    g.T = T; g.F = F;
+    g.TTh = GT_NPX / F;
+    g.TT = g.TTh * (GT_C / C);
     g.nTt = cdiv(T, g.TT);
-    g.To = T; g.Fo = F / 2;
-    g.tf_shift = 0;
-    while ((1 << g.tf_shift) < F) g.tf_shift++;
+    g.Fo = F / 2;
     return true;
 }
 
@@ -451,15 +474,16 @@ inline uint32_t drop_threshold16(float p) {
     return (uint32_t)t;
 }
 
-int make_maps(const float* z, const float* wmat, int B, const GtGeom& gm, CUtensorMap* tmZ, CUtensorMap* tmW) {
+int make_maps(const float* z, const float* wmat, int B, int C, const GtGeom& gm, CUtensorMap* tmZ, CUtensorMap* tmW) {
     EncodeTiledFn enc = encode_fn();
     SEDK_REQUIRE(enc != nullptr, "bnglu_tc5: cuTensorMapEncodeTiled is not available from the driver");
     SEDK_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(wmat) & 15) == 0,
                  "bnglu_tc5: operands must be 16-byte aligned");
     {
-        cuuint64_t dims[4] = {(cuuint64_t)GT_C, (cuuint64_t)gm.F, (cuuint64_t)gm.T, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)GT_C * 4, (cuuint64_t)gm.F * GT_C * 4, (cuuint64_t)gm.T * gm.F * GT_C * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)gm.TF, (cuuint32_t)gm.TT, 1};
+        // one box = one 32-channel chunk of one row-half: TTh full rows x F columns = 128 pixels
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)gm.F, (cuuint64_t)gm.T, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)gm.F * C * 4, (cuuint64_t)gm.T * gm.F * C * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)gm.F, (cuuint32_t)gm.TTh, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(tmZ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(z), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -479,81 +503,119 @@ int make_maps(const float* z, const float* wmat, int B, const GtGeom& gm, CUtens
     return SEDK_OK;
 }
 
+template <int C>
+int run_gt_fwd(const CUtensorMap& tmZ, const CUtensorMap& tmW, const float* bn, const float* pack, float* out, float* lin_out,
+               const GtGeom& gm, int tiles, float drop_p, uint64_t seed, const uint64_t* seed_dev, uint64_t drop_stream,
+               cudaStream_t s) {
+    static bool cfg = false;
+    if (!cfg) {
+        int rc = opt_in_smem(bnglu_tc5_fwd_kernel<C>, GT_SMEM_FWD);
+        if (rc) return rc;
+        cfg = true;
+    }
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    bnglu_tc5_fwd_kernel<C><<<grid, GT_THREADS, GT_SMEM_FWD, s>>>(tmZ, tmW, bn, pack + GT_PACK_B, out, lin_out, gm, tiles,
+                                                                  drop_threshold16(drop_p),
+                                                                  drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed,
+                                                                  seed_dev, drop_stream);
+    SEDK_LAUNCH_CHECK("bnglu_tc5_fwd_kernel");
+    return SEDK_OK;
+}
+
+template <int C>
+int run_gt_bwd(const CUtensorMap& tmZ, const CUtensorMap& tmW, const float* bn, const float* gout, float* lin_glin, float* gy,
+               float* gglu_b, double* stats, const GtGeom& gm, int tiles, float drop_p, uint64_t seed,
+               const uint64_t* seed_dev, uint64_t drop_stream, cudaStream_t s) {
+    static bool cfg = false;
+    if (!cfg) {
+        int rc = opt_in_smem(bnglu_tc5_bwd_kernel<C>, GT_SMEM_BWD);
+        if (rc) return rc;
+        cfg = true;
+    }
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    bnglu_tc5_bwd_kernel<C><<<grid, GT_THREADS, GT_SMEM_BWD, s>>>(tmZ, tmW, bn, gout, lin_glin, gy, gglu_b, stats, gm, tiles,
+                                                                  drop_threshold16(drop_p),
+                                                                  drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed,
+                                                                  seed_dev, drop_stream);
+    SEDK_LAUNCH_CHECK("bnglu_tc5_bwd_kernel");
+    return SEDK_OK;
+}
+
 }  // namespace
 
 bool bnglu_tc5_supports(int T, int F, int C, int pt, int pf, int precision) {
     GtGeom g;
-    return C == GT_C && precision == 0 && tc5_enabled() && get_option("bnglu_tc5", 1) != 0 && make_gtgeom(g, T, F, pt, pf);
+    return precision == 0 && tc5_enabled() && get_option("bnglu_tc5", 1) != 0 && make_gtgeom(g, T, F, C, pt, pf);
 }
+
+int bnglu_tc5_pack_floats() { return GT_PACK_RAW + GT_C * GT_C; }
 
 int launch_glu_prep(const double* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
                     int64_t* num_batches, float* bn, const float* glu_w, const float* glu_b, float* pack, double count,
                     float eps, float momentum, int training, int C, cudaStream_t s) {
     SEDK_PROF("glu_prep", s);
-    SEDK_REQUIRE(C == GT_C, "glu_prep: C must be %d", GT_C);
-    glu_prep_kernel<<<GT_C, GT_C, 0, s>>>(stats, gamma, beta, running_mean, running_var, num_batches, bn, glu_w, glu_b, pack,
-                                          count, eps, momentum, training);
+    SEDK_REQUIRE(C == 64 || C == 128, "glu_prep: C must be 64 or 128");
+    if (C == 128)
+        glu_prep_kernel<128><<<GT_C, GT_C, 0, s>>>(stats, gamma, beta, running_mean, running_var, num_batches, bn, glu_w, glu_b,
+                                                   pack, count, eps, momentum, training);
+    else
+        glu_prep_kernel<64><<<GT_C, GT_C, 0, s>>>(stats, gamma, beta, running_mean, running_var, num_batches, bn, glu_w, glu_b,
+                                                  pack, count, eps, momentum, training);
     SEDK_LAUNCH_CHECK("glu_prep_kernel");
     return SEDK_OK;
 }
 
 int launch_bnglu_tc5_fwd(const float* z, const float* bn, const float* pack, float* out, float* lin_out, int B, int T, int F,
-                         int pt, int pf, float drop_p, uint64_t seed, const uint64_t* seed_dev, uint64_t drop_stream,
+                         int C, int pt, int pf, float drop_p, uint64_t seed, const uint64_t* seed_dev, uint64_t drop_stream,
                          cudaStream_t s) {
-    SEDK_PROF("bnglu_tc5_fwd_c128", s);
+    char pname[64];
+    snprintf(pname, sizeof(pname), "bnglu_tc5_fwd_c%d", C);
+    SEDK_PROF(pname, s);
     GtGeom gm;
-    SEDK_REQUIRE(make_gtgeom(gm, T, F, pt, pf), "bnglu_tc5: unsupported geometry");
+    SEDK_REQUIRE(make_gtgeom(gm, T, F, C, pt, pf), "bnglu_tc5: unsupported geometry");
     CUtensorMap tmZ, tmW;
-    int rc = make_maps(z, pack, B, gm, &tmZ, &tmW);
+    int rc = make_maps(z, pack, B, C, gm, &tmZ, &tmW);
     if (rc) return rc;
-    static bool cfg = false;
-    if (!cfg) {
-        rc = opt_in_smem(bnglu_tc5_fwd_kernel, GT_SMEM_FWD);
-        if (rc) return rc;
-        cfg = true;
-    }
     const int tiles = B * gm.nTt;
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    bnglu_tc5_fwd_kernel<<<grid, GT_THREADS, GT_SMEM_FWD, s>>>(tmZ, tmW, bn, pack + 2 * GT_C * GT_C, out, lin_out, gm, tiles,
-                                                               drop_threshold16(drop_p),
-                                                               drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed, seed_dev,
-                                                               drop_stream);
-    SEDK_LAUNCH_CHECK("bnglu_tc5_fwd_kernel");
-    return SEDK_OK;
+    if (C == 128)
+        return run_gt_fwd<128>(tmZ, tmW, bn, pack, out, lin_out, gm, tiles, drop_p, seed, seed_dev, drop_stream, s);
+    return run_gt_fwd<64>(tmZ, tmW, bn, pack, out, lin_out, gm, tiles, drop_p, seed, seed_dev, drop_stream, s);
 }
 
 int launch_bnglu_tc5_bwd(const float* z, const float* bn, const float* pack, const float* gout, float* lin_glin, float* gy,
-                         float* gglu_b, double* stats, int B, int T, int F, int pt, int pf, float drop_p, uint64_t seed,
+                         float* gglu_b, double* stats, int B, int T, int F, int C, int pt, int pf, float drop_p, uint64_t seed,
                          const uint64_t* seed_dev, uint64_t drop_stream, cudaStream_t s) {
-    SEDK_PROF("bnglu_tc5_bwd_c128", s);
+    char pname[64];
+    snprintf(pname, sizeof(pname), "bnglu_tc5_bwd_c%d", C);
+    SEDK_PROF(pname, s);
     GtGeom gm;
-    SEDK_REQUIRE(make_gtgeom(gm, T, F, pt, pf), "bnglu_tc5: unsupported geometry");
+    SEDK_REQUIRE(make_gtgeom(gm, T, F, C, pt, pf), "bnglu_tc5: unsupported geometry");
     CUtensorMap tmZ, tmW;
-    int rc = make_maps(z, pack + GT_C * GT_C, B, gm, &tmZ, &tmW);          // A operand = WT
+    int rc = make_maps(z, pack + GT_C * GT_C, B, C, gm, &tmZ, &tmW);          // A operand = WT
     if (rc) return rc;
-    static bool cfg = false;
-    if (!cfg) {
-        rc = opt_in_smem(bnglu_tc5_bwd_kernel, GT_SMEM_BWD);
-        if (rc) return rc;
-        cfg = true;
-    }
     const int tiles = B * gm.nTt;
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    bnglu_tc5_bwd_kernel<<<grid, GT_THREADS, GT_SMEM_BWD, s>>>(tmZ, tmW, bn, gout, lin_glin, gy, gglu_b, stats, gm, tiles,
-                                                               drop_threshold16(drop_p),
-                                                               drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed, seed_dev,
-                                                               drop_stream);
-    SEDK_LAUNCH_CHECK("bnglu_tc5_bwd_kernel");
-    return SEDK_OK;
+    if (C == 128)
+        return run_gt_bwd<128>(tmZ, tmW, bn, gout, lin_glin, gy, gglu_b, stats, gm, tiles, drop_p, seed, seed_dev, drop_stream, s);
+    return run_gt_bwd<64>(tmZ, tmW, bn, gout, lin_glin, gy, gglu_b, stats, gm, tiles, drop_p, seed, seed_dev, drop_stream, s);
 }
 
-// gglu_w (zeroed by the caller) <- g_lin^T z on tcgen05, then the BatchNorm-fold fix-up; needs gglu_b = sum g_lin complete
-int launch_glu_wgrad_tc5(const float* z, const float* g_lin, const float* bn, float* gglu_w, const float* gglu_b, int B, int T,
-                         int F, cudaStream_t s) {
-    int rc = launch_tn_gemm_tc5_c128(z, g_lin, gglu_w, B, T, F, s);
+// gglu_w <- BatchNorm-fold fix-up of g_lin^T z (tcgen05 TN GEMM over all pixels); needs gglu_b = sum g_lin complete.
+// C = 128: the product accumulates straight into gglu_w (which must be zero on entry); C = 64: the 64-channel tensors are
+// viewed as [.., F / 2, 128] pixel pairs, the 128 x 128 product goes to the scratch area of `pack` (zeroed here).
+int launch_glu_wgrad_tc5(const float* z, const float* g_lin, const float* bn, float* pack, float* gglu_w, const float* gglu_b,
+                         int B, int T, int F, int C, cudaStream_t s) {
+    float* raw = gglu_w;
+    int Fv = F;
+    if (C == 64) {
+        raw = pack + GT_PACK_RAW;
+        Fv = F / 2;
+        SEDK_CUDA(cudaMemsetAsync(raw, 0, (size_t)GT_C * GT_C * sizeof(float), s));
+    }
+    int rc = launch_tn_gemm_tc5_c128(z, g_lin, raw, B, T, Fv, s);
     if (rc) return rc;
     SEDK_PROF("glu_wgrad_fix", s);
-    glu_wgrad_fix_kernel<<<GT_C, GT_C, 0, s>>>(gglu_w, gglu_b, bn);
+    if (C == 128) glu_wgrad_fix_kernel<128><<<128, 128, 0, s>>>(gglu_w, raw, gglu_b, bn);
+    else glu_wgrad_fix_kernel<64><<<64, 64, 0, s>>>(gglu_w, raw, gglu_b, bn);
     SEDK_LAUNCH_CHECK("glu_wgrad_fix_kernel");
     return SEDK_OK;
 }

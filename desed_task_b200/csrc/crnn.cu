@@ -162,7 +162,7 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
             rc = launch_glu_prep(L.stats, L.gamma, L.beta, L.running_mean, L.running_var, L.num_batches, L.bn, L.glu_w,
                                  L.glu_b, L.glu_pack, (double)B * L.T * L.F, p->bn_eps, p->bn_momentum, p->training, C, s);
             if (rc) return rc;
-            rc = launch_bnglu_tc5_fwd(L.z, L.bn, L.glu_pack, L.out, p->training ? L.lin : nullptr, B, L.T, L.F, L.pt, L.pf,
+            rc = launch_bnglu_tc5_fwd(L.z, L.bn, L.glu_pack, L.out, p->training ? L.lin : nullptr, B, L.T, L.F, C, L.pt, L.pf,
                                       pdrop, p->seed, p->seed_dev, (uint64_t)i, s);
             if (rc) return rc;
             continue;
@@ -338,14 +338,14 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
         if (!zs) SEDK_CUDA(cudaMemsetAsync(L.stats + 2 * Cc, 0, 2 * Cc * sizeof(double), s));
         if (!zb) SEDK_CUDA(cudaMemsetAsync(L.gglu_b, 0, (size_t)Cc * sizeof(float), s));
         if (use_glu_tc5(p, L)) {
-            rc = launch_bnglu_tc5_bwd(L.z, L.bn, L.glu_pack, L.gout, L.lin, L.gy, L.gglu_b, L.stats, B, L.T, L.F, L.pt, L.pf,
-                                      pdrop, p->seed, p->seed_dev, (uint64_t)i, s);
+            rc = launch_bnglu_tc5_bwd(L.z, L.bn, L.glu_pack, L.gout, L.lin, L.gy, L.gglu_b, L.stats, B, L.T, L.F, Cc, L.pt,
+                                      L.pf, pdrop, p->seed, p->seed_dev, (uint64_t)i, s);
             if (rc) return rc;
             // gate weight gradient = g_lin^T z over all pixels: off the chain
             rc = fk.forked ? fk.sync_side_to_main() : fk.begin();
             if (rc) return rc;
             if (!zb) SEDK_CUDA(cudaMemsetAsync(L.gglu_w, 0, (size_t)Cc * Cc * sizeof(float), fk.side_s));
-            rc = launch_glu_wgrad_tc5(L.z, L.lin, L.bn, L.gglu_w, L.gglu_b, B, L.T, L.F, fk.side_s);
+            rc = launch_glu_wgrad_tc5(L.z, L.lin, L.bn, L.glu_pack, L.gglu_w, L.gglu_b, B, L.T, L.F, Cc, fk.side_s);
             if (rc) return rc;
         } else {
         if (!zb) SEDK_CUDA(cudaMemsetAsync(L.gglu_w, 0, (size_t)Cc * Cc * sizeof(float), s));

@@ -66,17 +66,18 @@ int launch_bnglu_small_bwd(const float* z, const float* bn, const float* glu_w, 
 // bnglu_tc5.cu: tcgen05 / TMEM / TMA BN+GLU(+dropout+pool (1,2)) for the 128-channel layers, TF32 mode.
 //   launch_glu_prep = bn_finalize + gate-weight packs: pack = [W' = Wg*scale | WT = Wg^T | b' = bg + Wg shift]
 bool bnglu_tc5_supports(int T, int F, int C, int pt, int pf, int precision);
+int bnglu_tc5_pack_floats();     // size of the `glu_pack` workspace (floats)
 int launch_glu_prep(const double* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
                     int64_t* num_batches, float* bn, const float* glu_w, const float* glu_b, float* pack, double count,
                     float eps, float momentum, int training, int C, cudaStream_t s);
 int launch_bnglu_tc5_fwd(const float* z, const float* bn, const float* pack, float* out, float* lin_out, int B, int T, int F,
-                         int pt, int pf, float drop_p, uint64_t seed, const uint64_t* seed_dev, uint64_t drop_stream,
+                         int C, int pt, int pf, float drop_p, uint64_t seed, const uint64_t* seed_dev, uint64_t drop_stream,
                          cudaStream_t s);
 int launch_bnglu_tc5_bwd(const float* z, const float* bn, const float* pack, const float* gout, float* lin_glin, float* gy,
-                         float* gglu_b, double* stats, int B, int T, int F, int pt, int pf, float drop_p, uint64_t seed,
+                         float* gglu_b, double* stats, int B, int T, int F, int C, int pt, int pf, float drop_p, uint64_t seed,
                          const uint64_t* seed_dev, uint64_t drop_stream, cudaStream_t s);
-int launch_glu_wgrad_tc5(const float* z, const float* g_lin, const float* bn, float* gglu_w, const float* gglu_b, int B, int T,
-                         int F, cudaStream_t s);
+int launch_glu_wgrad_tc5(const float* z, const float* g_lin, const float* bn, float* pack, float* gglu_w, const float* gglu_b,
+                         int B, int T, int F, int C, cudaStream_t s);
 // train-mode BN backward: gy -> gz in place; writes ggamma, gbeta (and zero conv-bias grad gb)
 int launch_bn_bwd_apply(float* gy, const float* z, const float* bn, const double* stats, float* ggamma, float* gbeta,
                         float* gb, double count, int64_t n_pix, int C, cudaStream_t s);

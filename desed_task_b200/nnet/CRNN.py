@@ -99,8 +99,8 @@ class _Workspace:
                 out=new(B, T // pt, F // pf, C), gout=new(B, T // pt, F // pf, C),
                 stats=self.zero_fwd[st_off[i]:st_off[i] + 4 * C], bn=new(4 * C, zero=True),
                 # tcgen05 BN+GLU path of the 128-channel layers (include/sedk.h: glu_pack, lin)
-                glu_pack=new(2 * C * C + C, zero=True) if C == 128 else None,
-                lin=new(B, T, F, C) if C == 128 else None)
+                glu_pack=new(3 * 128 * 128 + 128, zero=True) if C in (64, 128) else None,
+                lin=new(B, T, F, C) if C in (64, 128) else None)
             for k, v in d.items():
                 setattr(L, k, _vp(v))
             pre = "cnn.cnn."

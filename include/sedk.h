@@ -189,8 +189,10 @@ typedef struct {
     float* gout;            /* grad wrt out                                                    */
     double* stats;          /* [4][cout]: sum z, sum z^2, sum gy, sum gy*zhat                   */
     float* bn;              /* [4][cout]: scale, shift, mean, invstd (saved for backward)      */
-    /* optional, cout == 128 layers only (NULL: the mma.sync BN+GLU kernels are used): workspace of the tcgen05 BN+GLU path */
-    float* glu_pack;        /* [2*cout*cout + cout]: BN-folded gate weight, transposed gate weight, folded bias */
+    /* optional, cout in {64, 128} layers only (NULL: the mma.sync BN+GLU kernels are used): workspace of the tcgen05
+     * BN+GLU path */
+    float* glu_pack;        /* [3*128*128 + 128]: BN-folded gate weight, transposed gate weight (both 128 x 128, block-
+                               diagonal for cout = 64), folded bias, weight-gradient scratch                           */
     float* lin;             /* [B,T,F,cout]: gate pre-activation saved by the forward; the backward overwrites it with
                                g_lin (the gate-output gradient), the operand of the gate weight-gradient GEMM          */
 } sedk_conv_layer;
