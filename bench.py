@@ -119,6 +119,13 @@ def kernel_work(name, B):
         if name.startswith("bnglu_pool_bwd"):
             return 6.0 * C * C * pix, 4.0 * pix * C * (2 + 1 / pool)
         return 8.0 * pix * C, 4.0 * pix * C * 3
+    if name.startswith("bnglu_tc5_fwd_c") or name.startswith("bnglu_tc5_bwd_c"):
+        C = int(name.rsplit("_c", 1)[1])
+        cands = [x for x in geo if x["cout"] == C]
+        pix = sum(x["pix"] for x in cands) / len(cands)
+        if "_fwd_" in name:       # z in, lin out (saved for backward), pooled out
+            return 2.0 * C * C * pix, 4.0 * pix * C * 2.5
+        return 2.0 * C * C * pix, 4.0 * pix * C * 4.5          # z, lin, gout/2 in; g_lin, gy out
     if name == "conv0_fwd":
         g = geo[0]
         return 2.0 * 9 * g["cout"] * g["pix"], 4.0 * g["pix"] * (2 + g["cout"])
@@ -273,9 +280,21 @@ def run_ours(args):
             roof = {"bound": "tensor", "achieved": round(flops / avg_ms / 1e9, 2), "peak": pk["bf16_tflops_sustained"],
                     "unit": "TFLOP/s"}
         roof["frac"] = round(roof["achieved"] / roof["peak"], 4)
+        if dom.startswith("gru_seq"):
+            roof["note"] = ("latency-bound persistent recurrence: 156 dependent time steps per launch, %.2f us per step on "
+                            "%d of the SMs; neither HBM nor the tensor pipe can bound it (DESIGN.md section 4)"
+                            % (avg_ms * 1e3 / 156.0, 2 * B))
+        # measured DRAM traffic of that kernel (dram__bytes_read.sum + dram__bytes_write.sum per launch) from the committed
+        # ncu full-set capture, when there is one (profiles/traffic.json: {kernel family: bytes per launch})
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        except Exception:
+            pass
+        roof["traffic"] = traffic
         roof.update({"kernel": dom, "avg_launch_ms": round(avg_ms, 5), "launches_per_step": dcnt / NP,
                      "share_of_step": round(dtot / NP / step_ms_eager, 4), "peak_source": pk_kind + " (MEASURED_PEAKS.json"
-                     " bf16 sustained / hbm copy; TF32 nominal is half the bf16 rate)", "traffic": None,
+                     " bf16 sustained / hbm copy; TF32 nominal is half the bf16 rate)",
                      "algorithmic_flops": flops, "algorithmic_bytes": nbytes})
         top5 = [{"kernel": k, "ms_per_step": round(v[1] / NP, 4), "launches_per_step": v[0] / NP} for k, v in top]
         # ---- front-end bandwidth (the second headline: mel GB/s vs HBM peak)
