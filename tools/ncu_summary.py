@@ -80,6 +80,51 @@ def launch_table(path):
     return "\n".join(out)
 
 
+def family(name):
+    """ncu kernel name -> the launcher family name bench.py's per-kernel breakdown uses."""
+    n = short(name)
+    m = re.search(r"<(?:\(int\))?(\d+)", name)
+    c = m.group(1) if m else ""
+    if "gru_fwd" in n:
+        return "gru_seq_fwd"
+    if "gru_bwd" in n:
+        return "gru_seq_bwd"
+    if "logmel" in n:
+        return "logmel"
+    if "bnglu_tc5_fwd" in n:
+        return "bnglu_tc5_fwd_c" + c
+    if "bnglu_tc5_bwd" in n:
+        return "bnglu_tc5_bwd_c" + c
+    if "bnglu_small_fwd" in n or "bnglu_fwd" in n:
+        return "bnglu_pool_fwd_c" + c
+    if "bnglu_small_bwd" in n or "bnglu_bwd" in n:
+        return "bnglu_pool_bwd_c" + c
+    if "conv0_fwd" in n:
+        return "conv0_fwd"
+    if "conv0_wgrad" in n:
+        return "conv0_wgrad"
+    return n.split("<")[0].split("::")[-1]
+
+
+def traffic_json(path):
+    """{family: mean dram__bytes_read.sum + dram__bytes_write.sum per launch} from a `--page raw --csv` export."""
+    import json
+    hdr, units, data = load(path)
+    ki = hdr.index("Kernel Name")
+    ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    agg = {}
+    for r in data:
+        try:
+            b = float(r[ri].replace(",", "")) * scale.get(units[ri], 1.0) + float(r[wi].replace(",", "")) * scale.get(units[wi], 1.0)
+        except ValueError:
+            continue
+        a = agg.setdefault(family(r[ki]), [0, 0.0])
+        a[0] += 1
+        a[1] += b
+    return json.dumps({k: round(v[1] / v[0]) for k, v in sorted(agg.items())}, indent=1)
+
+
 if __name__ == "__main__":
     mode, path = sys.argv[1], sys.argv[2]
-    print(raw_table(path) if mode == "raw" else launch_table(path))
+    print(raw_table(path) if mode == "raw" else traffic_json(path) if mode == "traffic" else launch_table(path))
