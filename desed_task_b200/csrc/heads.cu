@@ -116,37 +116,50 @@ heads_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dw, cons
                  float* __restrict__ gx, float* __restrict__ gdw, float* __restrict__ gdb, float* __restrict__ gsw,
                  float* __restrict__ gsb, int T, int D, int C) {
     __shared__ float gl[HT][2 * HC_MAX];
+    extern __shared__ float wst[];                       // [2 * HC_MAX][256]: this thread's weight-gradient sums, by class
     const int b = blockIdx.y, tid = threadIdx.x;
     const int tc = blockIdx.x * HT;
     const int nt = min(HT, T - tc);
-    if (tid < nt) {
-        const int t = tc + tid;
+    {
+        // 8 lanes per time step, classes strided over the lanes: every load of the step is in flight at once (one lane per
+        // step walked the classes serially: ~20 dependent global-latency round trips before the GEMM part could start)
+        const int tl = tid >> 3, cl = tid & 7;
+        const bool live = tl < nt;
+        const int t = tc + tl;
+        float p4[4], s4[4], ga4[4], gst4[4], den4[4], gw4[4];
         float S = 0.f;
-        for (int c = 0; c < C; c++) {
-            const bool ok = !cmask || cmask[b * C + c];
-            const float p = sof[((size_t)b * T + t) * C + c];
-            const float s = strong[((size_t)b * C + c) * T + t];
-            const float gw = (ok && gweak) ? gweak[b * C + c] : 0.f;
-            const float den = hsum[(b * 2 + 1) * C + c];
-            const float wk = hsum[(b * 2) * C + c] / den;
-            const float ga = gw * (s - wk) / den;
-            const float gp = (p >= 1e-7f && p <= 1.0f) ? ga : 0.f;
-            S += gp * p;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int c = cl + 8 * q;
+            p4[q] = s4[q] = ga4[q] = gst4[q] = gw4[q] = 0.f;
+            den4[q] = 1.f;
+            if (live && c < C) {
+                const bool ok = !cmask || cmask[b * C + c];
+                const float p = sof[((size_t)b * T + t) * C + c];
+                const float sv = strong[((size_t)b * C + c) * T + t];
+                const float gw = (ok && gweak) ? gweak[b * C + c] : 0.f;
+                const float gst = (ok && gstrong) ? gstrong[((size_t)b * C + c) * T + t] : 0.f;
+                const float den = hsum[(b * 2 + 1) * C + c];
+                const float wk = hsum[(b * 2) * C + c] / den;
+                const float ga = gw * (sv - wk) / den;
+                p4[q] = p; s4[q] = sv; ga4[q] = ga; gst4[q] = gst; den4[q] = den; gw4[q] = gw;
+                const float gp = (p >= 1e-7f && p <= 1.0f) ? ga : 0.f;
+                S += gp * p;
+            }
         }
-        for (int c = 0; c < C; c++) {
-            const bool ok = !cmask || cmask[b * C + c];
-            const float p = sof[((size_t)b * T + t) * C + c];
-            const float a = fminf(fmaxf(p, 1e-7f), 1.0f);
-            const float s = strong[((size_t)b * C + c) * T + t];
-            const float gw = (ok && gweak) ? gweak[b * C + c] : 0.f;
-            const float gst = (ok && gstrong) ? gstrong[((size_t)b * C + c) * T + t] : 0.f;
-            const float den = hsum[(b * 2 + 1) * C + c];
-            const float wk = hsum[(b * 2) * C + c] / den;
-            const float ga = gw * (s - wk) / den;
-            const float gp = (p >= 1e-7f && p <= 1.0f) ? ga : 0.f;
-            const float gs = gst + gw * a / den;
-            gl[tid][c] = gs * s * (1.0f - s);
-            gl[tid][HC_MAX + c] = p * (gp - S);
+#pragma unroll
+        for (int o = 1; o <= 4; o <<= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int c = cl + 8 * q;
+            if (live && c < C) {
+                const float p = p4[q], sv = s4[q];
+                const float a = fminf(fmaxf(p, 1e-7f), 1.0f);
+                const float gp = (p >= 1e-7f && p <= 1.0f) ? ga4[q] : 0.f;
+                const float gs = gst4[q] + gw4[q] * a / den4[q];
+                gl[tl][c] = gs * sv * (1.0f - sv);
+                gl[tl][HC_MAX + c] = p * (gp - S);
+            }
         }
     }
     __syncthreads();
@@ -185,12 +198,22 @@ heads_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dw, cons
                 }
             }
         }
+        // Every CTA adds into the same 2 C D addresses: started at class 0 everywhere, ~120 CTAs would queue on one L2
+        // atomic unit at a time (measured: the atomics, not the math, set this kernel's time).  Stage the per-thread sums in
+        // shared memory and let each CTA walk the classes from its own offset.
 #pragma unroll
         for (int c = 0; c < HC_MAX; c++) {
             if (c < C) {
-                atomicAdd(&gdw[c * D + k], ad[c]);
-                atomicAdd(&gsw[c * D + k], as[c]);
+                wst[c * 256 + tid] = ad[c];
+                wst[(HC_MAX + c) * 256 + tid] = as[c];
             }
+        }
+        const int rot = (blockIdx.x + blockIdx.y * gridDim.x) % C;
+        for (int i = 0; i < C; i++) {
+            int c = rot + i;
+            if (c >= C) c -= C;
+            atomicAdd(&gdw[c * D + k], wst[c * 256 + tid]);
+            atomicAdd(&gsw[c * D + k], wst[(HC_MAX + c) * 256 + tid]);
         }
     }
     for (int c = tid; c < 2 * C; c += 256) {
@@ -403,8 +426,15 @@ int launch_heads_bwd(const float* x, const float* dw, const float* sw, const uin
     SEDK_PROF("heads_bwd", s);
     SEDK_REQUIRE(C >= 1 && C <= HC_MAX, "heads: nclass %d must be in [1, %d]", C, HC_MAX);
     dim3 grid(cdiv(T, HT), B);
-    heads_bwd_kernel<<<grid, 256, 0, s>>>(x, dw, sw, cmask, strong, hsum, sof, gstrong, gweak, gx, gdw, gdb, gsw, gsb, T, D,
-                                          C);
+    const size_t smem = (size_t)2 * HC_MAX * 256 * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        int rc = opt_in_smem(heads_bwd_kernel, smem);
+        if (rc) return rc;
+        configured = true;
+    }
+    heads_bwd_kernel<<<grid, 256, smem, s>>>(x, dw, sw, cmask, strong, hsum, sof, gstrong, gweak, gx, gdw, gdb, gsw, gsb, T,
+                                             D, C);
     SEDK_LAUNCH_CHECK("heads_bwd_kernel");
     return SEDK_OK;
 }
