@@ -80,3 +80,17 @@ def test_unsupported_front_end_configs_raise():
         MelSpectrogram(16000, 1024, 1024, 256, n_mels=64, power=1)
     with pytest.raises(NotImplementedError):
         MelSpectrogram(16000, 2048, 2048, 256, n_mels=128, power=2.0)
+
+
+def test_kernel_variant_switches(built, monkeypatch):
+    """sedk_set_option / sedk_get_option (include/sedk.h): explicit values win, unset names fall back to the environment
+    variable SEDK_<NAME> and then to the caller's default; no CUDA call is involved."""
+    from desed_task_b200 import _lib
+    L = _lib.lib()
+    assert L.sedk_get_option(b"never_set_by_anyone", 7) == 7
+    assert L.sedk_get_option(b"never_set_by_anyone", 3) == 7          # the first lookup pins the value
+    monkeypatch.setenv("SEDK_FROM_THE_ENVIRONMENT", "5")
+    assert L.sedk_get_option(b"from_the_environment", 1) == 5
+    assert L.sedk_set_option(b"gru_v2", 0) == 0 and L.sedk_get_option(b"gru_v2", 1) == 0
+    assert L.sedk_set_option(b"gru_v2", 1) == 0 and L.sedk_get_option(b"gru_v2", 0) == 1
+    assert L.sedk_set_option(None, 1) == -1
