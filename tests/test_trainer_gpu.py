@@ -211,3 +211,77 @@ def test_predict_with_median_filter(dev):
     assert maxdiff(strong, so) < 2e-5 and maxdiff(weak, wo) < 2e-5
     ref = opost.median_filter_time(strong[1].t().cpu().numpy(), 7)
     assert np.array_equal(med[1].t().cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_engine_on_the_2024_network(dev, use_graph):
+    """BASELINE config 4 shape of the fused engine: the dcase2024 CRNN (27 classes, 192-unit BiGRU as a 3-CTA cluster,
+    BEATs-sized frame embeddings fused by pool1d, per-row class masks), mean teacher, gradient clipping
+    (pretrained.yaml:17 uses 5.0; 0.5 here so that the clip is active on this batch: |g| = 0.73) - two consecutive steps
+    against the oracle (losses, clipped update, EMA)."""
+    from desed_task_b200.engine import TrainEngine
+    from desed_task_b200.frontend import MelSpectrogram
+    from desed_task_b200.optim import FusedAdam
+    from desed_task_b200.utils.schedulers import ExponentialWarmup
+    from tests.test_crnn_gpu import build
+    cfg = dataclasses.replace(ocrnn.CFG_2024, dropout=0.0)
+    P = ocrnn.init_params(cfg, seed=5, trained_like=True)
+    student = build(cfg, P, dev, 1, specaugm_t_p=0.0, specaugm_f_p=0.0, dropstep_recurrent=0.0)
+    teacher = copy.deepcopy(student)
+    for p in teacher.parameters():
+        p.detach_()
+    student.train(); teacher.train()
+    mel = MelSpectrogram(16000, 2048, 2048, 256, 0, 8000, n_mels=128, window_fn=torch.hamming_window,
+                         wkwargs={"periodic": False}, power=1).to(dev)
+    g = torch.Generator().manual_seed(11)
+    audio = gen_wave(31, 8)
+    emb = torch.randn(8, 768, 496, generator=g)
+    cm = torch.zeros(8, 27, dtype=torch.bool)
+    cm[:4, :10] = True                                    # DESED rows: the 10 DESED classes
+    cm[4:, 10:] = True                                    # MAESTRO rows: the other 17
+    labels = (torch.rand(8, 27, 156, generator=g) < 0.15).float() * cm[:, :, None].float()
+    labels[2:4, :, 1:] = 0
+    opt = FusedAdam(student, 1e-3)
+    sched = ExponentialWarmup(opt, 1e-3, 100)
+    eng = TrainEngine(student, mel, BS, 160000, opt=opt, scheduler=sched, teacher=teacher, mixup_type=None,
+                      use_graph=use_graph, grad_clip=0.5, emb_shape=(768, 496), class_masks=cm.to(dev))
+    # ---- oracle: same two steps
+    names = ocrnn.param_names(P)
+    Ps = {k: (v.clone().requires_grad_(True) if ocrnn.is_float_param(k) else v.clone()) for k, v in P.items()}
+    Pt = {k: v.clone() for k, v in P.items()}
+    state, ref = {}, []
+    for step in (1, 2):
+        bs, bt = {}, {}
+        kw = dict(embeddings=emb, classes_mask=cm)
+        out = otr.mean_teacher_step(Ps, Pt, audio, labels, BS, step, 100, cfg, 2.0, None, "soft", gru_impl="aten",
+                                    student_kw=dict(bn_state=bs, **kw), teacher_kw=dict(bn_state=bt, **kw))
+        grads = list(torch.autograd.grad(out["tot_loss"], [Ps[k] for k in names]))
+        norm = torch.sqrt(sum((gg.double() ** 2).sum() for gg in grads)).item()
+        clip = min(1.0, 0.5 / (norm + 1e-6))               # torch.nn.utils.clip_grad_norm_
+        assert clip < 1.0
+        grads = [gg * clip for gg in grads]
+        with torch.no_grad():
+            otr.update_ema(0.999, step, Ps, Pt, names)
+            otr.adam_step({k: Ps[k] for k in names}, dict(zip(names, grads)), state, names,
+                          1e-3 if step == 1 else 1e-3 * otr.warmup_scale(step, 100))
+            for k, v in bs.items():
+                Ps[k] = v
+            for k, v in bt.items():
+                Pt[k] = v
+        ref.append((out["tot_loss"].item(), out["loss_strong"].item(), out["loss_weak"].item(), norm))
+    a_pin, l_pin, e_pin = audio.pin_memory(), labels.pin_memory(), emb.pin_memory()
+    for step in range(2):
+        r = eng.step(a_pin, l_pin, e_pin)
+        got = eng.read_losses(r)
+        assert abs(got["total"] - ref[step][0]) < 5e-4, (step, got, ref[step])
+        assert abs(got["bce_strong"] - ref[step][1]) < 2e-4 and abs(got["bce_weak"] - ref[step][2]) < 2e-4
+    torch.cuda.synchronize()
+    tot = bad = 0
+    for n, p in student.named_parameters():
+        if _noise_param(n):
+            continue
+        d = (p.detach().cpu() - Ps[n].detach()).abs()
+        assert d.max().item() <= 4.1e-3, n
+        tot += d.numel()
+        bad += int((d > 2e-4).sum())
+    assert bad / tot < 0.01, (bad, tot)
