@@ -171,7 +171,7 @@ constexpr int WG_THREADS = 192;
 template <int CIN, int TT, int TF, int NDX = 3>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_tc5_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
-                      float* __restrict__ gwp, int T, int F, int total_tiles, int dbg) {
+                      float* __restrict__ gwp, int T, int F, int total_tiles) {
     static_assert(TT * TF == WG_KPIX, "K tile must hold 32 pixels");
     constexpr int COUT = 128;
     constexpr int NCH = CIN / 32;                                   // 32-channel chunks of x
@@ -271,20 +271,11 @@ conv_wgrad_tc5_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
             for (int c = 0; c < NCH; c++) {
                 uint32_t v[32];
                 tmem_ld32(v, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(dx * CIN + c * 32));
-                if (dbg == 1) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = __float_as_uint(1.0f);
-                }
-                if (dbg == 2) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) atomicAdd(grow + c * 32 + j, __uint_as_float(v[j]));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        atomicAdd(reinterpret_cast<float4*>(grow + c * 32) + j,
-                                  make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
-                }
+                for (int j = 0; j < 8; j++)
+                    atomicAdd(reinterpret_cast<float4*>(grow + c * 32) + j,
+                              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -365,9 +356,7 @@ int run_wgrad_tc5(const CUtensorMap& tmG, const CUtensorMap& tmX, float* gwp, in
     int gx = num_sms() / NDX;
     if (gx > tiles) gx = tiles;
     dim3 grid(gx, NDX);
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("SEDK_WG_DBG"); dbg = e ? atoi(e) : 0; }
-    kern<<<grid, WG_THREADS, smem, s>>>(tmG, tmX, gwp, T, F, tiles, dbg);
+    kern<<<grid, WG_THREADS, smem, s>>>(tmG, tmX, gwp, T, F, tiles);
     SEDK_LAUNCH_CHECK("conv_wgrad_tc5_kernel");
     return SEDK_OK;
 }
