@@ -34,6 +34,34 @@ __global__ void pack_kernel(const float* __restrict__ w, float* __restrict__ wp,
     wp[i] = rnd ? __uint_as_float(to_tf32(v)) : v;
 }
 
+// Paired-pixel packs for a 16-channel layer (cin_l -> cout_l with one side = 16): two horizontally adjacent pixels are
+// viewed as one pixel with twice the channels, [.., F, C] == [.., F / 2, 2 C], so that the 3x3 convolution becomes a
+// 2 cin_l -> 2 cout_l convolution whose operand rows are >= 128 bytes (what the tcgen05 kernel tiles).  With output pixel
+// (P, ho), input pixel (P + dP, hi) the original horizontal tap is dx = 2 dP + hi - ho + 1; taps outside {0, 1, 2} are zero.
+//   wp[0 .. 9*2co*2ci)  forward  [tap'][(ho, co)][(hi, ci)] = w[co][ci][dy][dx],             tap' = dy * 3 + (dP + 1)
+//   wp[9*2co*2ci .. )   dgrad    [tap'][(hi, ci)][(ho, co)] = w[co][ci][2 - dy][2 - dx'],    dx' = 2 dP + ho - hi + 1
+__global__ void pack_pair_kernel(const float* __restrict__ w, float* __restrict__ wp, int cin, int cout) {
+    const int n = 9 * 4 * cin * cout;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n) return;
+    const int r = i % n;
+    const int tap = r / (4 * cin * cout), dy = tap / 3, dP = tap % 3 - 1;
+    int co, ci, ho, hi, dx;
+    float v = 0.f;
+    if (i < n) {
+        const int row = (r / (2 * cin)) % (2 * cout), col = r % (2 * cin);       // row = (ho, co), col = (hi, ci)
+        ho = row / cout; co = row % cout; hi = col / cin; ci = col % cin;
+        dx = 2 * dP + hi - ho + 1;
+        if (dx >= 0 && dx <= 2) v = w[((size_t)co * cin + ci) * 9 + dy * 3 + dx];
+    } else {
+        const int row = (r / (2 * cout)) % (2 * cin), col = r % (2 * cout);      // row = (hi, ci), col = (ho, co)
+        hi = row / cin; ci = row % cin; ho = col / cout; co = col % cout;
+        dx = 2 * dP + ho - hi + 1;
+        if (dx >= 0 && dx <= 2) v = w[((size_t)co * cin + ci) * 9 + (2 - dy) * 3 + (2 - dx)];
+    }
+    wp[i] = __uint_as_float(to_tf32(v));
+}
+
 __global__ void unpack_kernel(const float* __restrict__ gwp, float* __restrict__ gw, int cin, int cout) {
     const int n = 9 * cin * cout;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -524,8 +552,27 @@ int launch_with_smem(K kernel, dim3 grid, size_t smem, cudaStream_t s, const cha
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
+// Off by default.  Measured on B200 (layer 1 of the 2023 CRNN, 24 clips): the paired tcgen05 convolution takes 0.189 ms
+// forward / 0.102 ms data-gradient against 0.079 / 0.065 ms for the halo-staged mma.sync kernel - with only 32 (paired)
+// input channels the per-tap TMA re-fetch of the activation tile (9 x) and the 1920-CTA BatchNorm-statistics atomics cost
+// more than the tensor pipe gains.  Kept as a parity-tested option ("conv_pair" = 1).
+bool conv_pair_mode(int cin_l, int cout_l, int F, int precision) {
+    return precision == 0 && tc5_enabled() && get_option("conv_pair", 0) != 0 && (F % 2) == 0 && F >= 4 &&
+           ((cin_l == 16 && cout_l == 32) || (cin_l == 32 && cout_l == 16)) && tc5_supports(2 * cin_l, 2 * cout_l);
+}
+int conv_wpack_floats(int cin_l, int cout_l) {
+    const int plain = 2 * 9 * cin_l * cout_l;
+    return (cin_l == 16 || cout_l == 16) ? 4 * plain : plain;
+}
+
 int launch_pack_weights(const float* w, float* wpack, int cin, int cout, int round_tf32, cudaStream_t s) {
     SEDK_PROF("pack_weights", s);
+    if (round_tf32 == 2) {          // paired-pixel packs (the caller asked conv_pair_mode)
+        int n = 2 * 9 * 4 * cin * cout;
+        pack_pair_kernel<<<cdiv(n, 256), 256, 0, s>>>(w, wpack, cin, cout);
+        SEDK_LAUNCH_CHECK("pack_pair_kernel");
+        return SEDK_OK;
+    }
     int n = 2 * 9 * cin * cout;
     pack_kernel<<<cdiv(n, 256), 256, 0, s>>>(w, wpack, cin, cout, round_tf32);
     SEDK_LAUNCH_CHECK("pack_kernel");
@@ -607,10 +654,21 @@ static int run_conv_tiles(const float* in, const float* wp, const float* bias, f
     return run_conv<CIN, NT, 64, 2>(in, wp, bias, out, stats, B, T, F, cout, precision, s);
 }
 
+int launch_conv3x3_layer(const float* in, const float* wpack_base, int dgrad, const float* bias, float* out, double* stats,
+                         int B, int T, int F, int cin_l, int cout_l, int precision, cudaStream_t s) {
+    const int cin = dgrad ? cout_l : cin_l, cout = dgrad ? cin_l : cout_l;     // channels of THIS convolution
+    if (conv_pair_mode(cin_l, cout_l, F, precision)) {
+        const float* wp = wpack_base + (dgrad ? (size_t)9 * 4 * cin_l * cout_l : 0);
+        return launch_conv3x3_tc5(in, wp, bias, out, stats, B, T, F / 2, 2 * cin, 2 * cout, cout, s);
+    }
+    return launch_conv3x3(in, wpack_base + (dgrad ? (size_t)9 * cin_l * cout_l : 0), bias, out, stats, B, T, F, cin, cout,
+                          precision, s);
+}
+
 int launch_conv3x3(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T, int F,
                    int cin, int cout, int precision, cudaStream_t s) {
     if (precision == 0 && tc5_enabled() && tc5_supports(cin, cout))
-        return launch_conv3x3_tc5(in, wp, bias, out, stats, B, T, F, cin, cout, s);
+        return launch_conv3x3_tc5(in, wp, bias, out, stats, B, T, F, cin, cout, cout, s);
     char pname[64];
     snprintf(pname, sizeof(pname), "conv3x3_%dto%d_F%d", cin, cout, F);
     SEDK_PROF(pname, s);

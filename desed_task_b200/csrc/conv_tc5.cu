@@ -27,7 +27,10 @@ constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align sla
 template <int CIN, int COUT, int TT, int TF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const float* __restrict__ bias, float* __restrict__ out, double* __restrict__ stats, int T, int F) {
+                   const float* __restrict__ bias, float* __restrict__ out, double* __restrict__ stats, int T, int F,
+                   int cmod) {
+    // cmod: number of REAL output channels behind the COUT MMA columns (COUT, or COUT / 2 in the paired-pixel mode where
+    // column (h, co) is channel co of the pixel with parity h): bias and BatchNorm statistics are indexed modulo cmod
     static_assert(TT * TF == 128, "tile must hold 128 pixels");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;         // 1024-byte aligned (128B swizzle atoms)
@@ -121,7 +124,7 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; j++) {
                 x[j] = __uint_as_float(v[j]);
-                if (bias != nullptr) x[j] += bias[c * 32 + j];
+                if (bias != nullptr) x[j] += bias[(c * 32 + j) % cmod];
             }
             if (valid) {
 #pragma unroll
@@ -145,7 +148,8 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     __syncthreads();
     if (stats != nullptr) {
-        for (int i = tid; i < 2 * TC_C; i += TC_THREADS) atomicAdd(&stats[i], (double)s_stat[i]);
+        for (int i = tid; i < 2 * TC_C; i += TC_THREADS)
+            atomicAdd(&stats[(i / TC_C) * cmod + (i % TC_C) % cmod], (double)s_stat[i]);
     }
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -289,7 +293,7 @@ conv_wgrad_tc5_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
 
 template <int CIN, int COUT, int TT, int TF>
 int run_tc5(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, float* out, double* stats, int B, int T,
-            int F, cudaStream_t s) {
+            int F, int cmod, cudaStream_t s) {
     auto kern = conv3x3_tc5_kernel<CIN, COUT, TT, TF>;
     static bool cfg = false;
     if (!cfg) {
@@ -298,14 +302,14 @@ int run_tc5(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, f
         cfg = true;
     }
     dim3 grid(B * cdiv(T, TT) * cdiv(F, TF));
-    kern<<<grid, TC_THREADS, TC_SMEM, s>>>(tmA, tmB, bias, out, stats, T, F);
+    kern<<<grid, TC_THREADS, TC_SMEM, s>>>(tmA, tmB, bias, out, stats, T, F, cmod);
     SEDK_LAUNCH_CHECK("conv3x3_tc5_kernel");
     return SEDK_OK;
 }
 
 template <int CIN, int COUT>
 int run_tc5_tiles(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T, int F,
-                  cudaStream_t s) {
+                  int cmod, cudaStream_t s) {
     EncodeTiledFn enc = encode_fn();
     SEDK_REQUIRE(enc != nullptr, "conv3x3_tc5: cuTensorMapEncodeTiled is not available from the driver");
     SEDK_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0,
@@ -336,10 +340,10 @@ int run_tc5_tiles(const float* in, const float* wp, const float* bias, float* ou
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SEDK_REQUIRE(r == CUDA_SUCCESS, "conv3x3_tc5: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
     }
-    if (TF == 16) return run_tc5<CIN, COUT, 8, 16>(tmA, tmB, bias, out, stats, B, T, F, s);
-    if (TF == 8) return run_tc5<CIN, COUT, 16, 8>(tmA, tmB, bias, out, stats, B, T, F, s);
-    if (TF == 4) return run_tc5<CIN, COUT, 32, 4>(tmA, tmB, bias, out, stats, B, T, F, s);
-    return run_tc5<CIN, COUT, 64, 2>(tmA, tmB, bias, out, stats, B, T, F, s);
+    if (TF == 16) return run_tc5<CIN, COUT, 8, 16>(tmA, tmB, bias, out, stats, B, T, F, cmod, s);
+    if (TF == 8) return run_tc5<CIN, COUT, 16, 8>(tmA, tmB, bias, out, stats, B, T, F, cmod, s);
+    if (TF == 4) return run_tc5<CIN, COUT, 32, 4>(tmA, tmB, bias, out, stats, B, T, F, cmod, s);
+    return run_tc5<CIN, COUT, 64, 2>(tmA, tmB, bias, out, stats, B, T, F, cmod, s);
 }
 
 template <int CIN, int TT, int TF, int NDX>
@@ -412,12 +416,12 @@ bool tc5_supports(int cin, int cout) {
 }
 
 int launch_conv3x3_tc5(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T,
-                       int F, int cin, int cout, cudaStream_t s) {
+                       int F, int cin, int cout, int cmod, cudaStream_t s) {
     char pname[64];
-    snprintf(pname, sizeof(pname), "conv3x3_tc5_%dto%d_F%d", cin, cout, F);
+    snprintf(pname, sizeof(pname), cmod == cout ? "conv3x3_tc5_%dto%d_F%d" : "conv3x3_tc5_pair_%dto%d_F%d", cin, cout, F);
     SEDK_PROF(pname, s);
 #define SEDK_TC5(CI, CO) \
-    if (cin == CI && cout == CO) return run_tc5_tiles<CI, CO>(in, wp, bias, out, stats, B, T, F, s);
+    if (cin == CI && cout == CO) return run_tc5_tiles<CI, CO>(in, wp, bias, out, stats, B, T, F, cmod, s);
     SEDK_TC5(128, 128) SEDK_TC5(64, 128) SEDK_TC5(128, 64) SEDK_TC5(32, 64) SEDK_TC5(64, 32) SEDK_TC5(64, 64)
     SEDK_TC5(32, 32) SEDK_TC5(128, 32) SEDK_TC5(32, 128)
 #undef SEDK_TC5

@@ -132,7 +132,9 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
     rc = fk.begin();
     if (rc) return rc;
     for (int i = 1; i < p->n_conv; i++) {
-        rc = launch_pack_weights(p->conv[i].w, p->conv[i].wpack, p->conv[i].cin, p->conv[i].cout, p->precision == 0 ? 1 : 0,
+        const sedk_conv_layer& Lp = p->conv[i];
+        rc = launch_pack_weights(Lp.w, Lp.wpack, Lp.cin, Lp.cout,
+                                 conv_pair_mode(Lp.cin, Lp.cout, Lp.F, p->precision) ? 2 : (p->precision == 0 ? 1 : 0),
                                  fk.side_s);
         if (rc) return rc;
     }
@@ -155,7 +157,7 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
                 rc = fk.join();
                 if (rc) return rc;
             }
-            rc = launch_conv3x3(p->conv[i - 1].out, L.wpack, L.b, L.z, st, B, L.T, L.F, L.cin, C, p->precision, s);
+            rc = launch_conv3x3_layer(p->conv[i - 1].out, L.wpack, 0, L.b, L.z, st, B, L.T, L.F, L.cin, C, p->precision, s);
         }
         if (rc) return rc;
         if (use_glu_tc5(p, L)) {
@@ -365,8 +367,7 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
             if (rc) return rc;
             rc = launch_unpack_wgrad(L.gwpack, L.gw, L.cin, Cc, fk.side_s);
             if (rc) return rc;
-            rc = launch_conv3x3(L.gy, L.wpack + (size_t)9 * Cc * L.cin, nullptr, P.gout, nullptr, B, L.T, L.F, Cc, L.cin,
-                                p->precision, s);
+            rc = launch_conv3x3_layer(L.gy, L.wpack, 1, nullptr, P.gout, nullptr, B, L.T, L.F, L.cin, Cc, p->precision, s);
             if (rc) return rc;
         } else {
             if (!zb) SEDK_CUDA(cudaMemsetAsync(L.gw, 0, (size_t)9 * Cc * sizeof(float), s));

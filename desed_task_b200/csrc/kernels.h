@@ -24,6 +24,14 @@ int launch_conv0_wgrad(const float* x0, const float* gz, float* gw, int B, int T
 // The same kernel computes dgrad when given the flipped/transposed pack (wpack[1]).
 int launch_conv3x3(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T, int F,
                    int cin, int cout, int precision, cudaStream_t s);
+// Layer-level entry used by the network: picks the operand pack inside the layer's `wpack` workspace itself.
+//   wpack_base: the buffer launch_pack_weights filled for the layer (cin_l -> cout_l); dgrad = 0: forward (cin_l -> cout_l),
+//   dgrad = 1: data gradient (cout_l -> cin_l, flipped taps).  For 16-channel layers in the TF32 mode the buffer holds the
+//   PAIRED-PIXEL packs (see launch_pack_weights) and the convolution runs on tcgen05 as a 2 cin -> 2 cout layer over F / 2.
+int launch_conv3x3_layer(const float* in, const float* wpack_base, int dgrad, const float* bias, float* out, double* stats,
+                         int B, int T, int F, int cin_l, int cout_l, int precision, cudaStream_t s);
+bool conv_pair_mode(int cin_l, int cout_l, int F, int precision);
+int conv_wpack_floats(int cin_l, int cout_l);   // size of the layer's wpack workspace
 // tcgen05 / TMEM / TMA implicit-GEMM variant for 128 -> 128 channels (TF32); conv_tc5.cu
 bool tc5_enabled();
 void tc5_set(int on);
@@ -32,8 +40,9 @@ bool tc5_wgrad_supports(int cin, int cout);
 int launch_conv_wgrad_tc5(const float* x, const float* gz, float* gwpack, int B, int T, int F, int cin, int cout,
                           cudaStream_t s);
 int launch_tn_gemm_tc5_c128(const float* x, const float* g, float* out, int B, int T, int F, cudaStream_t s);
+// cmod = cout, or cout / 2 in the paired-pixel mode (bias / BatchNorm statistics are indexed modulo cmod)
 int launch_conv3x3_tc5(const float* in, const float* wp, const float* bias, float* out, double* stats, int B, int T,
-                       int F, int cin, int cout, cudaStream_t s);
+                       int F, int cin, int cout, int cmod, cudaStream_t s);
 // gwpack[tap][co][ci] += sum_pix gz[pix][co] * x[pix + shift(tap)][ci]   (gwpack zeroed by the caller)
 int launch_conv_wgrad(const float* x, const float* gz, float* gwpack, int B, int T, int F, int cin, int cout,
                       int precision, cudaStream_t s);

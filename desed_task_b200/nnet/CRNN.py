@@ -93,7 +93,8 @@ class _Workspace:
             L = plan.conv[i]
             L.cin, L.cout, L.T, L.F, L.pt, L.pf = cin, C, T, F, pt, pf
             d = dict(
-                wpack=new(2 * 9 * C * cin) if i > 0 else None,
+                # 16-channel layers: room for the paired-pixel tcgen05 packs (4x the plain pack, kernels.h conv_wpack_floats)
+                wpack=new(2 * 9 * C * cin * (4 if 16 in (C, cin) else 1)) if i > 0 else None,
                 gwpack=self.zero_bwd[gw_off[i]:gw_off[i] + gw_sizes[i]] if i > 0 else None,
                 z=new(B, T, F, C), gy=new(B, T, F, C),
                 out=new(B, T // pt, F // pf, C), gout=new(B, T // pt, F // pf, C),

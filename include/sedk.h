@@ -53,7 +53,9 @@ SEDK_API int sedk_set_gru_cluster(int cs);
  *   "bnglu_small" 1 (default): register-resident warp-autonomous BN+GLU+pool kernels for 16 / 32 channels; 0: tiled kernel
  *   "bnglu_tc5"   1 (default): tcgen05 / TMEM / TMA BN+GLU+pool kernels for the 128-channel layers (TF32 mode)
  *   "gemm_tc5"    1 (default): tcgen05 GEMMs for the GRU input projections and input gradients (TF32 mode)
- *   "side_stream" 1 (default): weight-gradient GEMMs and weight packs on a forked side stream */
+ *   "side_stream" 1 (default): weight-gradient GEMMs and weight packs on a forked side stream
+ *   "conv_pair"   0 (default): 1 runs the 16 <-> 32 channel convolutions on tcgen05 through a paired-pixel view (TF32 mode);
+ *                 measured slower than the halo-staged mma.sync kernel on B200, kept as a parity-tested experiment */
 SEDK_API int sedk_set_option(const char* name, int value);
 SEDK_API int sedk_get_option(const char* name, int dflt);
 /* number of kernels this library has launched (or captured into a CUDA graph) so far in this process */
@@ -181,7 +183,8 @@ typedef struct {
     /* gradients (same layouts), NULL when not training */
     float *gw, *gb, *ggamma, *gbeta, *gglu_w, *gglu_b;
     /* workspace */
-    float* wpack;           /* [2][9][cout][cin]: fwd pack [tap][co][ci] then dgrad pack [tap][ci][co]  */
+    float* wpack;           /* [2][9][cout][cin]: fwd pack [tap][co][ci] then dgrad pack [tap][ci][co]; layers with 16
+                               channels on one side need 4x that size (paired-pixel packs of the tcgen05 path)        */
     float* gwpack;          /* [9][cout][cin] wgrad accumulator                                */
     float* z;               /* conv output (pre-BN) [B,T,F,cout]                               */
     float* gy;              /* grad wrt BN output / conv output (in place) [B,T,F,cout]        */

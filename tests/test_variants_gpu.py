@@ -42,10 +42,11 @@ def _compare(a, b, tol_out, tol_grad):
     assert worst[1] < tol_grad, worst
 
 
-@pytest.mark.parametrize("option", ["gru_v2", "bnglu_small", "bnglu_tc5", "gemm_tc5", "side_stream"])
+@pytest.mark.parametrize("option", ["gru_v2", "bnglu_small", "bnglu_tc5", "gemm_tc5", "side_stream", "conv_pair"])
 @pytest.mark.parametrize("precision,tol_out,tol_grad", [(1, 2e-5, 2e-3), (0, 5e-4, 3e-2)])
 def test_kernel_generations_agree(dev, feats, option, precision, tol_out, tol_grad):
     from desed_task_b200._lib import lib
+    default = 0 if option == "conv_pair" else 1         # library defaults (include/sedk.h)
     res = {}
     for on in (1, 0):
         lib().sedk_set_option(option.encode(), on)
@@ -53,7 +54,7 @@ def test_kernel_generations_agree(dev, feats, option, precision, tol_out, tol_gr
             assert lib().sedk_get_option(option.encode(), -1) == on
             res[on] = _run(dev, feats, precision)
         finally:
-            lib().sedk_set_option(option.encode(), 1)
+            lib().sedk_set_option(option.encode(), default)
     _compare(res[1], res[0], tol_out, tol_grad)
 
 
