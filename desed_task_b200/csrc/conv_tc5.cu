@@ -124,7 +124,7 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; j++) {
                 x[j] = __uint_as_float(v[j]);
-                if (bias != nullptr) x[j] += bias[(c * 32 + j) % cmod];
+                if (bias != nullptr) x[j] += bias[(c * 32 + j) & (cmod - 1)];       // cmod is a power of two
             }
             if (valid) {
 #pragma unroll
@@ -149,7 +149,7 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     __syncthreads();
     if (stats != nullptr) {
         for (int i = tid; i < 2 * TC_C; i += TC_THREADS)
-            atomicAdd(&stats[(i / TC_C) * cmod + (i % TC_C) % cmod], (double)s_stat[i]);
+            atomicAdd(&stats[(i >= TC_C ? cmod : 0) + (i & (cmod - 1))], (double)s_stat[i]);
     }
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
