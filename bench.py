@@ -14,6 +14,7 @@ import argparse
 import ctypes
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -103,14 +104,20 @@ def layer_geometry(B):
 def kernel_work(name, B):
     """Algorithmic FLOPs and minimal HBM bytes of ONE launch of a kernel family."""
     geo = layer_geometry(B)
-    if name.startswith("conv3x3_") or name.startswith("conv_wgrad_"):
-        body = name.split("_", 2 if name.startswith("conv_wgrad") else 1)[-1]
-        ch, fpart = body.split("_F")
-        a, b = [int(v) for v in ch.split("to")]
-        F = int(fpart)
-        g = [x for x in geo if x["F"] == F][0]
-        pix = g["pix"]
+    m = re.match(r"conv(?:3x3|_wgrad)(?:_tc5)?(?:_pair)?_(\d+)to(\d+)_F(\d+)$", name)
+    if m:
+        a, b, F = int(m.group(1)), int(m.group(2)), int(m.group(3))
+        cands = [x for x in geo if x["F"] == F] or [x for x in geo if x["F"] == 2 * F]     # paired view: F / 2, 2 C
+        pix = cands[0]["pix"] if [x for x in geo if x["F"] == F] else cands[0]["pix"] / 2
         return 2.0 * 9 * a * b * pix, 4.0 * pix * (a + b)
+    m = re.match(r"gemm(?:_tc5)?_[NT]{2}_(\d+)x(\d+)x(\d+)_[xk](\d+)$", name)
+    if m:
+        M, N, K, n = [int(v) for v in m.groups()]
+        return 2.0 * M * N * K * n, 4.0 * n * (M * K + K * N) + 4.0 * M * N * (n if "_x" in name else 1)
+    if name.startswith("glu_wgrad_tc5_c"):
+        C = int(name.rsplit("_c", 1)[1])
+        pix = sum(x["pix"] for x in geo if x["cout"] in (64, 128)) / 5.0     # mean over the five launches of a step
+        return 2.0 * C * C * pix, 4.0 * pix * C * 2
     if name.startswith("bnglu_pool_fwd_c") or name.startswith("bnglu_pool_bwd_c") or name.startswith("bn_bwd_apply_c"):
         C = int(name.rsplit("_c", 1)[1])
         cands = [x for x in geo if x["cout"] == C]
