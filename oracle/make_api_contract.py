@@ -32,6 +32,22 @@ def sig(fn):
     return out
 
 
+def ast_methods(path, cls, names):
+    """Signatures of methods of a class whose module cannot be imported here (the recipe trainers need Lightning)."""
+    import ast
+    out = {}
+    for node in ast.parse(open(path).read()).body:
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            for f in node.body:
+                if isinstance(f, ast.FunctionDef) and f.name in names:
+                    a = f.args
+                    pos = [x.arg for x in a.args]
+                    dfl = [None] * (len(pos) - len(a.defaults)) + [ast.unparse(d) for d in a.defaults]
+                    out[f.name] = {"args": [[n, d] for n, d in zip(pos, dfl)], "vararg": a.vararg.arg if a.vararg else None,
+                                   "kwarg": a.kwarg.arg if a.kwarg else None}
+    return out
+
+
 def net_config(path):
     import yaml
     return yaml.safe_load(open(path))["net"]
@@ -61,6 +77,10 @@ def contract():
                           "state_dict": [[k, list(v.shape), str(v.dtype)] for k, v in net.state_dict().items()],
                           "parameters": [n for n, _ in net.named_parameters()],
                           "n_params": sum(p.numel() for p in net.parameters())}
+    # the Lightning module's hot-path surface (recipes/dcase2023_task4_baseline/local/sed_trainer.py:41-55,163,187,253,266,269,358)
+    c["SEDTask4"] = ast_methods(f"{REF}/recipes/dcase2023_task4_baseline/local/sed_trainer.py", "SEDTask4",
+                                ("__init__", "training_step", "update_ema", "detect", "take_log", "lr_scheduler_step",
+                                 "on_before_zero_grad", "configure_optimizers"))
     return c
 
 

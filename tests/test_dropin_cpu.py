@@ -59,6 +59,22 @@ def test_state_dict_and_parameter_order_match_the_reference(tag):
     net.load_state_dict(sd, strict=True)
 
 
+@pytest.mark.parametrize("name", sorted(CONTRACT["SEDTask4"]))
+def test_lightning_module_surface_matches_the_2023_recipe(name):
+    """SEDTask4 hot-path methods: same positional parameters and defaults as recipes/dcase2023_task4_baseline/local/
+    sed_trainer.py (parsed with ast: the recipe module itself needs Lightning); the mirror may only ADD **kwargs."""
+    from desed_task_b200.sed_trainer import SEDTask4
+    ref = CONTRACT["SEDTask4"][name]
+    ps = list(inspect.signature(getattr(SEDTask4, name)).parameters.values())
+    pos = [p for p in ps if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+    got = [[p.name, None if p.default is inspect.Parameter.empty else repr(p.default)] for p in pos]
+    assert got == ref["args"], name
+    if ref["vararg"]:
+        assert any(p.kind == p.VAR_POSITIONAL for p in ps)
+    if ref["kwarg"]:
+        assert any(p.kind == p.VAR_KEYWORD for p in ps)
+
+
 def test_recipe_import_lines_resolve():
     """The import lines of recipes/dcase202{3,4}_task4_baseline/{train_*.py,local/sed_trainer*.py} that belong to the hot path."""
     code = ("import sys; sys.path.insert(0, %r)\n"
