@@ -96,3 +96,37 @@ def test_fixture_is_current_against_the_live_reference():
                          capture_output=True, text=True, cwd="/")
     assert out.returncode == 0, out.stderr[-2000:]
     assert json.loads(out.stdout.strip().splitlines()[-1]) == json.loads(json.dumps(CONTRACT, sort_keys=True))
+
+
+def test_constructor_quirks_of_the_reference_are_kept():
+    """Probe-verified behaviours of desed_task.nnet.CRNN that recipes (silently) rely on - SURVEY.md section 7 'API quirks'."""
+    from desed_task_b200.nnet.CRNN import CRNN
+    cfg = dict(CONTRACT["nets"]["2024"]["config"])
+    assert cfg.get("rnn_layers") == 1                       # the YAML key is `rnn_layers`, the ctor argument `n_layers_RNN`
+    net = CRNN(**cfg)
+    assert net.rnn.rnn.num_layers == 2                      # ... so the 2024 config still builds a 2-layer GRU (CRNN.py:22,37)
+    assert net.train() is None and net.eval() is None       # CRNN.train returns None (CRNN.py:308-323)
+    assert net.training is False
+    with pytest.raises(AttributeError):
+        CRNN(nclass=(10, 17))                               # multi-head + attention crashes in the ctor (CRNN.py:113)
+    CRNN(rnn_type="BLSTM")                                  # a non-BGRU rnn_type does not raise at construction (CRNN.py:101)
+    assert CRNN(**dict(cfg, median_filter=[3] * 27, some_future_key=1)) is not None     # unknown keys are dropped (CNN.py:45)
+
+
+def test_no_cpu_fallback():
+    """The product path fails loudly without a CUDA device: no PyTorch / oracle arithmetic behind the module API."""
+    from desed_task_b200._lib import SedkError
+    from desed_task_b200.data_augm import mixup
+    from desed_task_b200.nnet.CRNN import CRNN
+    from desed_task_b200.utils.scaler import TorchScaler
+    net = CRNN(**CONTRACT["nets"]["2023"]["config"])
+    with pytest.raises(SedkError):
+        net(torch.zeros(1, 128, 626))
+    with pytest.raises(SedkError):
+        mixup(torch.zeros(4, 128, 626), torch.zeros(4, 10, 156))
+    with pytest.raises(SedkError):
+        TorchScaler("instance", "minmax", [1, 2])(torch.zeros(2, 128, 626))
+    import desed_task_b200
+    src = "".join(open(os.path.join(os.path.dirname(desed_task_b200.__file__), f)).read()
+                  for f in ("engine.py", "frontend.py", "data_augm.py", "optim.py", "sed_trainer.py", "nnet/CRNN.py"))
+    assert "import oracle" not in src and "from oracle" not in src
