@@ -126,6 +126,12 @@ class MelSpectrogram(nn.Module):
         self.mel_scale = MelScale(n_mels, sample_rate, f_min, f_max, n_fft // 2 + 1)
         self._tables = {}
 
+    def __getstate__(self):
+        # the table cache holds ctypes structures with device pointers: rebuilt on first use after a copy / unpickle
+        state = dict(self.__dict__)
+        state["_tables"] = {}
+        return state
+
     def tables(self, device):
         key = (str(device), self.spectrogram.window._version, self.mel_scale.fb._version,
                self.spectrogram.window.data_ptr(), self.mel_scale.fb.data_ptr())

@@ -190,6 +190,22 @@ class _Workspace:
         self.param_sig = sig
 
 
+class _NoBackward(torch.autograd.Function):
+    """Eval-mode forward with autograd enabled: the outputs stay attached to the graph (as in the reference) but a backward
+    through the eval-mode network (BatchNorm on running statistics) has no kernel - it raises instead of silently yielding
+    no gradients."""
+
+    @staticmethod
+    def forward(ctx, strong, weak, *params):
+        return strong.view_as(strong), weak.view_as(weak)
+
+    @staticmethod
+    def backward(ctx, gstrong, gweak):
+        raise NotImplementedError("desed_task_b200 CRNN: backward through an eval-mode forward (BatchNorm on running "
+                                  "statistics) is not implemented; call .train() (or freeze_bn=True) before a forward "
+                                  "that needs gradients, or wrap inference in torch.no_grad()")
+
+
 class _CRNNFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, ws, args, *params):
@@ -306,7 +322,24 @@ class CRNN(nn.Module):
         self.embedding_size = embedding_size
         self._ws = {}
         self._fwd_count = 0
+        # deterministic per-instance salt of the dropout / SpecAugment seed (construction order; a deepcopy gets a new one):
+        # two runs under the same seed_everything() draw the same masks, two models in one process draw different ones
+        self._instance = CRNN._next_instance()
         self.seed_dev = None            # optional device uint64 counter added to the dropout seed (CUDA-graph replays)
+
+    _instances = 0
+
+    @staticmethod
+    def _next_instance():
+        CRNN._instances += 1
+        return CRNN._instances
+
+    def __getstate__(self):
+        # workspaces hold ctypes structures full of device pointers: per-process scratch, never pickled / deep-copied
+        # (torch.save(module), Lightning ddp_spawn); they are rebuilt on the first forward
+        state = dict(self.__dict__)
+        state["_ws"] = {}
+        return state
 
     # ------------------------------------------------------------------------------------------------------------
     def _unsupported(self):
@@ -329,6 +362,8 @@ class CRNN(nn.Module):
             return "nclass > 32"
         if self.freeze_bn:
             return "freeze_bn=True"
+        if self.dropstep_recurrent and not self.use_embeddings:
+            return "dropstep_recurrent > 0 without embeddings (CRNN.py:295-301)"
         if self.use_embeddings and self.aggregation_type != "pool1d":
             return "aggregation_type=%r (kernels implement the shipped 'pool1d')" % self.aggregation_type
         return None
@@ -354,6 +389,7 @@ class CRNN(nn.Module):
         import copy
         for k, v in self.__dict__.items():
             new.__dict__[k] = {} if k == "_ws" else copy.deepcopy(v, memo)
+        new._instance = CRNN._next_instance()
         return new
 
     @staticmethod
@@ -444,7 +480,7 @@ class CRNN(nn.Module):
         ws = self._workspace(B, n_mels, n_frames, x.device, emb_shape)
         training = self.training
         self._fwd_count += 1
-        seed = (torch.initial_seed() * 1000003 + self._fwd_count * 7919 + id(self) % 65521) & 0xFFFFFFFFFFFFFFFF
+        seed = (torch.initial_seed() * 1000003 + self._fwd_count * 7919 + self._instance * 104729) & 0xFFFFFFFFFFFFFFFF
         specaug = self._specaug_spans(ws, B, n_mels, n_frames, seed) if training else None
         dropstep = None
         if training and self.use_embeddings and self.dropstep_recurrent:
@@ -455,7 +491,10 @@ class CRNN(nn.Module):
             want_grad = autograd
         if want_grad:
             return _CRNNFunction.apply(self, ws, args, *list(self.parameters()))
-        return self._launch_forward(ws, *args)
+        out = self._launch_forward(ws, *args)
+        if autograd is None and not training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return _NoBackward.apply(out[0], out[1], *[p for p in self.parameters() if p.requires_grad])
+        return out
 
     def forward(self, x, pad_mask=None, embeddings=None, classes_mask=None):
         return self.run(x, None, embeddings, classes_mask, pad_mask)

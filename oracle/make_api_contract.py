@@ -54,14 +54,14 @@ def net_config(path):
 
 
 def contract():
-    sys.path.insert(0, REF)
-    from desed_task.nnet.CRNN import CRNN
-    from desed_task.nnet.CNN import CNN, GLU, ContextGating
-    from desed_task.nnet.RNN import BidirectionalGRU
-    from desed_task.data_augm import add_noise, frame_shift, mixup
-    scaler = _load(f"{REF}/desed_task/utils/scaler.py", "ref_scaler")
-    sched = _load(f"{REF}/desed_task/utils/schedulers.py", "ref_sched")
-    post = _load(f"{REF}/desed_task/utils/postprocess.py", "ref_post")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import refload                       # private package name: never the repo's own `desed_task` shim
+    R = refload.load(REF)
+    CRNN = R.CRNN
+    CNN, GLU, ContextGating = R.CNN.CNN, R.CNN.GLU, R.CNN.ContextGating
+    BidirectionalGRU = R.RNN.BidirectionalGRU
+    add_noise, frame_shift, mixup = R.data_augm.add_noise, R.data_augm.frame_shift, R.data_augm.mixup
+    scaler, sched, post = R.scaler, R.schedulers, R.postprocess
     c = {"signatures": {
         "CRNN.__init__": sig(CRNN.__init__), "CRNN.forward": sig(CRNN.forward), "CNN.__init__": sig(CNN.__init__),
         "GLU.__init__": sig(GLU.__init__), "ContextGating.__init__": sig(ContextGating.__init__),

@@ -1,7 +1,7 @@
 """Pin the oracle against the reference itself and mint the golden fixtures.  Test infrastructure only.
 
-Run in the BUILD container only (needs /root/reference and torchaudio):
-    python -m oracle.make_golden
+Run in the BUILD container only (needs /root/reference and torchaudio), from the repository root:
+    python -m oracle.make_golden [--out DIR]
 It (1) imports the reference's own modules, (2) asserts every oracle restatement equals the reference
 on seeded inputs, (3) writes small fixtures to tests/golden/*.npz which the CPU and GPU tests compare
 against (the GPU box has no /root/reference).
@@ -32,12 +32,17 @@ def gen_wave(seed, B, L=160000, sigma=0.1):
 
 
 def main():
-    sys.path.insert(0, REF)
-    from desed_task.nnet.CRNN import CRNN                                   # noqa
-    from desed_task.data_augm import mixup as ref_mixup, frame_shift as ref_frame_shift, add_noise as ref_add_noise
-    RefScaler = _load(f"{REF}/desed_task/utils/scaler.py", "ref_scaler").TorchScaler
-    RefWarm = _load(f"{REF}/desed_task/utils/schedulers.py", "ref_sched").ExponentialWarmup
-    RefMedian = _load(f"{REF}/desed_task/utils/postprocess.py", "ref_post").ClassWiseMedianFilter
+    global OUT
+    if "--out" in sys.argv:                      # tests/test_oracle_cpu.py re-runs the pin into a scratch directory
+        OUT = sys.argv[sys.argv.index("--out") + 1]
+    # the reference is imported under a private package name: the repo's own `desed_task` shim must never be what is pinned
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import refload
+    R = refload.load(REF)
+    CRNN = R.CRNN
+    assert CRNN.__module__.startswith("_desed_ref") and sys.modules[CRNN.__module__].__file__.startswith(REF)
+    ref_mixup, ref_frame_shift, ref_add_noise = R.data_augm.mixup, R.data_augm.frame_shift, R.data_augm.add_noise
+    RefScaler, RefWarm, RefMedian = R.TorchScaler, R.ExponentialWarmup, R.ClassWiseMedianFilter
     import scipy.ndimage
     from torchaudio.transforms import AmplitudeToDB, MelSpectrogram
 
