@@ -1,4 +1,4 @@
-"""Load the UNMODIFIED reference modules under a private package name.  Test / benchmark infrastructure only.
+"""Load the UNMODIFIED reference modules under a private package name.  Pinning / benchmark infrastructure only (never imported by desed_task_b200).
 
 The repository ships an import shim called `desed_task` (a regular package), which wins over the reference's namespace
 package of the same name whenever the repo root is on sys.path.  Pinning scripts and the benchmark's reference legs must
@@ -13,7 +13,7 @@ import sys
 import types
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-CANDIDATES = ("/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref"))
+CANDIDATES = ("/root/reference", os.path.join(_HERE, "_ref"))
 PKG = "_desed_ref"
 
 

@@ -1,14 +1,21 @@
 #!/usr/bin/env python
-"""bench.py - clips/s of the SED hot path (10-s 16-kHz clip -> 128-mel -> CRNN fwd+bwd+Adam) on N B200s.
+"""bench.py - clips/s of the SED hot path (10-s 16-kHz clip -> 128-mel -> CRNN) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload supervised|mean_teacher]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload supervised|mean_teacher|dcase2024|inference] [--batch B]
 
-Workload (BASELINE.json configs[1], the one the metric is quoted on): supervised CRNN training, batch 24 per GPU
-([12 strong, 12 weak]), dcase2023 CRNN, 10-s clips, train-mode BN, dropout 0.5, SpecAugment, BCE strong + BCE weak, Adam.
-A step = one pass of the whole hot path over one batch.  `value` times K steps with inputs resident in HBM; `e2e` times
-the same K steps through the public engine call with pinned HOST batches (H2D of audio+labels and a D2H read of the loss
-inside the timed region).  `--impl reference` times the reference's CPU path (oracle port of the reference modules) on
-the host cores.  One JSON line is printed by rank 0.
+Workloads (BASELINE.json `configs`; the metric is quoted on `supervised` = configs[1], the default):
+  supervised    CRNN supervised training, batch 24/GPU ([12 strong, 12 weak]), dcase2023 CRNN, train-mode BN, dropout 0.5,
+                SpecAugment, BCE strong + BCE weak, Adam.
+  mean_teacher  configs[2]: batch 48/GPU [12 strong, 12 weak, 24 unlabelled], mixup, student fwd+bwd + teacher fwd, BCE + MSE
+                consistency, EMA + Adam.
+  dcase2024     configs[3]: 2024 CRNN (27 classes, 192-unit BiGRU) + synthetic frame embeddings [B, 768, 496], five-way batch
+                split, mixup on features and embeddings, masked losses, gradient clipping.
+  inference     configs[4]: mel -> eval CRNN -> median filter (k = 7), batch 64/GPU, clips sharded, no collective.
+A step = one pass of the whole hot path over one batch.  `value` times K steps with inputs resident in HBM; `e2e` times the
+same K steps through the public engine call with pinned HOST batches (H2D of the inputs and a D2H read of the loss / the
+scores inside the timed region).  `--impl reference` times the reference's own CPU path (its unmodified modules from
+baseline/_ref, else the oracle port) on the host cores.  Rank 0 prints ONE JSON line.
 """
 import argparse
 import ctypes
@@ -34,7 +41,44 @@ NET_2023 = dict(dropout=0.5, rnn_layers=2, n_in_channel=1, nclass=10, attention=
                 nb_filters=[16, 32, 64, 128, 128, 128, 128],
                 pooling=[[2, 2], [2, 2], [1, 2], [1, 2], [1, 2], [1, 2], [1, 2]], dropout_recurrent=0,
                 use_embeddings=False)
+# recipes/dcase2024_task4_baseline/confs/pretrained.yaml:86-110
+NET_2024 = dict(NET_2023, dropout=0.2, rnn_layers=1, nclass=27, n_RNN_cell=192, use_embeddings=True, embedding_size=768,
+                embedding_type="frame", aggregation_type="pool1d", specaugm_t_p=0.0, specaugm_f_p=0.0,
+                dropstep_recurrent=0.0, dropstep_recurrent_len=16)
+EMB_SHAPE = (768, 496)
 METRIC = "clips/sec (10s 16kHz 128-mel CRNN fwd+bwd)"
+DEFAULT_BATCH = {"supervised": 24, "mean_teacher": 48, "dcase2024": 24, "inference": 64}
+
+
+def batch_split(workload, B):
+    if workload == "mean_teacher":
+        return [B // 4, B // 4, B // 2]
+    if workload == "dcase2024":
+        # shipped [12 maestro, 6 synth, 6 strong, 12 weak, 24 unlabelled] = 60 (pretrained.yaml:8), kept in proportion
+        if B == 60:
+            return [12, 6, 6, 12, 24]
+        base = [B * 12 // 60, B * 6 // 60, B * 6 // 60, B * 12 // 60]
+        base = [max(1, v) for v in base]
+        return base + [B - sum(base)]
+    if workload == "inference":
+        return [B]
+    return [B // 2, B - B // 2, 0]
+
+
+def workload_config(workload, B, world):
+    """The `config` object, identical for both arms (the driver compares them)."""
+    desc = {
+        "supervised": "dcase2023 CRNN supervised training step (mel + fwd + BCE + bwd + Adam), %d clips/GPU x 10 s @16 kHz, "
+                      "128 mel, train-mode BN, dropout 0.5, SpecAugment" % B,
+        "mean_teacher": "dcase2023 CRNN mean-teacher step (mel, mixup, student fwd+bwd, teacher fwd, BCE + MSE consistency, "
+                        "EMA, Adam), %d clips/GPU x 10 s @16 kHz, 128 mel" % B,
+        "dcase2024": "dcase2024 CRNN (27 classes, BiGRU-192) + frame embeddings [768, 496] mean-teacher step (5-way split, "
+                     "mixup on features and embeddings, class-masked losses, grad clip 5.0), %d clips/GPU x 10 s" % B,
+        "inference": "dcase2023 CRNN inference (mel + eval forward + median filter k=7), %d clips/GPU x 10 s @16 kHz, clips "
+                     "sharded over ranks" % B,
+    }[workload]
+    return {"workload": desc, "name": workload, "global_batch": B * world, "batch_split": batch_split(workload, B),
+            "parallelism": "dp%d" % world}
 
 
 def peaks():
@@ -92,18 +136,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def layer_geometry(B):
+# =====================================================================================================================
+# algorithmic work per launch
+def layer_geometry(B, net=NET_2023):
     T, F, cin = 1 + L_SAMPLES // HOP, N_MELS, 1
     out = []
-    for cout, (pt, pf) in zip(NET_2023["nb_filters"], NET_2023["pooling"]):
+    for cout, (pt, pf) in zip(net["nb_filters"], net["pooling"]):
         out.append(dict(cin=cin, cout=cout, T=T, F=F, pt=pt, pf=pf, pix=B * T * F))
         T, F, cin = T // pt, F // pf, cout
     return out
 
 
-def kernel_work(name, B):
+def kernel_work(name, B, net=NET_2023):
     """Algorithmic FLOPs and minimal HBM bytes of ONE launch of a kernel family."""
-    geo = layer_geometry(B)
+    geo = layer_geometry(B, net)
     m = re.match(r"conv(?:3x3|_wgrad)(?:_tc5)?(?:_pair)?_(\d+)to(\d+)_F(\d+)$", name)
     if m:
         a, b, F = int(m.group(1)), int(m.group(2)), int(m.group(3))
@@ -144,31 +190,107 @@ def kernel_work(name, B):
     if name == "logmel":
         return 626 * 70e3 * B, 960512.0 * B
     if name.startswith("gru_seq"):
-        H = NET_2023["n_RNN_cell"]
+        H = net["n_RNN_cell"]
         return 2.0 * 3 * H * H * B * 156 * 2, 4.0 * B * 156 * 2 * (3 * H + 6 * H)
+    if name == "adam_ema":
+        n = 1112420 if net["nclass"] == 10 else 1785094
+        return 12.0 * n, 40.0 * n
     return 0.0, 0.0
 
 
-def make_batches(nbuf, B, seed, pin):
+FAMILIES = [
+    ("front end (logmel)", r"^logmel$"),
+    ("conv0 (1->16, CUDA cores)", r"^conv0_"),
+    ("conv3x3 tcgen05 fwd/dgrad", r"^conv3x3_tc5"),
+    ("conv3x3 mma.sync fwd/dgrad", r"^conv3x3_\d"),
+    ("conv wgrad tcgen05", r"^conv_wgrad_tc5"),
+    ("conv wgrad mma.sync", r"^conv_wgrad_\d"),
+    ("BN+GLU+pool C<=32 (registers)", r"^bnglu_pool"),
+    ("BN+GLU+pool C>=64 (tcgen05)", r"^bnglu_tc5|^glu_wgrad_tc5"),
+    ("BN backward apply", r"^bn_bwd_apply"),
+    ("GRU recurrence", r"^gru_seq"),
+    ("GRU / fusion GEMMs", r"^gemm"),
+    ("heads + loss", r"^heads|^sed_loss|^dropout|^emb_"),
+    ("optimizer (Adam + EMA)", r"^adam_ema|^sumsq"),
+    ("glue (packs, BN finalize, fix-ups)", r"."),
+]
+
+
+def family_table(prof, NP, B, net, pk):
+    """Per-family: ms/step, algorithmic FLOPs / bytes per step, achieved rates and the fraction of the bounding peak."""
+    ridge = pk["bf16_tflops_sustained"] * 1e12 / (pk["hbm_gbs"] * 1e9)
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        traffic = {}
+    rows = {}
+    for name, (cnt, tot) in prof.items():
+        fam = next(f for f, pat in FAMILIES if re.search(pat, name))
+        fl, by = kernel_work(name, B, net)
+        r = rows.setdefault(fam, dict(ms=0.0, launches=0.0, flops=0.0, bytes=0.0, dram=0.0, dram_known=True))
+        r["ms"] += tot / NP
+        r["launches"] += cnt / NP
+        r["flops"] += fl * cnt / NP
+        r["bytes"] += by * cnt / NP
+        if name in traffic and by > 0:
+            r["dram"] += traffic[name] * cnt / NP
+        elif by > 0:
+            r["dram_known"] = False
+    out = []
+    for fam, _ in FAMILIES:
+        if fam not in rows:
+            continue
+        r = rows[fam]
+        e = {"family": fam, "ms_per_step": round(r["ms"], 4), "launches_per_step": round(r["launches"], 1)}
+        if r["bytes"] > 0 and r["ms"] > 0:
+            gbs, tfs = r["bytes"] / r["ms"] / 1e6, r["flops"] / r["ms"] / 1e9
+            e.update({"algorithmic_MB": round(r["bytes"] / 1e6, 2), "algorithmic_GFLOP": round(r["flops"] / 1e9, 3),
+                      "GBps": round(gbs, 1), "TFLOPs": round(tfs, 2)})
+            if r["flops"] / r["bytes"] < ridge:
+                e.update({"bound": "hbm", "frac": round(gbs / pk["hbm_gbs"], 4)})
+            else:
+                e.update({"bound": "tensor", "frac": round(tfs / pk["bf16_tflops_sustained"], 4)})
+            if r["dram"] > 0 and r["dram_known"]:
+                e["dram_over_algorithmic"] = round(r["dram"] / r["bytes"], 2)
+        out.append(e)
+    return out
+
+
+def make_batches(nbuf, B, seed, pin, nclass=10, emb=False):
     g = torch.Generator().manual_seed(seed)
     n_s = B // 2
-    audio, labels = [], []
+    audio, labels, embs = [], [], []
     for _ in range(nbuf):
         a = torch.randn(B, L_SAMPLES, generator=g) * 0.1
-        y = (torch.rand(B, 10, 156, generator=g) < 0.1).float()
+        y = (torch.rand(B, nclass, 156, generator=g) < 0.1).float()
         y[n_s:, :, 1:] = 0.0                                   # weak clips: clip-level tags live in frame 0
         if pin:
             a, y = a.pin_memory(), y.pin_memory()
         audio.append(a)
         labels.append(y)
+        if emb:
+            e = torch.randn(B, *EMB_SHAPE, generator=g)
+            embs.append(e.pin_memory() if pin else e)
+    if emb:
+        return audio, labels, embs
     return audio, labels
+
+
+def class_masks_2024(split):
+    """valid_class_mask per row: MAESTRO rows use the 17 MAESTRO classes, DESED rows the 10 DESED classes
+    (recipes/dcase2024_task4_baseline/train_pretrained.py:190-193 / local/classes_dict.py)."""
+    B = sum(split)
+    cm = torch.zeros(B, 27, dtype=torch.bool)
+    cm[:split[0], 10:] = True
+    cm[split[0]:, :10] = True
+    return cm
 
 
 # =====================================================================================================================
 def run_ours(args):
     import torch.distributed as dist
     from desed_task_b200 import _lib
-    from desed_task_b200.engine import TrainEngine
+    from desed_task_b200.engine import InferEngine, TrainEngine
     from desed_task_b200.frontend import MelSpectrogram
     from desed_task_b200.nnet.CRNN import CRNN
     from desed_task_b200.optim import FusedAdam
@@ -189,14 +311,15 @@ def run_ours(args):
     if L.sedk_device_cc() < 100:
         raise SystemExit("bench.py needs an sm_100 device (got cc %d); there is no fallback path" % L.sedk_device_cc())
 
-    B = args.batch
-    mean_teacher = args.workload == "mean_teacher"
-    batch_sizes = [B // 4, B // 4, B // 2] if mean_teacher else [B // 2, B - B // 2, 0]
+    wl, B = args.workload, args.batch
+    split = batch_split(wl, B)
+    is_2024, is_inf = wl == "dcase2024", wl == "inference"
+    net_cfg = NET_2024 if is_2024 else NET_2023
+    nclass = net_cfg["nclass"]
     torch.manual_seed(42)
-    student = CRNN(**NET_2023).to(dev)
-    student.train()
+    student = CRNN(**net_cfg).to(dev)
     teacher = None
-    if mean_teacher:
+    if wl in ("mean_teacher", "dcase2024"):
         import copy
         teacher = copy.deepcopy(student)
         for p in teacher.parameters():
@@ -204,45 +327,66 @@ def run_ours(args):
         teacher.train()
     mel = MelSpectrogram(16000, 2048, 2048, HOP, 0, 8000, n_mels=N_MELS, window_fn=torch.hamming_window,
                          wkwargs={"periodic": False}, power=1).to(dev)
-    opt = FusedAdam(student, 1e-3, betas=(0.9, 0.999))
-    sched = ExponentialWarmup(opt, 1e-3, 50 * 250)
+    opt = sched = None
+    if is_inf:
+        student.eval()
+    else:
+        student.train()
+        opt = FusedAdam(student, 1e-3, betas=(0.9, 0.999))
+        sched = ExponentialWarmup(opt, 1e-3, 50 * 250)
 
     def new_engine(use_graph, distributed=True):
-        return TrainEngine(student, mel, batch_sizes, L_SAMPLES, opt=opt, scheduler=sched, teacher=teacher,
-                           mixup_type="soft" if mean_teacher else None, use_graph=use_graph, distributed=distributed)
+        if is_inf:
+            return InferEngine(student, mel, B, L_SAMPLES, median_window=7, use_graph=use_graph)
+        if is_2024:
+            return TrainEngine(student, mel, split, L_SAMPLES, opt=opt, scheduler=sched, teacher=teacher,
+                               mixup_type="soft", use_graph=use_graph, distributed=distributed, grad_clip=5.0,
+                               emb_shape=EMB_SHAPE, class_masks=class_masks_2024(split).to(dev), recipe="2024")
+        return TrainEngine(student, mel, split, L_SAMPLES, opt=opt, scheduler=sched, teacher=teacher,
+                           mixup_type="soft" if teacher is not None else None, use_graph=use_graph,
+                           distributed=distributed)
 
     eng = new_engine(True)
-    NBUF = 12                                                    # 12 x 15.4 MB of audio > 126 MB L2
-    host_a, host_y = make_batches(NBUF, B, 42 + rank, pin=True)
+    NBUF = max(4, -(-192 // B) + 1) if not is_2024 else 4          # distinct batches: > 126 MB of audio (+ embeddings) > L2
+    mk = make_batches(NBUF, B, 42 + rank, pin=True, nclass=nclass, emb=is_2024)
+    host_a, host_y = mk[0], mk[1]
+    host_e = mk[2] if is_2024 else [None] * NBUF
     dev_a = [a.to(dev) for a in host_a]
     dev_y = [y.to(dev) for y in host_y]
+    dev_e = [e.to(dev) if e is not None else None for e in host_e]
+
+    def one(e, src, i):
+        a, y, em = src
+        if is_inf:
+            return e.step(a[i % NBUF], inputs_ready=True)
+        if is_2024:
+            return e.step(a[i % NBUF], y[i % NBUF], em[i % NBUF], inputs_ready=True)
+        return e.step(a[i % NBUF], y[i % NBUF], inputs_ready=True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(use_host, steps, warm):
-        src_a, src_y = (host_a, host_y) if use_host else (dev_a, dev_y)
+    def timed(use_host, steps, warm, sample=True):
+        src = (host_a, host_y, host_e) if use_host else (dev_a, dev_y, dev_e)
         for i in range(warm):
-            eng.step(src_a[i % NBUF], src_y[i % NBUF], inputs_ready=True)
+            one(eng, src, i)
         barrier()
         launches0, replays0 = L.sedk_launch_count(), eng.replays
         sampler = ClockSampler(local)
-        if rank == 0:
+        if rank == 0 and sample:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
-            r = eng.step(src_a[(warm + i) % NBUF], src_y[(warm + i) % NBUF], inputs_ready=True)
-            if use_host:
-                pass                                             # the D2H loss read is issued inside step(); drained below
+            one(eng, src, warm + i)
         e1.record()
         barrier()
         if use_host:
-            eng.read_losses()
+            eng.read() if is_inf else eng.read_losses()          # the per-step D2H results have all landed
         ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.stop() if (rank == 0 and sample) else None
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -253,7 +397,9 @@ def run_ours(args):
     W = max(args.warmup, 3)
     ms_dev, clocks, launches = timed(False, args.steps, W)
     ms_e2e, clocks_e2e, _ = timed(True, args.steps, W)
-    loss_now = eng.read_losses()
+    # spread: the same K-step block repeated (device-resident inputs), min / median reported next to the headline block
+    reps = sorted(timed(False, args.steps, 1, sample=False)[0] / args.steps for _ in range(args.repeats))
+    final = None if is_inf else eng.read_losses()
     total_clips = B * world * args.steps
     value = total_clips / ms_dev * 1e3
     e2e = total_clips / ms_e2e * 1e3
@@ -261,16 +407,18 @@ def run_ours(args):
 
     out = None
     if rank == 0:
-        # ---- per-kernel device times (eager, outside any timed region) -> dominant kernel + roofline
+        # ---- per-kernel device times (eager, outside any timed region) -> dominant kernel + roofline + family table
         prof = {}
         eng2 = new_engine(False, distributed=False)       # rank-0-only pass: no collective in it
+        src = (dev_a, dev_y, dev_e)
         for i in range(3):
-            eng2.step(dev_a[i], dev_y[i])
+            one(eng2, src, i)
         torch.cuda.synchronize(dev)
         L.sedk_profile_enable(1)
         NP = 5
         for i in range(NP):
-            eng2.step(dev_a[(3 + i) % NBUF], dev_y[(3 + i) % NBUF])
+            one(eng2, src, 3 + i)
+        torch.cuda.synchronize(dev)
         buf = ctypes.create_string_buffer(1 << 16)
         _lib.check(L.sedk_profile_report(buf, len(buf)), "sedk_profile_report")
         L.sedk_profile_enable(0)
@@ -281,20 +429,18 @@ def run_ours(args):
         top = sorted(prof.items(), key=lambda kv: -kv[1][1])
         dom, (dcnt, dtot) = top[0]
         avg_ms = dtot / dcnt
-        flops, nbytes = kernel_work(dom, B)
+        flops, nbytes = kernel_work(dom, B, net_cfg)
         ridge = pk["bf16_tflops_sustained"] * 1e12 / (pk["hbm_gbs"] * 1e9)
         if nbytes > 0 and flops / nbytes < ridge:
             roof = {"bound": "hbm", "achieved": round(nbytes / avg_ms / 1e6, 1), "peak": pk["hbm_gbs"], "unit": "GB/s"}
         else:
             roof = {"bound": "tensor", "achieved": round(flops / avg_ms / 1e9, 2), "peak": pk["bf16_tflops_sustained"],
                     "unit": "TFLOP/s"}
-        roof["frac"] = round(roof["achieved"] / roof["peak"], 4)
+        roof["frac"] = round(roof["achieved"] / roof["peak"], 4) if roof["peak"] else None
+        us_per_step = {k: round(v[1] / v[0] * 1e3 / 156.0, 3) for k, v in prof.items() if k.startswith("gru_seq")}
         if dom.startswith("gru_seq"):
-            roof["note"] = ("latency-bound persistent recurrence: 156 dependent time steps per launch, %.2f us per step on "
-                            "%d of the SMs; neither HBM nor the tensor pipe can bound it (DESIGN.md section 4)"
-                            % (avg_ms * 1e3 / 156.0, 2 * B))
-        # measured DRAM traffic of that kernel (dram__bytes_read.sum + dram__bytes_write.sum per launch) from the committed
-        # ncu full-set capture, when there is one (profiles/traffic.json: {kernel family: bytes per launch})
+            roof["note"] = ("latency-bound persistent recurrence: 156 dependent time steps per launch, %.2f us per time step; "
+                            "neither HBM nor the tensor pipe can bound it (DESIGN.md section 4)" % (avg_ms * 1e3 / 156.0))
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
@@ -305,38 +451,51 @@ def run_ours(args):
                      "share_of_step": round(dtot / NP / step_ms_eager, 4), "peak_source": pk_kind + " (MEASURED_PEAKS.json"
                      " bf16 sustained / hbm copy; TF32 nominal is half the bf16 rate)",
                      "algorithmic_flops": flops, "algorithmic_bytes": nbytes})
-        top5 = [{"kernel": k, "ms_per_step": round(v[1] / NP, 4), "launches_per_step": v[0] / NP} for k, v in top]
-        # ---- front-end bandwidth (the second headline: mel GB/s vs HBM peak)
+        breakdown = [{"kernel": k, "ms_per_step": round(v[1] / NP, 4), "launches_per_step": v[0] / NP} for k, v in top]
+        # ---- front-end bandwidth (the second headline: mel GB/s vs HBM peak) and its fp32 rate
         lm_cnt, lm_tot = prof.get("logmel", (1, 0.0))
         mel_gbs = B * 960512 / (lm_tot / lm_cnt) / 1e6 if lm_tot > 0 else None
-        cpu = cpu_baseline(B, budget_s=20.0) if (world == 1 and not args.quick) else None
+        mel_tfs = B * 626 * 70e3 / (lm_tot / lm_cnt) / 1e9 if lm_tot > 0 else None
+        cpu = lib_bar = None
+        if world == 1 and not args.quick:
+            cpu = cpu_baseline(wl, B, budget_s=20.0)
+            lib_bar = library_bar(dev, wl, B, dev_a, dev_y)
+        h2d = B * L_SAMPLES * 4 + (0 if is_inf else B * nclass * 156 * 4 + 64) + (B * EMB_SHAPE[0] * EMB_SHAPE[1] * 4 if is_2024 else 0)
+        d2h = (B * nclass * 156 * 4 + B * nclass * 4) if is_inf else 64
+        cfg = workload_config(wl, B, world)
+        cfg.update({"precision": "front end fp32; CRNN GEMMs TF32 (fp32 storage / accumulate); recurrence, BN statistics, "
+                                 "heads, losses, optimizer fp32",
+                    "l2": "inputs rotate over %d distinct batches (%.0f MB > L2); per-step activations ~0.6 GB"
+                          % (NBUF, NBUF * B * L_SAMPLES * 4 / 1e6),
+                    "cuda_graph": True,
+                    "overlap": "front end of step k+1 runs on its own stream concurrently with step k's graph (ping-pong "
+                               "log-mel buffers); weight-gradient GEMMs on a side branch of the graph"})
         out = {
             "metric": METRIC, "value": round(value, 1), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": W, "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-            "config": {"workload": "dcase2023 CRNN %s training step, %d clips/GPU x 10 s @16 kHz, 128 mel; front end fp32, "
-                                   "CRNN GEMMs TF32 (fp32 storage/accumulate), train-mode BN, dropout 0.5, SpecAugment, "
-                                   "Adam" % (args.workload, B),
-                       "global_batch": B * world, "batch_split": batch_sizes, "parallelism": "dp%d" % world,
-                       "l2": "inputs rotate over %d distinct batches (%.0f MB > L2); per-step activations ~0.6 GB"
-                             % (NBUF, NBUF * B * L_SAMPLES * 4 / 1e6),
-                       "cuda_graph": True,
-                       "overlap": "front end of step k+1 runs on its own stream concurrently with step k's graph "
-                                  "(ping-pong log-mel buffers); weight-gradient GEMMs on a side branch of the graph"},
-            "clocks": clocks,
+            "vs_baseline": None, "dtype": "tf32", "data": "synthetic", "config": cfg, "clocks": clocks,
             "e2e": {"value": round(e2e, 1), "unit": "clips/s", "ms_per_step": round(ms_e2e / args.steps, 4),
-                    "h2d_bytes_per_step": B * L_SAMPLES * 4 + B * 10 * 156 * 4 + 64, "d2h_bytes_per_step": 64,
-                    "clocks": clocks_e2e},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "clocks": clocks_e2e},
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu,
-            "kernel_breakdown_ms": top5,
+            "gpu_library_baseline": lib_bar,
+            "repeats": {"blocks": args.repeats, "steps_per_block": args.steps,
+                        "ms_per_step_min": round(reps[0], 4) if reps else None,
+                        "ms_per_step_median": round(reps[len(reps) // 2], 4) if reps else None,
+                        "ms_per_step_max": round(reps[-1], 4) if reps else None},
+            "kernel_families": family_table(prof, NP, B, net_cfg, pk),
+            "kernel_breakdown_ms": breakdown,
             "eager_step_ms": round(step_ms_eager, 4),
+            "gru_us_per_time_step": us_per_step,
             "frontend": {"mel_GBps": None if mel_gbs is None else round(mel_gbs, 1),
                          "frac_of_hbm_peak": None if mel_gbs is None else round(mel_gbs / pk["hbm_gbs"], 4),
-                         "algorithmic_bytes_per_clip": 960512},
-            "final_loss": loss_now,
+                         "fp32_TFLOPs": None if mel_tfs is None else round(mel_tfs, 2),
+                         "algorithmic_bytes_per_clip": 960512, "fp32_flop_per_clip": 626 * 70e3},
+            "final_loss": final,
         }
+        if lib_bar and isinstance(lib_bar.get("best"), (int, float)) and lib_bar["best"] > 0:
+            out["vs_gpu_library"] = round(value / lib_bar["best"], 2)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -345,21 +504,63 @@ def run_ours(args):
 
 
 # =====================================================================================================================
-def cpu_step_fn(B, threads):
-    """The reference's own CPU path for this workload: oracle port (plain-torch restatement of the reference modules,
-    pinned against the live reference in oracle/make_golden.py).  Returns a callable running one full training step."""
-    import dataclasses
-    from oracle import crnn as ocrnn, trainer as otr
+def library_bar(dev, workload, B, dev_a, dev_y):
+    """the reference's UNMODIFIED modules on the same B200 through PyTorch's library kernels."""
+    if workload == "dcase2024":
+        return {"unavailable": "the 2024 library leg is not wired (needs the Lightning trainer's batch plumbing)"}
+    try:
+        from baseline import reference_arm
+        res = reference_arm.gpu_library_baseline(dev, workload, B, dev_a, dev_y, steps=15, warmup=4)
+    except Exception as e:                                           # noqa: BLE001
+        return {"unavailable": str(e).splitlines()[0][:200]}
+    nums = [v for v in res.values() if isinstance(v, (int, float))]
+    res.update({"unit": "clips/s", "best": max(nums) if nums else None,
+                "what": "reference desed_task.nnet.CRNN + torchaudio MelSpectrogram/AmplitudeToDB + reference TorchScaler + "
+                        "torch.optim.Adam on cuda:0 (torch %s, cuDNN %s; cudnn TF32 on, matmul fp32 = PyTorch defaults), "
+                        "inputs resident" % (torch.__version__, torch.backends.cudnn.version())})
+    return res
+
+
+def reference_cpu_step(workload, B, threads):
+    """One step of the reference's own CPU path.  Returns (callable, kind): the unmodified reference modules when
+    baseline/_ref (or the checkout) is present (`kind` "reference"), else the oracle port (`kind` "port")."""
     torch.set_num_threads(threads)
-    cfg = ocrnn.CFG_2023
+    split = batch_split(workload, B)
+    if workload != "dcase2024":
+        try:
+            from baseline import reference_arm
+            audio, labels = make_batches(1, B, 7, pin=False)
+            audio, labels = audio[0], labels[0]
+            path = reference_arm.ReferencePath("cpu", teacher=workload == "mean_teacher")
+            if workload == "supervised":
+                return (lambda: float(path.supervised_step(audio, labels, split[0]).detach())), "reference"
+            if workload == "mean_teacher":
+                return (lambda: float(path.mean_teacher_step(audio, labels, split).detach())), "reference"
+            return (lambda: len(path.inference(audio))), "reference"
+        except ImportError:
+            pass
+    from oracle import crnn as ocrnn, trainer as otr
+    cfg = ocrnn.CFG_2024 if workload == "dcase2024" else ocrnn.CFG_2023
     P = ocrnn.init_params(cfg, seed=42)
     names = ocrnn.param_names(P)
     for k in names:
         P[k].requires_grad_(True)
     state = {}
-    audio, labels = make_batches(1, B, 7, pin=False)
-    audio, labels = audio[0], labels[0]
-    n_s = B // 2
+    mk = make_batches(1, B, 7, pin=False, nclass=cfg.nclass, emb=workload == "dcase2024")
+    audio, labels = mk[0][0], mk[1][0]
+    if workload == "dcase2024":
+        Pt = {k: v.detach().clone() for k, v in P.items()}
+        emb, cm = mk[2][0], class_masks_2024(split)
+
+        def step24():
+            out = otr.mean_teacher_step_2024(P, Pt, audio, labels, emb, cm, split, 1, 12500, cfg, mix=None)
+            grads = torch.autograd.grad(out["tot_loss"], [P[k] for k in names])
+            with torch.no_grad():
+                otr.update_ema(0.999, 1, P, Pt, names)
+                otr.adam_step({k: P[k] for k in names}, dict(zip(names, grads)), state, names, 1e-3)
+            return float(out["tot_loss"].detach())
+        return step24, "port"
+    n_s = split[0]
 
     def step():
         spec = ocrnn.draw_specaugment(B, N_MELS, 626)
@@ -369,17 +570,17 @@ def cpu_step_fn(B, threads):
         with torch.no_grad():
             otr.adam_step({k: P[k] for k in names}, dict(zip(names, grads)), state, names, 1e-3)
         return float(loss.detach())
-    return step
+    return step, "port"
 
 
-def best_threads():
-    """The reference path is many small torch CPU ops: more threads is not faster.  Time one small step at a few thread
-    counts and keep the fastest (reported as `cores`)."""
+def best_threads(workload):
+    """The reference path is many small torch CPU ops: more threads is not always faster.  Time one small step at a few
+    thread counts and keep the fastest (reported as `cores`)."""
     ncpu = os.cpu_count() or 1
     cands = sorted({t for t in (8, 16, 32, 64, ncpu) if t <= ncpu})
     best, best_t = cands[0], None
     for t in cands:
-        step = cpu_step_fn(4, t)
+        step, _ = reference_cpu_step(workload, 4 if workload != "dcase2024" else 10, t)
         step()
         t0 = time.time()
         step()
@@ -389,10 +590,10 @@ def best_threads():
     return best
 
 
-def cpu_baseline(B, budget_s=20.0):
-    threads = best_threads()
+def cpu_baseline(workload, B, budget_s=20.0):
     prev = torch.get_num_threads()
-    step = cpu_step_fn(B, threads)
+    threads = best_threads(workload)
+    step, kind = reference_cpu_step(workload, B, threads)
     step()                                                       # warm-up
     t0 = time.time()
     n = 0
@@ -401,18 +602,18 @@ def cpu_baseline(B, budget_s=20.0):
         n += 1
     dt = time.time() - t0
     torch.set_num_threads(prev)
-    return {"value": round(B * n / dt, 2), "unit": "clips/s", "cores": threads, "kind": "port",
-            "sample": "%d full training steps of %d clips (fp32, torch CPU ops, %d threads), %.1f s" % (n, B, threads, dt)}
+    return {"value": round(B * n / dt, 2), "unit": "clips/s", "cores": threads, "kind": kind,
+            "sample": "%d full %s steps of %d clips (fp32, torch CPU ops, %d threads), %.1f s" % (n, workload, B, threads, dt)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = args.batch
-    threads = best_threads()
-    step = cpu_step_fn(B, threads)
-    W = max(1, min(args.warmup, 2))
+    wl, B = args.workload, args.batch
+    threads = best_threads(wl)
+    step, kind = reference_cpu_step(wl, B, threads)
+    W = max(args.warmup, 1)
     for _ in range(W):
         step()
     t0 = time.time()
@@ -420,13 +621,15 @@ def run_reference(args):
         step()
     dt = time.time() - t0
     v = round(B * args.steps / dt, 2)
+    what = ("the reference's unmodified modules (baseline/_ref: desed_task.nnet.CRNN, data_augm, TorchScaler; torchaudio "
+            "front end; torch.optim.Adam)" if kind == "reference" else "oracle port of the reference's torch/torchaudio path")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": W, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "dcase2023 CRNN %s training step on the host CPU (oracle port of the reference's torch/"
-                               "torchaudio path), %d clips x 10 s per step" % (args.workload, B), "global_batch": B},
-        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
+        "config": workload_config(wl, B, 1),
+        "arm": "host CPU, fp32, %s" % what,
+        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": threads, "kind": kind,
                          "sample": "%d steps of %d clips, %d of %d host threads (fastest of a sweep)"
                                    % (args.steps, B, threads, os.cpu_count() or 1)},
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -438,12 +641,13 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="supervised", choices=["supervised", "mean_teacher"])
-    ap.add_argument("--batch", type=int, default=None, help="clips per GPU (default 24 supervised / 48 mean-teacher)")
-    ap.add_argument("--quick", action="store_true", help="development runs: skip the CPU baseline leg")
+    ap.add_argument("--workload", default="supervised", choices=sorted(DEFAULT_BATCH))
+    ap.add_argument("--batch", type=int, default=None, help="clips per GPU (default: 24 / 48 / 24 / 64 by workload)")
+    ap.add_argument("--repeats", type=int, default=5, help="extra timed K-step blocks for the min / median spread")
+    ap.add_argument("--quick", action="store_true", help="development runs: skip the CPU / GPU-library baseline legs")
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = 48 if args.workload == "mean_teacher" else 24
+        args.batch = DEFAULT_BATCH[args.workload]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -93,6 +93,7 @@ _SIGS = {
     "sedk_crnn_backward": (i32, [C.POINTER(CrnnPlan), vp]),
     "sedk_sed_loss": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp]),
     "sedk_sed_loss_dev": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "sedk_sed_loss_ex": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
     "sedk_conv3x3": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "sedk_conv_wgrad": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "sedk_gemm": (i32, [i32, i32, i32, i32, i32, f32, vp, i32, vp, i32, f32, vp, i32, vp, i32, vp]),

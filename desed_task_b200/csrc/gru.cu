@@ -747,6 +747,9 @@ int launch_gru_seq_fwd(const float* const gi[2], const float* const w_hh[2], con
     SEDK_PROF("gru_seq_fwd", s);
     if (H == 128 && gru_cluster() == 2 && pick_nb(B, 2) == 1)
         return run_fwd<128, 2, 1>(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
+    // v3 (gru3.cu): octet-per-unit-group layout, every weight in registers, 4 LDS.128 of h per thread and step
+    if (H == 128 && get_option("gru_v3", 1) && pick_nb(B, 1) == 1)
+        return launch_gru_fwd_v3(gi, w_hh, b_hh, out, gates, hprev, B, T, save, get_option("gru_v3", 1), s);
     // v2 holds 80 weights + the loop state in exactly 128 registers at one batch row per CTA (two rows spill)
     if (H == 128 && get_option("gru_v2", 1) && pick_nb(B, 1) == 1)
         return run_fwd_v2(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
@@ -774,6 +777,8 @@ int launch_gru_seq_bwd(const float* gout, const float* const w_hh[2], const floa
     SEDK_PROF("gru_seq_bwd", s);
     if (H == 128 && gru_cluster() == 2 && pick_nb(B, 2) == 1)
         return run_bwd<128, 2, 1>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, zeroed, s);
+    if (H == 128 && get_option("gru_v3", 1) && pick_nb(B, 1) == 1)
+        return launch_gru_bwd_v3(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, zeroed, get_option("gru_v3", 1), s);
     if (H == 128 && get_option("gru_v2", 1) && pick_nb(B, 1) == 1)
         return run_bwd_v2(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, zeroed, s);
     if (H == 128) {

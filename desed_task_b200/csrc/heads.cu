@@ -251,13 +251,15 @@ __device__ __forceinline__ float bce_grad(float p, float y) { return (p - y) / f
 __global__ void __launch_bounds__(256)
 sed_loss_kernel(const float* __restrict__ strong, const float* __restrict__ weak, const float* __restrict__ ts,
                 const float* __restrict__ tw, const float* __restrict__ labels, const float* __restrict__ lweak, int B,
-                int C, int T, int n_strong, int n_weak, float cw, const float* __restrict__ cw_dev,
-                float* __restrict__ sums, float* __restrict__ gstrong, float* __restrict__ gweak) {
+                int C, int T, int n_strong, int n_weak, int cons_row0, int cons_bce, float cw,
+                const float* __restrict__ cw_dev, float* __restrict__ sums, float* __restrict__ gstrong,
+                float* __restrict__ gweak) {
     if (cw_dev != nullptr) cw = *cw_dev;
     const int64_t ns = (int64_t)B * C * T, nw = (int64_t)B * C;
     const float inv_bs = n_strong > 0 ? 1.f / (float)((int64_t)n_strong * C * T) : 0.f;
     const float inv_bw = n_weak > 0 ? 1.f / (float)((int64_t)n_weak * C) : 0.f;
-    const float inv_ms = 1.f / (float)ns, inv_mw = 1.f / (float)nw;
+    // consistency term over rows [cons_row0, B): all rows in the 2023 recipe, `mask_unlabeled` in the 2024 one
+    const float inv_ms = 1.f / (float)((int64_t)(B - cons_row0) * C * T), inv_mw = 1.f / (float)((int64_t)(B - cons_row0) * C);
     float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ns + nw; i += (int64_t)gridDim.x * blockDim.x) {
         if (i < ns) {
@@ -270,10 +272,15 @@ sed_loss_kernel(const float* __restrict__ strong, const float* __restrict__ weak
                 g += bce_grad(p, y) * inv_bs;
                 if (ts) acc[4] += bce_term(ts[i], y);
             }
-            if (ts) {
-                const float d = p - ts[i];
-                acc[2] += d * d;
-                g += cw * 2.f * d * inv_ms;
+            if (ts && b >= cons_row0) {
+                if (cons_bce) {
+                    acc[2] += bce_term(p, ts[i]);
+                    g += cw * bce_grad(p, ts[i]) * inv_ms;
+                } else {
+                    const float d = p - ts[i];
+                    acc[2] += d * d;
+                    g += cw * 2.f * d * inv_ms;
+                }
             }
             if (gstrong) gstrong[i] = g;
         } else {
@@ -287,10 +294,15 @@ sed_loss_kernel(const float* __restrict__ strong, const float* __restrict__ weak
                 g += bce_grad(p, y) * inv_bw;
                 if (tw) acc[5] += bce_term(tw[j], y);
             }
-            if (tw) {
-                const float d = p - tw[j];
-                acc[3] += d * d;
-                g += cw * 2.f * d * inv_mw;
+            if (tw && b >= cons_row0) {
+                if (cons_bce) {
+                    acc[3] += bce_term(p, tw[j]);
+                    g += cw * bce_grad(p, tw[j]) * inv_mw;
+                } else {
+                    const float d = p - tw[j];
+                    acc[3] += d * d;
+                    g += cw * 2.f * d * inv_mw;
+                }
             }
             if (gweak) gweak[j] = g;
         }
@@ -303,13 +315,13 @@ sed_loss_kernel(const float* __restrict__ strong, const float* __restrict__ weak
 }
 
 __global__ void sed_loss_finalize(float* losses, const float* sums, int B, int C, int T, int n_strong, int n_weak,
-                                  float cw, const float* cw_dev) {
+                                  int cons_row0, float cw, const float* cw_dev) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (cw_dev != nullptr) cw = *cw_dev;
     const float bs = n_strong > 0 ? sums[0] / (float)((int64_t)n_strong * C * T) : 0.f;
     const float bw = n_weak > 0 ? sums[1] / (float)((int64_t)n_weak * C) : 0.f;
-    const float ms = sums[2] / (float)((int64_t)B * C * T);
-    const float mw = sums[3] / (float)((int64_t)B * C);
+    const float ms = sums[2] / (float)((int64_t)(B - cons_row0) * C * T);
+    const float mw = sums[3] / (float)((int64_t)(B - cons_row0) * C);
     losses[1] = bs;
     losses[2] = bw;
     losses[3] = ms;
@@ -485,9 +497,10 @@ int launch_emb_concat_bwd(const float* gcat, const int32_t* dropstep, float* gx,
 
 static int sed_loss_impl(const float* strong, const float* weak, const float* t_strong, const float* t_weak,
                          const float* labels, const float* labels_weak, int B, int C, int T, int n_strong, int n_weak,
-                         float cons_weight, const float* cw_dev, float* losses, float* gstrong, float* gweak,
-                         void* stream) {
+                         int cons_row0, int cons_kind, float cons_weight, const float* cw_dev, float* losses,
+                         float* gstrong, float* gweak, void* stream) {
     using namespace sedk;
+    SEDK_REQUIRE(cons_row0 >= 0 && cons_row0 < B && (cons_kind == 0 || cons_kind == 1), "sedk_sed_loss: bad cons_row0 / cons_kind");
     SEDK_REQUIRE(strong && weak && losses && B > 0 && C > 0 && T > 0, "sedk_sed_loss: bad arguments");
     SEDK_REQUIRE(n_strong >= 0 && n_weak >= 0 && n_strong + n_weak <= B, "sedk_sed_loss: n_strong + n_weak > B");
     SEDK_REQUIRE(n_strong == 0 || labels, "sedk_sed_loss: labels missing");
@@ -500,9 +513,9 @@ static int sed_loss_impl(const float* strong, const float* weak, const float* t_
     int blocks = (int)((n + 255) / 256);
     if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
     sed_loss_kernel<<<blocks, 256, 0, s>>>(strong, weak, t_strong, t_weak, labels, labels_weak, B, C, T, n_strong, n_weak,
-                                           cons_weight, cw_dev, losses + 8, gstrong, gweak);
+                                           cons_row0, cons_kind, cons_weight, cw_dev, losses + 8, gstrong, gweak);
     SEDK_LAUNCH_CHECK("sed_loss_kernel");
-    sed_loss_finalize<<<1, 32, 0, s>>>(losses, losses + 8, B, C, T, n_strong, n_weak, cons_weight, cw_dev);
+    sed_loss_finalize<<<1, 32, 0, s>>>(losses, losses + 8, B, C, T, n_strong, n_weak, cons_row0, cons_weight, cw_dev);
     SEDK_LAUNCH_CHECK("sed_loss_finalize");
     return SEDK_OK;
 }
@@ -510,8 +523,16 @@ static int sed_loss_impl(const float* strong, const float* weak, const float* t_
 extern "C" int sedk_sed_loss(const float* strong, const float* weak, const float* t_strong, const float* t_weak,
                              const float* labels, const float* labels_weak, int B, int C, int T, int n_strong,
                              int n_weak, float cons_weight, float* losses, float* gstrong, float* gweak, void* stream) {
-    return sed_loss_impl(strong, weak, t_strong, t_weak, labels, labels_weak, B, C, T, n_strong, n_weak, cons_weight,
+    return sed_loss_impl(strong, weak, t_strong, t_weak, labels, labels_weak, B, C, T, n_strong, n_weak, 0, 0, cons_weight,
                          nullptr, losses, gstrong, gweak, stream);
+}
+
+extern "C" int sedk_sed_loss_ex(const float* strong, const float* weak, const float* t_strong, const float* t_weak,
+                                const float* labels, const float* labels_weak, int B, int C, int T, int n_strong,
+                                int n_weak, int cons_row0, int cons_kind, float cons_weight, const float* cons_weight_dev,
+                                float* losses, float* gstrong, float* gweak, void* stream) {
+    return sed_loss_impl(strong, weak, t_strong, t_weak, labels, labels_weak, B, C, T, n_strong, n_weak, cons_row0,
+                         cons_kind, cons_weight, cons_weight_dev, losses, gstrong, gweak, stream);
 }
 
 extern "C" int sedk_sed_loss_dev(const float* strong, const float* weak, const float* t_strong, const float* t_weak,
@@ -522,6 +543,6 @@ extern "C" int sedk_sed_loss_dev(const float* strong, const float* weak, const f
         sedk::set_error("sedk_sed_loss_dev: cons_weight_dev is null");
         return SEDK_ERR_INVALID;
     }
-    return sed_loss_impl(strong, weak, t_strong, t_weak, labels, labels_weak, B, C, T, n_strong, n_weak, 0.f,
+    return sed_loss_impl(strong, weak, t_strong, t_weak, labels, labels_weak, B, C, T, n_strong, n_weak, 0, 0, 0.f,
                          cons_weight_dev, losses, gstrong, gweak, stream);
 }

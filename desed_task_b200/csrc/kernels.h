@@ -116,6 +116,14 @@ int launch_gru_seq_bwd(const float* gout, const float* const w_hh[2], const floa
                        const float* const hprev[2], float* const dgi[2], float* const dghn[2], float* const gb_ih[2],
                        float* const gb_hh[2], int B, int T, int H, int zeroed, cudaStream_t s);
 
+// gru3.cu: third-generation H = 128 recurrence, one (row, direction) per CTA (variant 1: 8 warps, all weights in registers;
+// variant 2: 16 warps)
+int launch_gru_fwd_v3(const float* const gi[2], const float* const w_hh[2], const float* const b_hh[2], float* out,
+                      float* const gates[2], float* const hprev[2], int B, int T, int save, int variant, cudaStream_t s);
+int launch_gru_bwd_v3(const float* gout, const float* const w_hh[2], const float* const gates[2],
+                      const float* const hprev[2], float* const dgi[2], float* const dghn[2], float* const gb_ih[2],
+                      float* const gb_hh[2], int B, int T, int zeroed, int variant, cudaStream_t s);
+
 // ---- heads.cu -----------------------------------------------------------------------------------------------
 int launch_heads_fwd(const float* x, const float* dw, const float* db, const float* sw, const float* sb,
                      const uint8_t* cmask, float* strong, float* weak, float* sof, float* hsum, int B, int T, int D,

@@ -48,6 +48,9 @@ SEDK_API int sedk_get_tcgen05(void);
 SEDK_API int sedk_set_gru_cluster(int cs);
 /* Named integer switches selecting between kernel variants (A/B measurements, parity tests).  Unset options take their
  * default from the environment variable SEDK_<NAME> (upper case), else the built-in default.  Known names:
+ *   "gru_v3"      1 (default): H = 128 recurrence, third generation (csrc/gru3.cu): 8 warps, every W_hh weight in registers,
+ *                 octet-per-4-units layout (4 LDS.128 of h per thread and step, transposing-butterfly reductions); 2: the
+ *                 16-warp variant of the same layout; 0: fall through to "gru_v2"
  *   "gru_v2"      1 (default): H = 128 recurrence with the quad-per-unit layout (shuffle reductions, one barrier per
  *                 step); 0: first-generation kernel (row x k-segment layout, partial sums through shared memory)
  *   "bnglu_small" 1 (default): register-resident warp-autonomous BN+GLU+pool kernels for 16 / 32 channels; 0: tiled kernel
@@ -291,6 +294,16 @@ SEDK_API int sedk_sed_loss(const float* strong, const float* weak, const float* 
 SEDK_API int sedk_sed_loss_dev(const float* strong, const float* weak, const float* t_strong, const float* t_weak,
                       const float* labels, const float* labels_weak, int B, int C, int T, int n_strong, int n_weak,
                       const float* cons_weight_dev, float* losses, float* gstrong, float* gweak, void* stream);
+
+/* General form.  cons_row0: the consistency term covers rows [cons_row0, B) only - 0 in the 2023 recipe, `indx_maestro` in the
+ * 2024 one (`mask_unlabeled`, recipes/dcase2024_task4_baseline/local/sed_trainer_pretrained.py:343-346,408-415); its mean is
+ * taken over those rows.  cons_kind: 0 = MSELoss, 1 = BCELoss(student, teacher) (`self_sup_loss: bce`,
+ * recipes/dcase2023_task4_baseline/local/sed_trainer.py:96-100).  cons_weight_dev (device float) overrides cons_weight
+ * when not NULL. */
+SEDK_API int sedk_sed_loss_ex(const float* strong, const float* weak, const float* t_strong, const float* t_weak,
+                     const float* labels, const float* labels_weak, int B, int C, int T, int n_strong, int n_weak,
+                     int cons_row0, int cons_kind, float cons_weight, const float* cons_weight_dev, float* losses,
+                     float* gstrong, float* gweak, void* stream);
 
 /* Stand-alone entry points of the two convolution building blocks (channels-last tensors, 3x3 / pad 1 / stride 1), used by the
  * unit tests and micro-benchmarks; inside the network they are driven through sedk_crnn_forward / backward.

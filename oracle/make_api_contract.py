@@ -54,8 +54,8 @@ def net_config(path):
 
 
 def contract():
-    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-    import refload                       # private package name: never the repo's own `desed_task` shim
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from baseline import refload                       # private package name: never the repo's own `desed_task` shim
     R = refload.load(REF)
     CRNN = R.CRNN
     CNN, GLU, ContextGating = R.CNN.CNN, R.CNN.GLU, R.CNN.ContextGating

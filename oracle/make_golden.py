@@ -37,7 +37,7 @@ def main():
         OUT = sys.argv[sys.argv.index("--out") + 1]
     # the reference is imported under a private package name: the repo's own `desed_task` shim must never be what is pinned
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    from oracle import refload
+    from baseline import refload
     R = refload.load(REF)
     CRNN = R.CRNN
     assert CRNN.__module__.startswith("_desed_ref") and sys.modules[CRNN.__module__].__file__.startswith(REF)

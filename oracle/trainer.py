@@ -158,3 +158,60 @@ def mean_teacher_step(student, teacher, audio, labels, batch_sizes, step_num, ra
                 loss_weak_teacher=loss_weak_t, weight=weight, strong_self_sup=strong_ss, weak_self_sup=weak_ss,
                 strong_student=strong_s, weak_student=weak_s, strong_teacher=strong_t, weak_teacher=weak_t,
                 features=features, labels=labels, labels_weak=labels_weak)
+
+
+def draw_mixup_2024(batch_sizes, with_embeddings=True):
+    """RNG consumption of the three `apply_mixup` calls of the 2024 step (sed_trainer_pretrained.py:350-363 ->
+    :282-301): groups in the order weak [indx_strong, indx_weak), synth+strong [indx_maestro, indx_strong),
+    maestro [0, indx_maestro); inside a group first the features' (c, perm), then the embeddings' (c, perm)."""
+    cs = np.cumsum(batch_sizes)
+    groups = [(int(cs[2]), int(cs[3])), (int(cs[0]), int(cs[2])), (0, int(cs[0]))]
+    out = []
+    for lo, hi in groups:
+        feat = draw_mixup(hi - lo)
+        emb = draw_mixup(hi - lo) if with_embeddings else None
+        out.append(((lo, hi), feat, emb))
+    return out
+
+
+def mean_teacher_step_2024(student, teacher, audio, labels, embeddings, valid_class_mask, batch_sizes, step_num,
+                           rampup_len, cfg=ocrnn.CFG_2024, const_max=2.0, mix=None, mixup_type="soft", student_kw=None,
+                           teacher_kw=None, gru_impl="aten", use_const_weight=False):
+    """recipes/dcase2024_task4_baseline/local/sed_trainer_pretrained.py:318-430.
+
+    batch_sizes = [maestro, synth, strong, weak, unlabelled] (:335-337).  Masks (:339-346): strong rows [0, indx_strong),
+    weak rows [indx_strong, indx_weak), consistency rows `mask_unlabeled` = [indx_maestro, B).  `mix` = None or the list
+    draw_mixup_2024 returns (the `mixup_prob > random.random()` draw is the caller's): per group the FEATURES are mixed
+    with one (c, perm) and the EMBEDDINGS with an independent one, and the group's labels are mixed by both in turn
+    (:282-301).  Weak labels are derived from the MIXED labels (:366), then labels / weak labels are masked by
+    valid_class_mask (:367-370).  `use_const_weight`: current_epoch >= epoch_decay (:402-405)."""
+    cs = np.cumsum(batch_sizes)
+    i_maestro, i_strong, i_weak = int(cs[0]), int(cs[2]), int(cs[3])
+    features = ofe.mel_spectrogram(audio)
+    labels = labels.clone()
+    if mix is not None:
+        features = features.clone()
+        embeddings = embeddings.clone()
+        for (lo, hi), (c1, p1), emb_draw in mix:
+            f, y = mixup(features[lo:hi], labels[lo:hi], c1, p1, mixup_label_type=mixup_type)
+            features[lo:hi], labels[lo:hi] = f, y
+            if emb_draw is not None:
+                c2, p2 = emb_draw
+                e, y = mixup(embeddings[lo:hi], labels[lo:hi], c2, p2, mixup_label_type=mixup_type)
+                embeddings[lo:hi], labels[lo:hi] = e, y
+    labels_weak = (torch.sum(labels[i_strong:i_weak], -1) > 0).float()
+    labels = labels.masked_fill(~valid_class_mask[:, :, None].expand_as(labels), 0.0)
+    labels_weak = labels_weak.masked_fill(~valid_class_mask[i_strong:i_weak], 0.0)
+    kw = dict(embeddings=embeddings, classes_mask=valid_class_mask, gru_impl=gru_impl)
+    strong_s, weak_s = detect(features, student, cfg, True, **kw, **(student_kw or {}))
+    loss_strong = bce(strong_s[:i_strong], labels[:i_strong])
+    loss_weak = bce(weak_s[i_strong:i_weak], labels_weak)
+    with torch.no_grad():
+        strong_t, weak_t = detect(features, teacher, cfg, True, **kw, **(teacher_kw or {}))
+    weight = const_max if use_const_weight else const_max * warmup_scale(step_num, rampup_len)
+    strong_ss = F.mse_loss(strong_s[i_maestro:], strong_t.detach()[i_maestro:])
+    weak_ss = F.mse_loss(weak_s[i_maestro:], weak_t.detach()[i_maestro:])
+    tot = loss_strong + loss_weak + (strong_ss + weak_ss) * weight
+    return dict(tot_loss=tot, loss_strong=loss_strong, loss_weak=loss_weak, weight=weight, strong_self_sup=strong_ss,
+                weak_self_sup=weak_ss, strong_student=strong_s, weak_student=weak_s, strong_teacher=strong_t,
+                weak_teacher=weak_t, features=features, embeddings=embeddings, labels=labels, labels_weak=labels_weak)

@@ -58,6 +58,21 @@ def test_kernel_generations_agree(dev, feats, option, precision, tol_out, tol_gr
     _compare(res[1], res[0], tol_out, tol_grad)
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [(1, 2e-5, 2e-3), (0, 5e-4, 3e-2)])
+def test_gru_third_generation_agrees_with_second(dev, feats, variant, precision, tol_out, tol_grad):
+    """csrc/gru3.cu (octet layout, weights in registers; variant 1 = 8 warps, 2 = 16 warps) against the v2 recurrence."""
+    from desed_task_b200._lib import lib
+    res = {}
+    for on in (variant, 0):
+        lib().sedk_set_option(b"gru_v3", on)
+        try:
+            res[on] = _run(dev, feats, precision)
+        finally:
+            lib().sedk_set_option(b"gru_v3", 1)
+    _compare(res[variant], res[0], tol_out, tol_grad)
+
+
 def test_gru_two_rows_per_cta_path(dev):
     """Batches above 74 rows put two rows on a CTA: that path still runs the first-generation recurrence; it must agree
     with the single-row (v2) result on the same clips."""

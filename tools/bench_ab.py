@@ -53,10 +53,16 @@ def main():
     base = profile(L, student, mel, a, y, B)
     print("all defaults: eager step %.3f ms" % sum(base.values()))
     for opt in opts:
-        L.sedk_set_option(opt.encode(), 0)
+        alt = 0
+        if "=" in opt:                       # name=value: compare the default against that value
+            opt, alt = opt.split("=")
+            alt = int(alt)
+        dflt = L.sedk_get_option(opt.encode(), 1)
+        L.sedk_set_option(opt.encode(), alt)
         off = profile(L, student, mel, a, y, B)
-        L.sedk_set_option(opt.encode(), 1)
-        print("--- %s: eager step %.3f ms with the option OFF (%.3f ms ON)" % (opt, sum(off.values()), sum(base.values())))
+        L.sedk_set_option(opt.encode(), dflt)
+        print("--- %s: eager step %.3f ms with the option = %d (%.3f ms at the default %d)"
+              % (opt, sum(off.values()), alt, sum(base.values()), dflt))
         for k in sorted(set(base) | set(off)):
             t1, t0 = base.get(k, 0.0), off.get(k, 0.0)
             if abs(t1 - t0) > 0.004:
