@@ -462,18 +462,19 @@ def run_ours(args):
             lib_bar = library_bar(dev, wl, B, dev_a, dev_y)
         h2d = B * L_SAMPLES * 4 + (0 if is_inf else B * nclass * 156 * 4 + 64) + (B * EMB_SHAPE[0] * EMB_SHAPE[1] * 4 if is_2024 else 0)
         d2h = (B * nclass * 156 * 4 + B * nclass * 4) if is_inf else 64
-        cfg = workload_config(wl, B, world)
-        cfg.update({"precision": "front end fp32; CRNN GEMMs TF32 (fp32 storage / accumulate); recurrence, BN statistics, "
-                                 "heads, losses, optimizer fp32",
-                    "l2": "inputs rotate over %d distinct batches (%.0f MB > L2); per-step activations ~0.6 GB"
-                          % (NBUF, NBUF * B * L_SAMPLES * 4 / 1e6),
-                    "cuda_graph": True,
-                    "overlap": "front end of step k+1 runs on its own stream concurrently with step k's graph (ping-pong "
-                               "log-mel buffers); weight-gradient GEMMs on a side branch of the graph"})
+        cfg = workload_config(wl, B, world)             # identical in both arms; arm-specific detail goes to `implementation`
+        impl = {"precision": "front end fp32; CRNN GEMMs TF32 (fp32 storage / accumulate); recurrence, BN statistics, "
+                             "heads, losses, optimizer fp32",
+                "l2": "inputs rotate over %d distinct batches (%.0f MB > L2); per-step activations ~0.6 GB"
+                      % (NBUF, NBUF * B * L_SAMPLES * 4 / 1e6),
+                "cuda_graph": "forward + loss + backward + gradient all-reduce + fused EMA/Adam: one graph replay per step",
+                "overlap": "front end of step k+1 runs on its own stream concurrently with step k's graph (ping-pong "
+                           "log-mel buffers); weight-gradient GEMMs on a side branch of the graph"}
         out = {
             "metric": METRIC, "value": round(value, 1), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": W, "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32", "data": "synthetic", "config": cfg, "clocks": clocks,
+            "vs_baseline": None, "dtype": "tf32", "data": "synthetic", "config": cfg, "implementation": impl,
+            "clocks": clocks,
             "e2e": {"value": round(e2e, 1), "unit": "clips/s", "ms_per_step": round(ms_e2e / args.steps, 4),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "clocks": clocks_e2e},
             "gpu_launches": int(launches),
@@ -627,8 +628,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": W, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(wl, B, 1),
-        "arm": "host CPU, fp32, %s" % what,
+        "config": workload_config(wl, B, max(1, args.gpus)),
+        "implementation": "host CPU (rank 0 only), fp32, %s" % what,
         "cpu_baseline": {"value": v, "unit": "clips/s", "cores": threads, "kind": kind,
                          "sample": "%d steps of %d clips, %d of %d host threads (fastest of a sweep)"
                                    % (args.steps, B, threads, os.cpu_count() or 1)},

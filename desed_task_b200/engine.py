@@ -419,9 +419,12 @@ class InferEngine:
         self.B, self.L = int(batch), int(n_samples)
         self.dev = dev = next(model.parameters()).device
         self.use_graph = use_graph
-        self.win = median_window
         self.T = mel_spec.n_frames(n_samples)
         self.C = model.nclass
+        wins = [int(median_window)] * self.C if isinstance(median_window, int) else [int(v) for v in median_window]
+        if len(wins) != self.C or min(wins) < 1 or max(wins) > 31:
+            raise ValueError("InferEngine: need one median window in [1, 31] per class")
+        self.win = torch.tensor(wins, dtype=torch.int32, device=dev)
         self.emb_shape, self.class_masks = emb_shape, class_masks
         B = self.B
         self.audio_dev = [torch.empty(B, n_samples, device=dev) for _ in range(2)]

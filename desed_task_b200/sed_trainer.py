@@ -45,32 +45,37 @@ class _SedLoss(torch.autograd.Function):
     """BCE(strong rows) + BCE(weak rows) + w * (MSE strong + MSE weak) in one kernel pair (sedk_sed_loss)."""
 
     @staticmethod
-    def forward(ctx, strong, weak, t_strong, t_weak, labels, labels_weak, n_strong, n_weak, cons_weight):
+    def forward(ctx, strong, weak, t_strong, t_weak, labels, labels_weak, n_strong, n_weak, cons_weight, cons_row0,
+                cons_kind):
         B, C, T = strong.shape
         losses = torch.zeros(16, device=strong.device)
         gs, gw = torch.empty_like(strong), torch.empty_like(weak)
-        check(lib().sedk_sed_loss(ptr(strong.contiguous()), ptr(weak.contiguous()), ptr(t_strong), ptr(t_weak),
-                                  ptr(labels), ptr(labels_weak), B, C, T, n_strong, n_weak, float(cons_weight),
-                                  ptr(losses), ptr(gs), ptr(gw), stream_ptr()), "sedk_sed_loss")
+        check(lib().sedk_sed_loss_ex(ptr(strong.contiguous()), ptr(weak.contiguous()), ptr(t_strong), ptr(t_weak),
+                                     ptr(labels), ptr(labels_weak), B, C, T, n_strong, n_weak, int(cons_row0),
+                                     int(cons_kind), float(cons_weight), None, ptr(losses), ptr(gs), ptr(gw),
+                                     stream_ptr()), "sedk_sed_loss_ex")
         ctx.save_for_backward(gs, gw)
         return losses[0], losses[:8]
 
     @staticmethod
     def backward(ctx, g_total, g_parts):
         gs, gw = ctx.saved_tensors
-        return gs * g_total, gw * g_total, None, None, None, None, None, None, None
+        return gs * g_total, gw * g_total, None, None, None, None, None, None, None, None, None
 
 
-def sed_loss(strong, weak, labels_strong, labels_weak, t_strong=None, t_weak=None, cons_weight=0.0):
+def sed_loss(strong, weak, labels_strong, labels_weak, t_strong=None, t_weak=None, cons_weight=0.0, cons_row0=0,
+             self_sup_loss="mse"):
     """rows [0, n_strong) of `strong` against labels_strong [n_strong,C,T]; rows [n_strong, n_strong+n_weak) of `weak`
-    against labels_weak [n_weak,C]; consistency against the teacher on every row.  Returns (total, parts[8])."""
+    against labels_weak [n_weak,C]; consistency (MSELoss or BCELoss, sed_trainer.py:96-100) against the teacher on rows
+    [cons_row0, B).  Returns (total, parts[8])."""
     n_s = 0 if labels_strong is None else labels_strong.shape[0]
     n_w = 0 if labels_weak is None else labels_weak.shape[0]
     ls = labels_strong.float().contiguous() if n_s else None
     lw = labels_weak.float().contiguous() if n_w else None
     ts = t_strong.detach().float().contiguous() if t_strong is not None else None
     tw = t_weak.detach().float().contiguous() if t_weak is not None else None
-    return _SedLoss.apply(strong, weak, ts, tw, ls, lw, n_s, n_w, cons_weight)
+    return _SedLoss.apply(strong, weak, ts, tw, ls, lw, n_s, n_w, cons_weight, cons_row0,
+                          1 if self_sup_loss == "bce" else 0)
 
 
 class SEDTask4(_Base):
@@ -102,7 +107,7 @@ class SEDTask4(_Base):
         if hparams["training"]["self_sup_loss"] == "mse":
             self.selfsup_loss = torch.nn.MSELoss()
         elif hparams["training"]["self_sup_loss"] == "bce":
-            raise NotImplementedError("self_sup_loss='bce' is not implemented by the fused loss kernel (shipped: 'mse')")
+            self.selfsup_loss = torch.nn.BCELoss()
         else:
             raise NotImplementedError
         self.scaler = self._init_scaler()
@@ -172,7 +177,8 @@ class SEDTask4(_Base):
             strong_preds_teacher, weak_preds_teacher = self.detect(features, self.sed_teacher)
         weight = self.hparams["training"]["const_max"] * self.scheduler["scheduler"]._get_scaling_factor()
         tot_loss, parts = sed_loss(strong_preds_student, weak_preds_student, labels[:indx_synth], labels_weak,
-                                   strong_preds_teacher, weak_preds_teacher, weight)
+                                   strong_preds_teacher, weak_preds_teacher, weight,
+                                   self_sup_loss=self.hparams["training"]["self_sup_loss"])
         self.log("train/student/loss_strong", parts[1])
         self.log("train/student/loss_weak", parts[2])
         self.log("train/teacher/loss_strong", parts[5])
@@ -202,7 +208,9 @@ class SEDTask4(_Base):
                 self.sed_student, self.mel_spec, tr["batch_size"], n_samples, opt=opt, scheduler=sched,
                 teacher=self.sed_teacher if teacher else None, ema_factor=tr.get("ema_factor", 0.999),
                 const_max=tr.get("const_max", 2.0), mixup_type=tr.get("mixup"), use_graph=use_graph,
-                process_group=process_group, grad_clip=tr.get("gradient_clip", 0.0) or 0.0)
+                process_group=process_group, grad_clip=tr.get("gradient_clip", 0.0) or 0.0,
+                recipe="2024" if len(tr["batch_size"]) == 5 else "2023", mixup_prob=tr.get("mixup_prob", 0.5),
+                self_sup_loss=tr.get("self_sup_loss", "mse"))
         return self._engine
 
     def fit_step(self, batch, use_graph=True, process_group=None):

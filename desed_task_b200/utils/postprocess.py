@@ -17,12 +17,18 @@ def median_filter(strong, win, class_dim=1):
     assert x.dim() == 3 and class_dim in (1, 2)
     Cn = x.shape[class_dim]
     Tn = x.shape[3 - class_dim]
-    if isinstance(win, int):
-        win = [win] * Cn
-    win = [int(w) for w in win]
-    if len(win) != Cn or min(win) < 1 or max(win) > 31:
-        raise ValueError("median_filter: need one window in [1, 31] per class (got %s)" % (win,))
-    w = torch.tensor(win, dtype=torch.int32, device=x.device)
+    if isinstance(win, torch.Tensor):
+        # a ready-made int32 device tensor of per-class windows (validated by its maker; lets the call sit in a CUDA graph)
+        if win.dtype != torch.int32 or win.numel() != Cn or win.device != x.device:
+            raise ValueError("median_filter: window tensor must be int32 [%d] on %s" % (Cn, x.device))
+        w = win
+    else:
+        if isinstance(win, int):
+            win = [win] * Cn
+        win = [int(v) for v in win]
+        if len(win) != Cn or min(win) < 1 or max(win) > 31:
+            raise ValueError("median_filter: need one window in [1, 31] per class (got %s)" % (win,))
+        w = torch.tensor(win, dtype=torch.int32, device=x.device)
     out = torch.empty_like(x)
     sc, st = x.stride(class_dim), x.stride(3 - class_dim)
     oc, ot = out.stride(class_dim), out.stride(3 - class_dim)

@@ -17,9 +17,25 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "clips/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference": the unmodified reference modules (checkout / baseline/_ref install); "port": the oracle restatement
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config("supervised", 2, 1)          # the same object the GPU arm prints
+
+
+def test_workload_splits():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.batch_split("supervised", 24) == [12, 12, 0] and bench.batch_split("mean_teacher", 48) == [12, 12, 24]
+    assert bench.batch_split("dcase2024", 60) == [12, 6, 6, 12, 24]          # pretrained.yaml:8
+    s = bench.batch_split("dcase2024", 24)
+    assert sum(s) == 24 and len(s) == 5 and min(s) >= 1
+    cm = bench.class_masks_2024(s)
+    assert cm.shape == (24, 27) and cm[0, 10:].all() and not cm[0, :10].any() and cm[-1, :10].all()
 
 
 def test_reference_arm_other_ranks_exit_quietly():

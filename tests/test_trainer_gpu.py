@@ -285,3 +285,232 @@ def test_fused_engine_on_the_2024_network(dev, use_graph):
         tot += d.numel()
         bad += int((d > 2e-4).sum())
     assert bad / tot < 0.01, (bad, tot)
+
+
+# =====================================================================================================================
+# round 2: parity at the shapes bench.py times, and the 2024 recipe's own step semantics
+def _margin(line):
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "r2_parity_margins.txt"), "a") as f:
+        f.write(line + "\n")
+
+
+def _param_check(student, Ps, steps, tag):
+    tot = bad = 0
+    worst = 0.0
+    for n, p in student.named_parameters():
+        if _noise_param(n):
+            continue
+        d = (p.detach().cpu() - Ps[n].detach()).abs()
+        assert d.max().item() <= steps * 2.05e-3, (tag, n, d.max().item())      # |dp| <= lr per Adam step
+        tot += d.numel()
+        bad += int((d > 2e-4).sum())
+        worst = max(worst, d.max().item())
+    return bad / tot, worst
+
+
+@pytest.mark.parametrize("workload,precision", [("supervised", 1), ("supervised", 0), ("mean_teacher", 1), ("mean_teacher", 0)])
+def test_engine_parity_at_the_benchmarked_shapes(dev, workload, precision):
+    """The exact batch shapes bench.py times - 24 clips [12 strong, 12 weak] supervised and 48 clips [12, 12, 24] mean
+    teacher (confs/default.yaml:3) - two consecutive fused steps (CUDA graph) against the oracle: frame / clip posteriors of
+    the first forward (north-star bound 1e-3 in the TF32 production mode, 2e-5 in the 3xTF32 mode), losses, the Adam / EMA
+    updates.  Dropout and SpecAugment off (device-side Philox draws cannot be mirrored on the host)."""
+    from desed_task_b200.engine import TrainEngine
+    from desed_task_b200.frontend import MelSpectrogram
+    from desed_task_b200.optim import FusedAdam
+    from desed_task_b200.utils.schedulers import ExponentialWarmup
+    from tests.test_crnn_gpu import build
+    mt = workload == "mean_teacher"
+    bs = [12, 12, 24] if mt else [12, 12, 0]
+    B = sum(bs)
+    cfg = dataclasses.replace(ocrnn.CFG_2023, dropout=0.0)
+    P = ocrnn.init_params(cfg, seed=9, trained_like=True)
+    student = build(cfg, P, dev, precision, specaugm_t_p=0.0, specaugm_f_p=0.0)
+    teacher = None
+    if mt:
+        teacher = copy.deepcopy(student)
+        for p in teacher.parameters():
+            p.detach_()
+        teacher.train()
+    student.train()
+    mel = MelSpectrogram(16000, 2048, 2048, 256, 0, 8000, n_mels=128, window_fn=torch.hamming_window,
+                         wkwargs={"periodic": False}, power=1).to(dev)
+    audio = gen_wave(77, B)
+    g = torch.Generator().manual_seed(78)
+    labels = (torch.rand(B, 10, 156, generator=g) < 0.12).float()
+    labels[12:24, :, 1:] = 0
+    opt = FusedAdam(student, 1e-3)
+    sched = ExponentialWarmup(opt, 1e-3, 100)
+    eng = TrainEngine(student, mel, bs, 160000, opt=opt, scheduler=sched, teacher=teacher,
+                      mixup_type="soft" if mt else None, use_graph=True)
+    names = ocrnn.param_names(P)
+    Ps = {k: (v.clone().requires_grad_(True) if ocrnn.is_float_param(k) else v.clone()) for k, v in P.items()}
+    Pt = {k: v.clone() for k, v in P.items()}
+    state, ref, first = {}, [], None
+    random.seed(4); np.random.seed(4); torch.manual_seed(4)
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    for step in (1, 2):
+        bsn, btn = {}, {}
+        if mt:
+            mix = None
+            if 0.5 > random.random():
+                w = otr.draw_mixup(bs[1]); s = otr.draw_mixup(bs[0])
+                mix = dict(weak=w, strong=s)
+            out = otr.mean_teacher_step(Ps, Pt, audio, labels, bs, step, 100, cfg, 2.0, mix, "soft", gru_impl="aten",
+                                        student_kw=dict(bn_state=bsn), teacher_kw=dict(bn_state=btn))
+            loss, so, wo = out["tot_loss"], out["strong_student"], out["weak_student"]
+        else:
+            loss, so, wo = otr.supervised_step(Ps, audio, labels, bs[0], bs[1], cfg, True, fwd_kw=dict(bn_state=bsn),
+                                               gru_impl="aten")
+        if first is None:
+            first = (so.detach().clone(), wo.detach().clone())
+        grads = torch.autograd.grad(loss, [Ps[k] for k in names])
+        with torch.no_grad():
+            if mt:
+                otr.update_ema(0.999, step, Ps, Pt, names)
+            otr.adam_step({k: Ps[k] for k in names}, dict(zip(names, grads)), state, names,
+                          1e-3 if step == 1 else 1e-3 * otr.warmup_scale(step, 100))
+            for k, v in bsn.items():
+                Ps[k] = v
+            for k, v in btn.items():
+                Pt[k] = v
+        ref.append(loss.item())
+    random.seed(4); np.random.seed(4); torch.manual_seed(4)
+    a_pin, l_pin = audio.pin_memory(), labels.pin_memory()
+    got = []
+    for step in range(2):
+        r = eng.step(a_pin, l_pin)
+        got.append(eng.read_losses(r)["total"])
+        if step == 0:
+            torch.cuda.synchronize()
+            keep = eng.keeps[0]
+            es, ew = maxdiff(keep[2], first[0]), maxdiff(keep[3], first[1])
+    tol_post = 2e-5 if precision == 1 else 1e-3
+    tol_loss = 3e-4 if precision == 1 else 5e-3
+    torch.cuda.synchronize()
+    frac_bad, worst = _param_check(student, Ps, 2, workload)
+    _margin("engine %s B=%d precision=%d: posterior max|diff| strong %.3g weak %.3g (bound %.0e); loss diff %s (bound %.0e); "
+            "params off by > 2e-4: %.4f%% (worst %.3g)" % (workload, B, precision, es, ew, tol_post,
+                                                           ["%.3g" % abs(a - b) for a, b in zip(got, ref)], tol_loss,
+                                                           100 * frac_bad, worst))
+    assert es < tol_post and ew < tol_post, (es, ew)
+    for a, b in zip(got, ref):
+        assert abs(a - b) < tol_loss, (got, ref)
+    assert frac_bad < (0.01 if precision == 1 else 0.05), frac_bad
+    sd = student.state_dict()
+    # running_var, not running_mean: the batch mean carries the conv bias, a zero-gradient parameter that the oracle's Adam
+    # moves by +-lr per step on fp32 noise (see _noise_param), which shows up 1:1 in the second step's running mean
+    for i in (0, 3):
+        k = "cnn.cnn.batchnorm%d.running_var" % i
+        assert maxdiff(sd[k], Ps[k]) < (2e-5 if precision else 2e-3) * max(1.0, Ps[k].abs().max().item()), k
+    assert int(sd["cnn.cnn.batchnorm6.num_batches_tracked"]) == 2
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+@pytest.mark.parametrize("seed", [1, 0])               # seed 1: the mixup branch is taken on step 1, seed 0: it is not
+def test_fused_engine_follows_the_2024_recipe_step(dev, use_graph, seed):
+    """recipes/dcase2024_task4_baseline/local/sed_trainer_pretrained.py:318-430 through the fused engine: five-way batch
+    split [maestro, synth, strong, weak, unlabelled], mixup inside the three label groups with independent (c, perm) for
+    features and embeddings (labels mixed by both), weak labels from the mixed labels, class-masked labels and posteriors,
+    consistency (MSE) on the rows after the MAESTRO block only, gradient clipping - two steps against the oracle."""
+    from desed_task_b200.engine import TrainEngine
+    from desed_task_b200.frontend import MelSpectrogram
+    from desed_task_b200.optim import FusedAdam
+    from desed_task_b200.utils.schedulers import ExponentialWarmup
+    from tests.test_crnn_gpu import build
+    bs = [3, 2, 1, 2, 2]
+    B = sum(bs)
+    cfg = dataclasses.replace(ocrnn.CFG_2024, dropout=0.0)
+    P = ocrnn.init_params(cfg, seed=5, trained_like=True)
+    student = build(cfg, P, dev, 1, specaugm_t_p=0.0, specaugm_f_p=0.0, dropstep_recurrent=0.0)
+    teacher = copy.deepcopy(student)
+    for p in teacher.parameters():
+        p.detach_()
+    student.train(); teacher.train()
+    mel = MelSpectrogram(16000, 2048, 2048, 256, 0, 8000, n_mels=128, window_fn=torch.hamming_window,
+                         wkwargs={"periodic": False}, power=1).to(dev)
+    g = torch.Generator().manual_seed(12)
+    audio = gen_wave(32, B)
+    emb = torch.randn(B, 768, 496, generator=g)
+    cm = torch.zeros(B, 27, dtype=torch.bool)
+    cm[:3, 10:] = True                                     # MAESTRO rows: the 17 MAESTRO classes
+    cm[3:, :10] = True                                     # DESED rows
+    # labels are NOT pre-masked: the step itself has to zero the classes a row's dataset does not annotate (:367-370)
+    labels = (torch.rand(B, 27, 156, generator=g) < 0.15).float()
+    labels[6:8, :, 1:] = 0
+    opt = FusedAdam(student, 1e-3)
+    sched = ExponentialWarmup(opt, 1e-3, 100)
+    eng = TrainEngine(student, mel, bs, 160000, opt=opt, scheduler=sched, teacher=teacher, mixup_type="soft",
+                      use_graph=use_graph, grad_clip=0.5, emb_shape=(768, 496), class_masks=cm.to(dev), recipe="2024")
+    names = ocrnn.param_names(P)
+    Ps = {k: (v.clone().requires_grad_(True) if ocrnn.is_float_param(k) else v.clone()) for k, v in P.items()}
+    Pt = {k: v.clone() for k, v in P.items()}
+    state, ref, mixes = {}, [], []
+    random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+    for step in (1, 2):
+        bsn, btn = {}, {}
+        mix = otr.draw_mixup_2024(bs) if 0.5 > random.random() else None
+        mixes.append(mix is not None)
+        out = otr.mean_teacher_step_2024(Ps, Pt, audio, labels, emb, cm, bs, step, 100, cfg, 2.0, mix, "soft",
+                                         student_kw=dict(bn_state=bsn), teacher_kw=dict(bn_state=btn))
+        grads = list(torch.autograd.grad(out["tot_loss"], [Ps[k] for k in names]))
+        norm = torch.sqrt(sum((gg.double() ** 2).sum() for gg in grads)).item()
+        clip = min(1.0, 0.5 / (norm + 1e-6))
+        grads = [gg * clip for gg in grads]
+        with torch.no_grad():
+            otr.update_ema(0.999, step, Ps, Pt, names)
+            otr.adam_step({k: Ps[k] for k in names}, dict(zip(names, grads)), state, names,
+                          1e-3 if step == 1 else 1e-3 * otr.warmup_scale(step, 100))
+            for k, v in bsn.items():
+                Ps[k] = v
+            for k, v in btn.items():
+                Pt[k] = v
+        ref.append((out["tot_loss"].item(), out["loss_strong"].item(), out["loss_weak"].item(),
+                    out["strong_self_sup"].item(), out["weak_self_sup"].item()))
+    assert mixes[0] == (seed == 1)
+    random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+    a_pin, l_pin, e_pin = audio.pin_memory(), labels.pin_memory(), emb.pin_memory()
+    worst = 0.0
+    for step in range(2):
+        r = eng.step(a_pin, l_pin, e_pin)
+        got = eng.read_losses(r)
+        vals = (got["total"], got["bce_strong"], got["bce_weak"], got["mse_strong"], got["mse_weak"])
+        for a, b, tol in zip(vals, ref[step], (5e-4, 2e-4, 2e-4, 5e-5, 5e-5)):
+            worst = max(worst, abs(a - b))
+            assert abs(a - b) < tol, (step, vals, ref[step])
+    torch.cuda.synchronize()
+    frac_bad, wp = _param_check(student, Ps, 2, "2024")
+    _margin("engine 2024 recipe B=%d graph=%s seed=%d (mixup on step 1: %s): worst loss-term diff %.3g; params off by > 2e-4: "
+            "%.4f%% (worst %.3g)" % (B, use_graph, seed, mixes[0], worst, 100 * frac_bad, wp))
+    assert frac_bad < 0.01, frac_bad
+    for n, p in teacher.named_parameters():
+        if not _noise_param(n):
+            d = (p.detach().cpu() - Pt[n].detach()).abs()
+            assert d.max().item() <= 4.1e-3 and (d > 2e-4).float().mean().item() < 0.01, n
+
+
+def test_bce_consistency_loss_matches_torch(dev):
+    """`self_sup_loss: bce` (sed_trainer.py:96-100): BCELoss(student, teacher) as the consistency term, values + gradients."""
+    from desed_task_b200._lib import check, lib, ptr, stream_ptr
+    g = torch.Generator().manual_seed(3)
+    B, C, T = 6, 10, 156
+    strong = torch.rand(B, C, T, generator=g) * 0.98 + 0.01
+    weak = torch.rand(B, C, generator=g) * 0.98 + 0.01
+    ts, tw = torch.rand(B, C, T, generator=g), torch.rand(B, C, generator=g)
+    y = (torch.rand(2, C, T, generator=g) < 0.2).float()
+    yw = (torch.rand(2, C, generator=g) < 0.3).float()
+    for row0 in (0, 2):
+        s_, w_ = strong.clone().requires_grad_(True), weak.clone().requires_grad_(True)
+        f = torch.nn.functional.binary_cross_entropy
+        ref = f(s_[:2], y) + f(w_[2:4], yw) + 1.5 * (f(s_[row0:], ts[row0:]) + f(w_[row0:], tw[row0:]))
+        ref.backward()
+        losses = torch.zeros(16, device=dev)
+        gs, gw = torch.empty(B, C, T, device=dev), torch.empty(B, C, device=dev)
+        d = [t.to(dev).contiguous() for t in (strong, weak, ts, tw, y, yw)]
+        check(lib().sedk_sed_loss_ex(ptr(d[0]), ptr(d[1]), ptr(d[2]), ptr(d[3]), ptr(d[4]), ptr(d[5]), B, C, T, 2, 2, row0, 1,
+                                     1.5, None, ptr(losses), ptr(gs), ptr(gw), stream_ptr()), "sedk_sed_loss_ex")
+        assert abs(losses[0].item() - ref.item()) < 2e-5 * max(1.0, abs(ref.item()))
+        assert maxdiff(gs, s_.grad) < 1e-6 + 1e-4 * s_.grad.abs().max().item()
+        assert maxdiff(gw, w_.grad) < 1e-6 + 1e-4 * w_.grad.abs().max().item()
