@@ -89,6 +89,7 @@ _SIGS = {
     "sedk_sumsq": (i32, [vp, i64, vp, vp]),
     "sedk_mask_spans": (i32, [vp, i32, i32, i32, i32, i32, u64, vp, u64, vp]),
     "sedk_median_filter": (i32, [vp, vp, i32, i32, i32, i64, i64, i64, i64, i64, i64, vp, vp]),
+    "sedk_decode_events": (i32, [vp, i32, i32, i32, i64, i64, i64, vp, i32, vp, vp, vp, i32, vp]),
     "sedk_crnn_forward": (i32, [C.POINTER(CrnnPlan), vp]),
     "sedk_crnn_backward": (i32, [C.POINTER(CrnnPlan), vp]),
     "sedk_sed_loss": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp]),

@@ -253,6 +253,74 @@ median_kernel(const float* __restrict__ s, float* __restrict__ out, int C, int T
     }
 }
 
+// ---- threshold + run-length event decoding -----------------------------------------------------------------------
+// One thread owns one row (threshold th, clip b, class c) and scans its T frames once: an event starts where
+// score > threshold turns true and ends at the first frame where it is false again (or at the clip's length).
+// COUNT = true: number of events of the row -> cnt[row];  COUNT = false: the row's events -> events[off[row] + e].
+template <bool COUNT>
+__global__ void __launch_bounds__(EW_THREADS)
+decode_events_kernel(const float* __restrict__ s, int B, int C, int T, int64_t sb, int64_t sc, int64_t st,
+                     const float* __restrict__ thr, int n_th, const int32_t* __restrict__ n_frames,
+                     int32_t* __restrict__ cnt, const int32_t* __restrict__ off, int32_t* __restrict__ events,
+                     int capacity) {
+    const int rows = n_th * B * C;
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += gridDim.x * blockDim.x) {
+        // rows ordered (th, b, c); neighbouring threads share (th, b) and walk neighbouring classes
+        const int c = row % C, b = (row / C) % B, th = row / (C * B);
+        const float* p = s + (int64_t)b * sb + (int64_t)c * sc;
+        const float t_ = thr[th];
+        int len = T;
+        if (n_frames != nullptr) len = min(max(n_frames[b], 0), T);
+        int n = 0, onset = -1;
+        int base = COUNT ? 0 : off[row];
+        for (int t = 0; t < len; t++) {
+            const bool a = p[(int64_t)t * st] > t_;
+            if (a && onset < 0) onset = t;
+            if (!a && onset >= 0) {
+                if (!COUNT && base + n < capacity) {
+                    events[2 * (base + n)] = onset;
+                    events[2 * (base + n) + 1] = t;
+                }
+                n++;
+                onset = -1;
+            }
+        }
+        if (onset >= 0) {
+            if (!COUNT && base + n < capacity) {
+                events[2 * (base + n)] = onset;
+                events[2 * (base + n) + 1] = len;
+            }
+            n++;
+        }
+        if (COUNT) cnt[row] = n;
+    }
+}
+
+// exclusive prefix sum of n int32 counts, in place, by ONE block of 1024 threads (n is a few 10^4 rows); v[n] = total
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(int32_t* __restrict__ v, int n) {
+    __shared__ int32_t part[1024];
+    const int tid = threadIdx.x;
+    const int per = (n + 1023) / 1024;
+    const int lo = min(tid * per, n), hi = min(lo + per, n);
+    int32_t sum = 0;
+    for (int i = lo; i < hi; i++) sum += v[i];
+    part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int32_t add = tid >= o ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += add;
+        __syncthreads();
+    }
+    int32_t run = part[tid] - sum;           // exclusive prefix of this thread's chunk
+    for (int i = lo; i < hi; i++) {
+        const int32_t c = v[i];
+        v[i] = run;
+        run += c;
+    }
+    if (tid == 1023) v[n] = part[1023];
+}
+
 inline dim3 grid2(int64_t n, int B, int per_thread = 4) {
     int64_t blocks = (n + (int64_t)EW_THREADS * per_thread - 1) / ((int64_t)EW_THREADS * per_thread);
     int64_t cap = (int64_t)num_sms() * 8 / (B > 0 ? B : 1) + 1;
@@ -446,5 +514,27 @@ extern "C" int sedk_median_filter(const float* scores, float* out, int B, int C,
     median_kernel<<<grid1(total, 1), EW_THREADS, 0, (cudaStream_t)stream>>>(scores, out, C, T, sb, sc, st, ob, oc, ot, win,
                                                                            total);
     SEDK_LAUNCH_CHECK("median_kernel");
+    return SEDK_OK;
+}
+
+extern "C" int sedk_decode_events(const float* scores, int B, int C, int T, int64_t sb, int64_t sc, int64_t st,
+                                  const float* thresholds, int n_th, const int32_t* n_frames, int32_t* offsets,
+                                  int32_t* events, int capacity, void* stream) {
+    using namespace sedk;
+    SEDK_REQUIRE(scores && thresholds && offsets && events, "sedk_decode_events: null pointer");
+    SEDK_REQUIRE(B > 0 && C > 0 && T > 0 && n_th > 0 && capacity >= 0, "sedk_decode_events: bad sizes");
+    SEDK_REQUIRE((int64_t)n_th * B * C < (1ll << 30), "sedk_decode_events: too many rows");
+    cudaStream_t s = (cudaStream_t)stream;
+    SEDK_PROF("decode_events", s);
+    const int rows = n_th * B * C;
+    const int blocks = cdiv(rows, EW_THREADS);
+    decode_events_kernel<true><<<blocks, EW_THREADS, 0, s>>>(scores, B, C, T, sb, sc, st, thresholds, n_th, n_frames,
+                                                            offsets, nullptr, nullptr, 0);
+    SEDK_LAUNCH_CHECK("decode_events_kernel<count>");
+    exclusive_scan_kernel<<<1, 1024, 0, s>>>(offsets, rows);
+    SEDK_LAUNCH_CHECK("exclusive_scan_kernel");
+    decode_events_kernel<false><<<blocks, EW_THREADS, 0, s>>>(scores, B, C, T, sb, sc, st, thresholds, n_th, n_frames,
+                                                             nullptr, offsets, events, capacity);
+    SEDK_LAUNCH_CHECK("decode_events_kernel<write>");
     return SEDK_OK;
 }

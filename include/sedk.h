@@ -165,6 +165,20 @@ SEDK_API int sedk_sumsq(const float* g, int64_t n, double* out, void* stream);
 SEDK_API int sedk_median_filter(const float* scores, float* out, int B, int C, int T, int64_t sb, int64_t sc, int64_t st,
                        int64_t ob, int64_t oc, int64_t ot, const int32_t* win, void* stream);
 
+/* Threshold + run-length event decoding of (median-filtered) frame scores on the device: replaces the per-clip D2H,
+ * `c_scores > c_th` and ManyHotEncoder.decode_strong loop of batched_decode_preds
+ * (recipes/dcase2023_task4_baseline/local/utils.py:64-71; desed_task/utils/encoder.py:189-211, whose
+ * DecisionEncoder.find_contiguous_regions comes from dcase_util: regions [onset, offset) of consecutive true frames).
+ * scores element (b, c, t) at base + b*sb + c*sc + t*st; thresholds float[n_th] (device); n_frames int32[B] (device) = true
+ * length of each clip in frames (pad_indx), or NULL for T.
+ * Rows are ordered (threshold, clip, class) - the order in which the reference appends to its per-threshold DataFrames.
+ *   offsets int32[n_th*B*C + 1]: on return the exclusive prefix sum of the per-row event counts, offsets[rows] = total
+ *   events  int32[capacity][2] : {onset_frame, offset_frame} of event e of row r at events[offsets[r] + e]
+ * Events beyond `capacity` are dropped (the total still reports all of them, so the caller can re-run with a larger buffer). */
+SEDK_API int sedk_decode_events(const float* scores, int B, int C, int T, int64_t sb, int64_t sc, int64_t st,
+                       const float* thresholds, int n_th, const int32_t* n_frames, int32_t* offsets, int32_t* events,
+                       int capacity, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * CRNN (desed_task/nnet/CRNN.py, CNN.py, RNN.py) - whole-network forward / backward on a caller-provided plan.
  */

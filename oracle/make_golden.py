@@ -259,6 +259,57 @@ def main():
     assert (pr.data - P["p"]).abs().max().item() < 1e-7
     report["adam"] = "oracle adam_step == torch.optim.Adam (5 steps, <=1e-7)"
 
+    # ------------------------------------------------------------------ event decoding (f1)
+    # desed_task/utils/encoder.py imports dcase_util (absent here) for ONE function, DecisionEncoder.find_contiguous_regions;
+    # the encoder itself (frame <-> time maps, decode_strong's loop) is the reference's own code and is pinned live with
+    # that single dependency stubbed by the oracle's restatement of the published algorithm.
+    import types
+    stub, stub_data = types.ModuleType("dcase_util"), types.ModuleType("dcase_util.data")
+
+    class DecisionEncoder:                                        # noqa: D401 - stand-in for dcase_util.data.DecisionEncoder
+        def find_contiguous_regions(self, activity_array):
+            return opost.find_contiguous_regions(activity_array)
+    stub_data.DecisionEncoder = DecisionEncoder
+    stub.data = stub_data
+    saved = {k: sys.modules.get(k) for k in ("dcase_util", "dcase_util.data")}
+    sys.modules["dcase_util"], sys.modules["dcase_util.data"] = stub, stub_data
+    try:
+        enc_mod = _load(f"{REF}/desed_task/utils/encoder.py", "ref_encoder")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    labels10 = ["c%d" % i for i in range(10)]
+    enc = enc_mod.ManyHotEncoder(labels10, audio_len=10, frame_len=2048, frame_hop=256, net_pooling=4, fs=16000)
+    fr = np.arange(0, 200)
+    assert np.array_equal(enc._frame_to_time(fr), opost.frame_to_time(fr))
+    rs = np.random.RandomState(11)
+    # smooth-ish scores so that thresholding gives realistic event runs, plus hand-made edge cases (clip start / end)
+    dsc = rs.rand(4, 10, 156).astype(np.float32)
+    dsc = (dsc + np.roll(dsc, 1, -1) + np.roll(dsc, 2, -1) + np.roll(dsc, 3, -1)) / 4
+    dsc[0, 0, :5] = 0.99
+    dsc[0, 1, 150:] = 0.99
+    dsc[1, 2, :] = 0.99
+    dsc[1, 3, :] = 0.0
+    ths = [0.3, 0.5, 0.55, 0.7]
+    post, preds = opost.batched_decode(dsc, labels10, ths, 7)
+    flat = []
+    for ti, th in enumerate(ths):
+        want = []
+        for j in range(dsc.shape[0]):
+            c_scores = scipy.ndimage.median_filter(dsc[j].T, (7, 1))
+            assert np.array_equal(c_scores, post[j])
+            for lab, on, of in enc.decode_strong(c_scores > th):
+                want.append((j, lab, float(on), float(of)))
+        assert want == preds[th], th
+        flat += [(ti, j, labels10.index(lab), on, of) for j, lab, on, of in want]
+    report["decode"] = ("oracle batched_decode == reference ManyHotEncoder.decode_strong/_frame_to_time on scipy-filtered "
+                        "scores (dcase_util.find_contiguous_regions stubbed by its restatement), %d events" % len(flat))
+    np.savez(os.path.join(OUT, "decode.npz"), scores=dsc, thresholds=np.array(ths, np.float32),
+             events=np.array(flat, np.float64), post=post)
+
     with open(os.path.join(OUT, "PINNING.txt"), "w") as f:
         f.write("oracle pinned against the live reference (commit c6bcb45b) + torchaudio %s, torch %s\n"
                 % (__import__("torchaudio").__version__, torch.__version__))

@@ -179,3 +179,66 @@ def test_mask_spans_follow_torchaudio_iid_semantics(dev):
     assert (out2 != out).any()
     check(lib().sedk_mask_spans(ptr(out2), B, 128, 0, 626, 5, 1234, ptr(ctr), 300, None), "sedk_mask_spans")
     assert (out2[:, :2] == 0).all() and (out2[:, 3] >= out2[:, 2]).all()
+
+
+def test_decode_events_matches_golden(dev):
+    """f1: median filter + thresholds + run-length events on the device == the reference's batched_decode_preds numerics
+    (fixture minted from the live ManyHotEncoder in oracle/make_golden.py): bit-exact frame boundaries, exact seconds."""
+    from desed_task_b200.utils.postprocess import decode_events, frame_to_time, median_filter
+    from oracle import postprocess as opost
+    g = golden("decode")
+    sc = torch.from_numpy(g["scores"]).to(dev)
+    ths = [float(t) for t in g["thresholds"]]
+    filt = median_filter(sc, 7, class_dim=1)
+    assert np.array_equal(filt.transpose(1, 2).cpu().numpy(), g["post"])
+    off, ev = decode_events(filt, ths, class_dim=1)
+    B, C = sc.shape[0], sc.shape[1]
+    got = []
+    for ti in range(len(ths)):
+        for j in range(B):
+            for c in range(C):
+                r = (ti * B + j) * C + c
+                for on, of in ev[off[r]:off[r + 1]]:
+                    got.append((ti, j, c, float(frame_to_time(on)), float(frame_to_time(of))))
+    want = [tuple(float(v) if i > 2 else int(v) for i, v in enumerate(row)) for row in g["events"]]
+    assert got == want and len(got) > 100
+    # ragged clips (pad_indx): the scan stops at each clip's own length; an event still open there ends at that length
+    nf = torch.tensor([156, 100, 1, 0], dtype=torch.int32)
+    off2, ev2 = decode_events(filt, ths[:2], n_frames=nf, class_dim=1)
+    post = g["post"]
+    for ti, th in enumerate(ths[:2]):
+        for j in range(B):
+            for c in range(C):
+                r = (ti * B + j) * C + c
+                ref = opost.find_contiguous_regions(post[j, :int(nf[j]), c] > np.float32(th))
+                assert np.array_equal(ev2[off2[r]:off2[r + 1]].reshape(-1, 2), ref), (ti, j, c)
+    # a capacity that is too small is reported and recovered from
+    off3, ev3 = decode_events(filt, ths, class_dim=1, capacity=8)
+    assert np.array_equal(off3, off) and np.array_equal(ev3, ev)
+    # time-major layout [B, T, C] gives the same events
+    off4, ev4 = decode_events(filt.transpose(1, 2).contiguous(), ths, class_dim=2)
+    assert np.array_equal(off4, off) and np.array_equal(ev4, ev)
+
+
+def test_batched_decode_preds_mirror(dev):
+    """Same arguments / return triple as recipes/dcase2023_task4_baseline/local/utils.py:16-73."""
+    from desed_task_b200.utils.postprocess import batched_decode_preds
+    from oracle import postprocess as opost
+    g = golden("decode")
+    sc = torch.from_numpy(g["scores"]).to(dev)
+
+    class Enc:                      # the two members of ManyHotEncoder the function touches
+        labels = ["c%d" % i for i in range(10)]
+
+        def _frame_to_time(self, f):
+            return opost.frame_to_time(f)
+    names = ["/x/clip%d.wav" % i for i in range(sc.shape[0])]
+    raw, post, dfs = batched_decode_preds(sc, names, Enc(), thresholds=[0.5, 0.7], median_filter=7)
+    assert sorted(raw) == ["clip0", "clip1", "clip2", "clip3"] and list(raw["clip0"].columns[:2]) == ["onset", "offset"]
+    assert np.allclose(post["clip1"][Enc.labels].to_numpy(), g["post"][1])
+    _, want = opost.batched_decode(g["scores"], Enc.labels, [0.5, 0.7], 7)
+    for th in (0.5, 0.7):
+        df = dfs[th]
+        assert list(df.columns) == ["event_label", "onset", "offset", "filename"]
+        rows = [(int(f[4:-4]), l, on, of) for l, on, of, f in df.itertuples(index=False)]
+        assert rows == want[th]

