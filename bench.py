@@ -32,6 +32,17 @@ sys.path.insert(0, ROOT)
 # stdout carries exactly one JSON line: NCCL's own banner / debug output ("NCCL version ...") goes to stderr
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
+# ... and so does everything else a library may print (PyTorch's own "NCCL version" banner goes to stdout): fd 1 is pointed
+# at stderr for the whole run and the JSON line is written to the saved descriptor at the end
+_STDOUT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_STDOUT_FD, (line + "\n").encode())
+
+
 import torch  # noqa: E402
 
 L_SAMPLES = 160000
@@ -497,10 +508,14 @@ def run_ours(args):
         }
         if lib_bar and isinstance(lib_bar.get("best"), (int, float)) and lib_bar["best"] > 0:
             out["vs_gpu_library"] = round(value / lib_bar["best"], 2)
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # no collective teardown: every rank leaves as soon as its own work is done (rank 0's profiling pass above is local);
+        # destroying a process group whose collectives were captured into CUDA graphs was seen to hang
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return out
 
 
@@ -624,7 +639,7 @@ def run_reference(args):
     v = round(B * args.steps / dt, 2)
     what = ("the reference's unmodified modules (baseline/_ref: desed_task.nnet.CRNN, data_augm, TorchScaler; torchaudio "
             "front end; torch.optim.Adam)" if kind == "reference" else "oracle port of the reference's torch/torchaudio path")
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": W, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -48,6 +48,7 @@ class GruLayer(C.Structure):
 class CrnnPlan(C.Structure):
     _fields_ = [("B", C.c_int32), ("n_mels", C.c_int32), ("n_frames", C.c_int32), ("n_conv", C.c_int32),
                 ("n_gru", C.c_int32), ("nclass", C.c_int32), ("training", C.c_int32), ("precision", C.c_int32),
+                ("bn_eval", C.c_int32), ("activation", C.c_int32),
                 ("dropout_p", f32), ("bn_eps", f32), ("bn_momentum", f32), ("seed", u64), ("seed_dev", vp),
                 ("x", vp), ("x_sb", i64), ("x_sm", i64), ("x_st", i64), ("minmax", vp), ("scaler_eps", f32),
                 ("specaug", vp), ("x0", vp),
@@ -92,6 +93,7 @@ _SIGS = {
     "sedk_decode_events": (i32, [vp, i32, i32, i32, i64, i64, i64, vp, i32, vp, vp, vp, i32, vp]),
     "sedk_crnn_forward": (i32, [C.POINTER(CrnnPlan), vp]),
     "sedk_crnn_backward": (i32, [C.POINTER(CrnnPlan), vp]),
+    "sedk_crnn_backward_phase": (i32, [C.POINTER(CrnnPlan), i32, vp]),
     "sedk_sed_loss": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp]),
     "sedk_sed_loss_dev": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
     "sedk_sed_loss_ex": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp]),

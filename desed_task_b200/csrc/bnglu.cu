@@ -98,7 +98,8 @@ template <int C, bool X3>
 __global__ void __launch_bounds__(256)
 bnglu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, const float* __restrict__ glu_w,
                  const float* __restrict__ glu_b, float* __restrict__ out, TileGeom gm, uint32_t thresh, float inv_keep,
-                 uint64_t seed, const uint64_t* __restrict__ seed_dev, uint64_t dstream, int total_tiles) {
+                 uint64_t seed, const uint64_t* __restrict__ seed_dev, uint64_t dstream, int total_tiles, int act) {
+    // act (CNN.py:81-88): 0 GLU (Wy + b) * sigmoid(y); 1 ContextGating y * sigmoid(Wy + b); 2 ReLU; 3 LeakyReLU(0.2)
     using Cfg = GluCfg<C>;
     constexpr int YS = Cfg::YS, WN = Cfg::WN, MF = Cfg::MF, NF = Cfg::NF;
     extern __shared__ float smem[];
@@ -109,12 +110,13 @@ bnglu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
     const int wm0 = (warp / WN) * (MF * 16), wn0 = (warp % WN) * (NF * 8);
     for (int idx = tid; idx < C * (C / 4); idx += 256) {
         int n = idx / (C / 4), q = idx - n * (C / 4);
-        *reinterpret_cast<float4*>(W + n * YS + q * 4) = *reinterpret_cast<const float4*>(glu_w + n * C + q * 4);
+        *reinterpret_cast<float4*>(W + n * YS + q * 4) =
+            glu_w != nullptr ? *reinterpret_cast<const float4*>(glu_w + n * C + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int i = tid; i < C; i += 256) {
         vec[i] = bn[i];
         vec[C + i] = bn[C + i];
-        vec[2 * C + i] = glu_b[i];
+        vec[2 * C + i] = glu_b != nullptr ? glu_b[i] : 0.f;
     }
     const Philox ph(seed + (seed_dev ? *seed_dev : 0ull));
     const float inv_pool = 1.0f / (float)(gm.pt * gm.pf);
@@ -172,8 +174,19 @@ bnglu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
                 for (int j = 0; j < NF; j++) {
                     const int n = wn0 + j * 8 + 2 * t4;
                     float2 y = *reinterpret_cast<float2*>(Y + m * YS + n);
-                    float a0 = (acc[i][j][2 * rr] + vec[2 * C + n]) * fast_sigmoidf_(y.x);
-                    float a1 = (acc[i][j][2 * rr + 1] + vec[2 * C + n + 1]) * fast_sigmoidf_(y.y);
+                    const float l0 = acc[i][j][2 * rr] + vec[2 * C + n], l1 = acc[i][j][2 * rr + 1] + vec[2 * C + n + 1];
+                    float a0, a1;
+                    if (act == 0) {
+                        a0 = l0 * fast_sigmoidf_(y.x);
+                        a1 = l1 * fast_sigmoidf_(y.y);
+                    } else if (act == 1) {
+                        a0 = y.x * fast_sigmoidf_(l0);
+                        a1 = y.y * fast_sigmoidf_(l1);
+                    } else {
+                        const float slope = act == 2 ? 0.f : 0.2f;
+                        a0 = y.x > 0.f ? y.x : slope * y.x;
+                        a1 = y.y > 0.f ? y.y : slope * y.y;
+                    }
                     if (thresh != 0u) {
                         if ((j & 1) == 0) rnd = philox_frag_pair(ph, pix, C / 16, (wn0 >> 4) + (j >> 1), t4, dstream);
                         const bool k0 = ((j & 1) ? rnd.z : rnd.x) >= thresh, k1 = ((j & 1) ? rnd.w : rnd.y) >= thresh;
@@ -214,7 +227,7 @@ bnglu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
                  const float* __restrict__ glu_b, const float* __restrict__ gout, float* __restrict__ gy,
                  float* __restrict__ gglu_w, float* __restrict__ gglu_b, double* __restrict__ stats, TileGeom gm,
                  uint32_t thresh, float inv_keep, uint64_t seed, const uint64_t* __restrict__ seed_dev, uint64_t dstream,
-                 int total_tiles) {
+                 int total_tiles, int act) {
     using Cfg = GluCfg<C>;
     constexpr int YS = Cfg::YS, WN = Cfg::WN, MF = Cfg::MF, NF = Cfg::NF;
     constexpr int DWM = Cfg::DWM, DWN = Cfg::DWN, DWK = Cfg::DWK, DMF = Cfg::DMF, DNF = Cfg::DNF;
@@ -230,12 +243,13 @@ bnglu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
     const int dk = warp / (DWM * DWN), dm0 = ((warp / DWN) % DWM) * (DMF * 16), dn0 = (warp % DWN) * (DNF * 8);
     for (int idx = tid; idx < C * (C / 4); idx += 256) {
         int n = idx / (C / 4), q = idx - n * (C / 4);
-        *reinterpret_cast<float4*>(W + n * YS + q * 4) = *reinterpret_cast<const float4*>(glu_w + n * C + q * 4);
+        *reinterpret_cast<float4*>(W + n * YS + q * 4) =
+            glu_w != nullptr ? *reinterpret_cast<const float4*>(glu_w + n * C + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int i = tid; i < C; i += 256) {
         vec[i] = bn[i];
         vec[C + i] = bn[C + i];
-        vec[2 * C + i] = glu_b[i];
+        vec[2 * C + i] = glu_b != nullptr ? glu_b[i] : 0.f;
         vec[3 * C + i] = bn[2 * C + i];
         vec[4 * C + i] = bn[3 * C + i];
         red[i] = red[C + i] = red[2 * C + i] = 0.f;
@@ -322,12 +336,24 @@ bnglu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
                         }
                     }
                     float2 y = *reinterpret_cast<float2*>(Y + m * YS + n);
-                    float s0 = fast_sigmoidf_(y.x), s1 = fast_sigmoidf_(y.y);
                     float l0 = acc[i][j][2 * rr] + vec[2 * C + n], l1 = acc[i][j][2 * rr + 1] + vec[2 * C + n + 1];
-                    float gl0 = ga0 * s0, gl1 = ga1 * s1;
+                    float gl0, gl1, e0, e1;         // gradient wrt the gate pre-activation / element-wise part of g_y
+                    if (act == 0) {                 // out = l * sigmoid(y)
+                        const float s0 = fast_sigmoidf_(y.x), s1 = fast_sigmoidf_(y.y);
+                        gl0 = ga0 * s0; gl1 = ga1 * s1;
+                        e0 = ga0 * l0 * s0 * (1.0f - s0); e1 = ga1 * l1 * s1 * (1.0f - s1);
+                    } else if (act == 1) {          // out = y * sigmoid(l)
+                        const float s0 = fast_sigmoidf_(l0), s1 = fast_sigmoidf_(l1);
+                        gl0 = ga0 * y.x * s0 * (1.0f - s0); gl1 = ga1 * y.y * s1 * (1.0f - s1);
+                        e0 = ga0 * s0; e1 = ga1 * s1;
+                    } else {                        // (leaky) ReLU: no gate
+                        const float slope = act == 2 ? 0.f : 0.2f;
+                        gl0 = gl1 = 0.f;
+                        e0 = y.x > 0.f ? ga0 : slope * ga0; e1 = y.y > 0.f ? ga1 : slope * ga1;
+                    }
                     *reinterpret_cast<float2*>(G + m * YS + n) = make_float2(gl0, gl1);
-                    acc[i][j][2 * rr] = ga0 * l0 * s0 * (1.0f - s0);
-                    acc[i][j][2 * rr + 1] = ga1 * l1 * s1 * (1.0f - s1);
+                    acc[i][j][2 * rr] = e0;
+                    acc[i][j][2 * rr + 1] = e1;
                     cs[j][0] += gl0;
                     cs[j][1] += gl1;
                 }
@@ -399,6 +425,7 @@ bnglu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
         __syncthreads();
     }
     // ---- flush the persistent accumulators
+    if (gglu_w != nullptr)
 #pragma unroll
     for (int i = 0; i < DMF; i++)
 #pragma unroll
@@ -413,7 +440,7 @@ bnglu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
     for (int i = tid; i < C; i += 256) {
         atomicAdd(&stats[2 * C + i], (double)red[i]);
         atomicAdd(&stats[3 * C + i], (double)red[C + i]);
-        atomicAdd(&gglu_b[i], red[2 * C + i]);
+        if (gglu_b != nullptr) atomicAdd(&gglu_b[i], red[2 * C + i]);
     }
 }
 
@@ -421,19 +448,21 @@ bnglu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, cons
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(float* __restrict__ gy, const float* __restrict__ z, const float* __restrict__ bn,
                     const double* __restrict__ stats, float* __restrict__ ggamma, float* __restrict__ gbeta,
-                    float* __restrict__ gb, float inv_count, int64_t n4, int C) {
+                    float* __restrict__ gb, float inv_count, int64_t n4, int C, int frozen) {
     extern __shared__ float sv[];    // scale, mean, invstd, m1, m2
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         sv[c] = bn[c];
         sv[C + c] = bn[2 * C + c];
         sv[2 * C + c] = bn[3 * C + c];
         double s1 = stats[2 * C + c], s2 = stats[3 * C + c];
-        sv[3 * C + c] = (float)(s1 * (double)inv_count);
-        sv[4 * C + c] = (float)(s2 * (double)inv_count);
+        // running-statistics (frozen / eval) BatchNorm is a fixed affine map: no mean terms in its backward
+        sv[3 * C + c] = frozen ? 0.f : (float)(s1 * (double)inv_count);
+        sv[4 * C + c] = frozen ? 0.f : (float)(s2 * (double)inv_count);
         if (blockIdx.x == 0) {
             gbeta[c] = (float)s1;
             ggamma[c] = (float)s2;
-            if (gb != nullptr) gb[c] = 0.f;     // the conv bias cancels inside a batch-statistics BatchNorm
+            // the conv bias cancels inside a batch-statistics BatchNorm; through a frozen one it sees scale * sum gy
+            if (gb != nullptr) gb[c] = frozen ? bn[c] * (float)s1 : 0.f;
         }
     }
     __syncthreads();
@@ -479,7 +508,7 @@ inline int geom_ok(const TileGeom& g) {
 
 template <int C>
 int run_fwd(const float* z, const float* bn, const float* glu_w, const float* glu_b, float* out, int B, TileGeom gm,
-            float p, uint64_t seed, const uint64_t* seed_dev, uint64_t dstream, int precision, cudaStream_t s) {
+            float p, uint64_t seed, const uint64_t* seed_dev, uint64_t dstream, int precision, int act, cudaStream_t s) {
     using Cfg = GluCfg<C>;
     const int tiles = B * gm.nTt * gm.nTf;
     const uint32_t thresh = p > 0.f ? drop_threshold(p) : 0u;
@@ -498,8 +527,8 @@ int run_fwd(const float* z, const float* bn, const float* glu_w, const float* gl
     }
     int grid = num_sms() * occ[pi];
     if (grid > tiles) grid = tiles;
-    if (precision) k1<<<grid, 256, Cfg::SMEM_FWD, s>>>(z, bn, glu_w, glu_b, out, gm, thresh, inv_keep, seed, seed_dev, dstream, tiles);
-    else k0<<<grid, 256, Cfg::SMEM_FWD, s>>>(z, bn, glu_w, glu_b, out, gm, thresh, inv_keep, seed, seed_dev, dstream, tiles);
+    if (precision) k1<<<grid, 256, Cfg::SMEM_FWD, s>>>(z, bn, glu_w, glu_b, out, gm, thresh, inv_keep, seed, seed_dev, dstream, tiles, act);
+    else k0<<<grid, 256, Cfg::SMEM_FWD, s>>>(z, bn, glu_w, glu_b, out, gm, thresh, inv_keep, seed, seed_dev, dstream, tiles, act);
     SEDK_LAUNCH_CHECK("bnglu_fwd_kernel");
     return SEDK_OK;
 }
@@ -507,7 +536,7 @@ int run_fwd(const float* z, const float* bn, const float* glu_w, const float* gl
 template <int C>
 int run_bwd(const float* z, const float* bn, const float* glu_w, const float* glu_b, const float* gout, float* gy,
             float* gglu_w, float* gglu_b, double* stats, int B, TileGeom gm, float p, uint64_t seed, const uint64_t* seed_dev,
-            uint64_t dstream, int precision, cudaStream_t s) {
+            uint64_t dstream, int precision, int act, cudaStream_t s) {
     using Cfg = GluCfg<C>;
     const int tiles = B * gm.nTt * gm.nTf;
     const uint32_t thresh = p > 0.f ? drop_threshold(p) : 0u;
@@ -528,10 +557,10 @@ int run_bwd(const float* z, const float* bn, const float* glu_w, const float* gl
     if (grid > tiles) grid = tiles;
     if (precision)
         k1<<<grid, 256, Cfg::SMEM_BWD, s>>>(z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, gm, thresh, inv_keep, seed,
-                                            seed_dev, dstream, tiles);
+                                            seed_dev, dstream, tiles, act);
     else
         k0<<<grid, 256, Cfg::SMEM_BWD, s>>>(z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, gm, thresh, inv_keep, seed,
-                                            seed_dev, dstream, tiles);
+                                            seed_dev, dstream, tiles, act);
     SEDK_LAUNCH_CHECK("bnglu_bwd_kernel");
     return SEDK_OK;
 }
@@ -550,20 +579,22 @@ int launch_bn_finalize(const double* stats, const float* gamma, const float* bet
 
 int launch_bnglu_pool_fwd(const float* z, const float* bn, const float* glu_w, const float* glu_b, float* out, int B,
                           int T, int F, int C, int pt, int pf, float drop_p, uint64_t seed, const uint64_t* seed_dev,
-                          uint64_t drop_stream, int precision, cudaStream_t s) {
+                          uint64_t drop_stream, int precision, int act, cudaStream_t s) {
     char pname[64];
     snprintf(pname, sizeof(pname), "bnglu_pool_fwd_c%d", C);
     SEDK_PROF(pname, s);
-    if (bnglu_small_supports(B, T, F, C, pt, pf))
+    SEDK_REQUIRE(act >= 0 && act <= 3, "bnglu_pool: unknown activation %d", act);
+    SEDK_REQUIRE(act >= 2 || (glu_w != nullptr && glu_b != nullptr), "bnglu_pool: gate parameters missing");
+    if (act == 0 && bnglu_small_supports(B, T, F, C, pt, pf))
         return launch_bnglu_small_fwd(z, bn, glu_w, glu_b, out, B, T, F, C, pt, pf, drop_p, seed, seed_dev, drop_stream,
                                       precision, s);
     TileGeom gm = make_geom(T, F, pt, pf);
     SEDK_REQUIRE(geom_ok(gm), "bnglu_pool: pooling (%d,%d) on a %dx%d map is not supported", pt, pf, T, F);
     switch (C) {
-        case 16: return run_fwd<16>(z, bn, glu_w, glu_b, out, B, gm, drop_p, seed, seed_dev, drop_stream, precision, s);
-        case 32: return run_fwd<32>(z, bn, glu_w, glu_b, out, B, gm, drop_p, seed, seed_dev, drop_stream, precision, s);
-        case 64: return run_fwd<64>(z, bn, glu_w, glu_b, out, B, gm, drop_p, seed, seed_dev, drop_stream, precision, s);
-        case 128: return run_fwd<128>(z, bn, glu_w, glu_b, out, B, gm, drop_p, seed, seed_dev, drop_stream, precision, s);
+        case 16: return run_fwd<16>(z, bn, glu_w, glu_b, out, B, gm, drop_p, seed, seed_dev, drop_stream, precision, act, s);
+        case 32: return run_fwd<32>(z, bn, glu_w, glu_b, out, B, gm, drop_p, seed, seed_dev, drop_stream, precision, act, s);
+        case 64: return run_fwd<64>(z, bn, glu_w, glu_b, out, B, gm, drop_p, seed, seed_dev, drop_stream, precision, act, s);
+        case 128: return run_fwd<128>(z, bn, glu_w, glu_b, out, B, gm, drop_p, seed, seed_dev, drop_stream, precision, act, s);
     }
     SEDK_UNSUPPORTED("bnglu_pool: channel width %d not in {16,32,64,128}", C);
 }
@@ -571,27 +602,27 @@ int launch_bnglu_pool_fwd(const float* z, const float* bn, const float* glu_w, c
 int launch_bnglu_pool_bwd(const float* z, const float* bn, const float* glu_w, const float* glu_b, const float* gout,
                           float* gy, float* gglu_w, float* gglu_b, double* stats, int B, int T, int F, int C, int pt,
                           int pf, float drop_p, uint64_t seed, const uint64_t* seed_dev, uint64_t drop_stream, int precision,
-                          cudaStream_t s) {
+                          int act, cudaStream_t s) {
     char pname[64];
     snprintf(pname, sizeof(pname), "bnglu_pool_bwd_c%d", C);
     SEDK_PROF(pname, s);
     TileGeom gm = make_geom(T, F, pt, pf);
     SEDK_REQUIRE(geom_ok(gm), "bnglu_pool: pooling (%d,%d) on a %dx%d map is not supported", pt, pf, T, F);
     if (gm.Te != T || gm.Fe != F) SEDK_CUDA(cudaMemsetAsync(gy, 0, (size_t)B * T * F * C * sizeof(float), s));
-    if (bnglu_small_supports(B, T, F, C, pt, pf))
+    if (act == 0 && bnglu_small_supports(B, T, F, C, pt, pf))
         return launch_bnglu_small_bwd(z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, B, T, F, C, pt, pf, drop_p, seed,
                                       seed_dev, drop_stream, precision, s);
     switch (C) {
-        case 16: return run_bwd<16>(z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, B, gm, drop_p, seed, seed_dev, drop_stream, precision, s);
-        case 32: return run_bwd<32>(z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, B, gm, drop_p, seed, seed_dev, drop_stream, precision, s);
-        case 64: return run_bwd<64>(z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, B, gm, drop_p, seed, seed_dev, drop_stream, precision, s);
-        case 128: return run_bwd<128>(z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, B, gm, drop_p, seed, seed_dev, drop_stream, precision, s);
+        case 16: return run_bwd<16>(z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, B, gm, drop_p, seed, seed_dev, drop_stream, precision, act, s);
+        case 32: return run_bwd<32>(z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, B, gm, drop_p, seed, seed_dev, drop_stream, precision, act, s);
+        case 64: return run_bwd<64>(z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, B, gm, drop_p, seed, seed_dev, drop_stream, precision, act, s);
+        case 128: return run_bwd<128>(z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, B, gm, drop_p, seed, seed_dev, drop_stream, precision, act, s);
     }
     SEDK_UNSUPPORTED("bnglu_pool: channel width %d not in {16,32,64,128}", C);
 }
 
 int launch_bn_bwd_apply(float* gy, const float* z, const float* bn, const double* stats, float* ggamma, float* gbeta,
-                        float* gb, double count, int64_t n_pix, int C, cudaStream_t s) {
+                        float* gb, double count, int64_t n_pix, int C, int frozen, cudaStream_t s) {
     char pname[64];
     snprintf(pname, sizeof(pname), "bn_bwd_apply_c%d", C);
     SEDK_PROF(pname, s);
@@ -602,7 +633,7 @@ int launch_bn_bwd_apply(float* gy, const float* z, const float* bn, const double
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     bn_bwd_apply_kernel<<<(int)blocks, 256, 5 * C * sizeof(float), s>>>(gy, z, bn, stats, ggamma, gbeta, gb,
-                                                                       (float)(1.0 / count), n4, C);
+                                                                       (float)(1.0 / count), n4, C, frozen);
     SEDK_LAUNCH_CHECK("bn_bwd_apply_kernel");
     return SEDK_OK;
 }

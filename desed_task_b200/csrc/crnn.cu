@@ -71,7 +71,7 @@ struct Fork {
 // the tcgen05 BN+GLU path needs its two workspaces and covers C = 128, pooling (1, 2), TF32 mode; the backward of a layer
 // must take the same path as its forward (different dropout-mask mapping, lin saved), so both sides ask this one function
 bool use_glu_tc5(const sedk_crnn_plan* p, const sedk_conv_layer& L) {
-    return L.glu_pack != nullptr && L.lin != nullptr && bnglu_tc5_supports(L.T, L.F, L.cout, L.pt, L.pf, p->precision);
+    return p->activation == 0 && L.glu_pack != nullptr && L.lin != nullptr && bnglu_tc5_supports(L.T, L.F, L.cout, L.pt, L.pf, p->precision);
 }
 
 template <class... P>
@@ -83,13 +83,15 @@ int validate(const sedk_crnn_plan* p, bool backward) {
     SEDK_REQUIRE(p != nullptr, "crnn: null plan");
     SEDK_REQUIRE(p->B > 0 && p->n_conv >= 1 && p->n_conv <= SEDK_MAX_CONV, "crnn: bad B / n_conv");
     SEDK_REQUIRE(p->n_gru >= 1 && p->n_gru <= SEDK_MAX_GRU_LAYERS, "crnn: bad n_gru");
+    SEDK_REQUIRE(p->activation >= 0 && p->activation <= 3, "crnn: unknown activation %d", p->activation);
     SEDK_REQUIRE(p->x && p->strong && p->weak && p->sof && p->hsum, "crnn: missing input / output buffers");
     SEDK_REQUIRE(p->conv[0].cin == 1, "crnn: the first conv layer must have one input channel (n_in_channel=1)");
     SEDK_REQUIRE(p->conv[0].T == p->n_frames && p->conv[0].F == p->n_mels, "crnn: layer-0 geometry mismatch");
     for (int i = 0; i < p->n_conv; i++) {
         const sedk_conv_layer& L = p->conv[i];
-        SEDK_REQUIRE(L.w && L.b && L.gamma && L.beta && L.running_mean && L.running_var && L.glu_w && L.glu_b,
+        SEDK_REQUIRE(L.w && L.b && L.gamma && L.beta && L.running_mean && L.running_var,
                      "crnn: conv layer %d has null parameters", i);
+        SEDK_REQUIRE(p->activation >= 2 || (L.glu_w && L.glu_b), "crnn: conv layer %d has no gate parameters", i);
         SEDK_REQUIRE(L.z && L.out && L.stats && L.bn, "crnn: conv layer %d has null workspace", i);
         if (i > 0) {
             SEDK_REQUIRE(L.wpack, "crnn: conv layer %d needs wpack", i);
@@ -98,8 +100,9 @@ int validate(const sedk_crnn_plan* p, bool backward) {
                          "crnn: conv layer %d geometry does not chain", i);
         }
         if (backward) {
-            SEDK_REQUIRE(L.gw && L.gb && L.ggamma && L.gbeta && L.gglu_w && L.gglu_b && L.gy && L.gout,
+            SEDK_REQUIRE(L.gw && L.gb && L.ggamma && L.gbeta && L.gy && L.gout,
                          "crnn: conv layer %d has null gradient buffers", i);
+            SEDK_REQUIRE(p->activation >= 2 || (L.gglu_w && L.gglu_b), "crnn: conv layer %d has no gate gradient buffers", i);
             SEDK_REQUIRE(i == 0 || L.gwpack, "crnn: conv layer %d needs gwpack", i);
         }
     }
@@ -125,6 +128,8 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const int B = p->B;
     const float pdrop = p->training ? p->dropout_p : 0.f;
+    // batch statistics only in a training forward whose BatchNorm is not frozen (freeze_bn / eval-mode autograd)
+    const int bn_train = (p->training && !p->bn_eval) ? 1 : 0;
     const bool zf = p->zero_fwd != nullptr && p->zero_fwd_bytes > 0;
     if (zf && p->training) SEDK_CUDA(cudaMemsetAsync(p->zero_fwd, 0, (size_t)p->zero_fwd_bytes, s));
     // ---------------- weight packs of every layer: off the chain, overlapped with the first conv
@@ -147,7 +152,7 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
         const sedk_conv_layer& L = p->conv[i];
         const int C = L.cout;
         if (p->training && !zf) SEDK_CUDA(cudaMemsetAsync(L.stats, 0, 4 * C * sizeof(double), s));
-        double* st = p->training ? L.stats : nullptr;
+        double* st = bn_train ? L.stats : nullptr;
         if (i == 0) {
             rc = launch_conv0_fwd(p->x, p->x_sb, p->x_sm, p->x_st, p->minmax, p->scaler_eps,
                                   p->training ? p->specaug : nullptr, L.w, L.b, p->training ? p->x0 : nullptr, L.z, st, B,
@@ -162,7 +167,7 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
         if (rc) return rc;
         if (use_glu_tc5(p, L)) {
             rc = launch_glu_prep(L.stats, L.gamma, L.beta, L.running_mean, L.running_var, L.num_batches, L.bn, L.glu_w,
-                                 L.glu_b, L.glu_pack, (double)B * L.T * L.F, p->bn_eps, p->bn_momentum, p->training, C, s);
+                                 L.glu_b, L.glu_pack, (double)B * L.T * L.F, p->bn_eps, p->bn_momentum, bn_train, C, s);
             if (rc) return rc;
             rc = launch_bnglu_tc5_fwd(L.z, L.bn, L.glu_pack, L.out, p->training ? L.lin : nullptr, B, L.T, L.F, C, L.pt, L.pf,
                                       pdrop, p->seed, p->seed_dev, (uint64_t)i, s);
@@ -170,10 +175,10 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
             continue;
         }
         rc = launch_bn_finalize(L.stats, L.gamma, L.beta, L.running_mean, L.running_var, L.num_batches, L.bn,
-                                (double)B * L.T * L.F, p->bn_eps, p->bn_momentum, p->training, C, s);
+                                (double)B * L.T * L.F, p->bn_eps, p->bn_momentum, bn_train, C, s);
         if (rc) return rc;
         rc = launch_bnglu_pool_fwd(L.z, L.bn, L.glu_w, L.glu_b, L.out, B, L.T, L.F, C, L.pt, L.pf, pdrop, p->seed,
-                                   p->seed_dev, (uint64_t)i, p->precision, s);
+                                   p->seed_dev, (uint64_t)i, p->precision, p->activation, s);
         if (rc) return rc;
     }
     const sedk_conv_layer& last = p->conv[p->n_conv - 1];
@@ -230,7 +235,10 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
                             p->sof, p->hsum, B, Tp, in_dim, p->nclass, s);
 }
 
-extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
+// phases: 1 = heads + BiGRU (+ embedding fusion), 2 = CNN, 3 = both.  Each phase joins its own side-stream work before it
+// returns, so after phase 1 every RNN / head / fusion gradient is final (a data-parallel caller can start reducing that
+// part of the flat gradient while phase 2 runs).
+static int crnn_backward_impl(const sedk_crnn_plan* p, int phases, void* stream) {
     int rc = validate(p, true);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
@@ -246,7 +254,8 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
     // zb: every gradient buffer was cleared by one memset; zs: the backward halves of `stats` were cleared by the forward
     const bool zb = p->zero_bwd != nullptr && p->zero_bwd_bytes > 0;
     const bool zs = p->zero_fwd != nullptr && p->zero_fwd_bytes > 0;
-    if (zb) SEDK_CUDA(cudaMemsetAsync(p->zero_bwd, 0, (size_t)p->zero_bwd_bytes, s));
+    if (zb && (phases & 1)) SEDK_CUDA(cudaMemsetAsync(p->zero_bwd, 0, (size_t)p->zero_bwd_bytes, s));
+    if (phases & 1) {
     // ---------------- heads
     if (!zb) {
         SEDK_CUDA(cudaMemsetAsync(p->gdense_w, 0, (size_t)C * D * sizeof(float), s));
@@ -332,13 +341,17 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
                                    s);
         if (rc) return rc;
     }
+    }  // phase 1
+    // split mode: the RNN-side weight-gradient GEMMs (side stream) must be complete when phase 1 returns; in the one-call
+    // mode they keep overlapping the CNN backward and are joined at the very end
+    if (!(phases & 2)) return fk.join();
     // ---------------- CNN
     for (int i = p->n_conv - 1; i >= 0; i--) {
         const sedk_conv_layer& L = p->conv[i];
         const int Cc = L.cout;
         const int64_t npix = (int64_t)B * L.T * L.F;
         if (!zs) SEDK_CUDA(cudaMemsetAsync(L.stats + 2 * Cc, 0, 2 * Cc * sizeof(double), s));
-        if (!zb) SEDK_CUDA(cudaMemsetAsync(L.gglu_b, 0, (size_t)Cc * sizeof(float), s));
+        if (!zb && L.gglu_b) SEDK_CUDA(cudaMemsetAsync(L.gglu_b, 0, (size_t)Cc * sizeof(float), s));
         if (use_glu_tc5(p, L)) {
             rc = launch_bnglu_tc5_bwd(L.z, L.bn, L.glu_pack, L.gout, L.lin, L.gy, L.gglu_b, L.stats, B, L.T, L.F, Cc, L.pt,
                                       L.pf, pdrop, p->seed, p->seed_dev, (uint64_t)i, s);
@@ -350,12 +363,13 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
             rc = launch_glu_wgrad_tc5(L.z, L.lin, L.bn, L.glu_pack, L.gglu_w, L.gglu_b, B, L.T, L.F, Cc, fk.side_s);
             if (rc) return rc;
         } else {
-        if (!zb) SEDK_CUDA(cudaMemsetAsync(L.gglu_w, 0, (size_t)Cc * Cc * sizeof(float), s));
+        if (!zb && L.gglu_w) SEDK_CUDA(cudaMemsetAsync(L.gglu_w, 0, (size_t)Cc * Cc * sizeof(float), s));
         rc = launch_bnglu_pool_bwd(L.z, L.bn, L.glu_w, L.glu_b, L.gout, L.gy, L.gglu_w, L.gglu_b, L.stats, B, L.T, L.F, Cc,
-                                   L.pt, L.pf, pdrop, p->seed, p->seed_dev, (uint64_t)i, p->precision, s);
+                                   L.pt, L.pf, pdrop, p->seed, p->seed_dev, (uint64_t)i, p->precision, p->activation, s);
         if (rc) return rc;
         }
-        rc = launch_bn_bwd_apply(L.gy, L.z, L.bn, L.stats, L.ggamma, L.gbeta, L.gb, (double)npix, npix, Cc, s);
+        rc = launch_bn_bwd_apply(L.gy, L.z, L.bn, L.stats, L.ggamma, L.gbeta, L.gb, (double)npix, npix, Cc,
+                                 p->bn_eval ? 1 : 0, s);
         if (rc) return rc;
         if (i > 0) {
             const sedk_conv_layer& P = p->conv[i - 1];
@@ -376,4 +390,14 @@ extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) {
         }
     }
     return fk.join();
+}
+
+extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) { return crnn_backward_impl(p, 3, stream); }
+
+extern "C" int sedk_crnn_backward_phase(const sedk_crnn_plan* p, int phases, void* stream) {
+    if (phases < 1 || phases > 3) {
+        sedk::set_error("sedk_crnn_backward_phase: phases must be 1, 2 or 3 (got %d)", phases);
+        return SEDK_ERR_INVALID;
+    }
+    return crnn_backward_impl(p, phases, stream);
 }

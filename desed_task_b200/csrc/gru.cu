@@ -761,6 +761,7 @@ int launch_gru_seq_fwd(const float* const gi[2], const float* const w_hh[2], con
         }
     }
     if (H == 64) return run_fwd<64, 1, 2>(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
+    if (H == 192 && get_option("gru_v3", 1)) return launch_gru_fwd_c3(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
     if (H == 192) {
         switch (pick_nb(B, 3)) {
             case 1: return run_fwd<192, 3, 1>(gi, w_hh, b_hh, out, gates, hprev, B, T, save, s);
@@ -789,6 +790,8 @@ int launch_gru_seq_bwd(const float* gout, const float* const w_hh[2], const floa
         }
     }
     if (H == 64) return run_bwd<64, 1, 2>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, zeroed, s);
+    if (H == 192 && get_option("gru_v3", 1))
+        return launch_gru_bwd_c3(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, zeroed, s);
     if (H == 192) {
         switch (pick_nb(B, 3)) {
             case 1: return run_bwd<192, 3, 1>(gout, w_hh, gates, hprev, dgi, dghn, gb_ih, gb_hh, B, T, zeroed, s);

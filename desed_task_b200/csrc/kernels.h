@@ -53,16 +53,17 @@ int launch_conv_wgrad(const float* x, const float* gz, float* gwpack, int B, int
 int launch_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
                        float* running_var, int64_t* num_batches, float* bn, double count, float eps, float momentum,
                        int training, int C, cudaStream_t s);
-// out = avgpool( dropout( (Wg y + bg) * sigmoid(y) ) ),  y = scale*z + shift
+// out = avgpool( dropout( act(y) ) ),  y = scale*z + shift;  act (CNN.py:81-88): 0 GLU (Wg y + bg) * sigmoid(y),
+// 1 ContextGating y * sigmoid(Wg y + bg), 2 ReLU, 3 LeakyReLU(0.2) (glu_w / glu_b / their gradients NULL for 2, 3)
 int launch_bnglu_pool_fwd(const float* z, const float* bn, const float* glu_w, const float* glu_b, float* out, int B,
                           int T, int F, int C, int pt, int pf, float drop_p, uint64_t seed, const uint64_t* seed_dev,
-                          uint64_t drop_stream, int precision, cudaStream_t s);
+                          uint64_t drop_stream, int precision, int act, cudaStream_t s);
 // backward of the block above: writes gy (grad wrt y = BN output) for every pooled pixel, accumulates gglu_w, gglu_b
 // and stats[2C..4C) = {sum gy, sum gy*zhat}.  gy must be pre-zeroed when the pooling drops rows/cols.
 int launch_bnglu_pool_bwd(const float* z, const float* bn, const float* glu_w, const float* glu_b, const float* gout,
                           float* gy, float* gglu_w, float* gglu_b, double* stats, int B, int T, int F, int C, int pt,
                           int pf, float drop_p, uint64_t seed, const uint64_t* seed_dev, uint64_t drop_stream, int precision,
-                          cudaStream_t s);
+                          int act, cudaStream_t s);
 // bnglu_small.cu: register-resident warp-autonomous variants of the two kernels above for C in {16, 32} (pf == 2)
 bool bnglu_small_supports(int B, int T, int F, int C, int pt, int pf);
 int launch_bnglu_small_fwd(const float* z, const float* bn, const float* glu_w, const float* glu_b, float* out, int B,
@@ -87,9 +88,10 @@ int launch_bnglu_tc5_bwd(const float* z, const float* bn, const float* pack, con
                          const uint64_t* seed_dev, uint64_t drop_stream, cudaStream_t s);
 int launch_glu_wgrad_tc5(const float* z, const float* g_lin, const float* bn, float* pack, float* gglu_w, const float* gglu_b,
                          int B, int T, int F, int C, cudaStream_t s);
-// train-mode BN backward: gy -> gz in place; writes ggamma, gbeta (and zero conv-bias grad gb)
+// BN backward: gy -> gz in place; writes ggamma, gbeta and the conv-bias grad gb.  frozen = 0: batch-statistics BatchNorm
+// (gb = 0: the bias cancels); frozen = 1: running-statistics BatchNorm, gz = scale * gy, gb = scale * sum gy
 int launch_bn_bwd_apply(float* gy, const float* z, const float* bn, const double* stats, float* ggamma, float* gbeta,
-                        float* gb, double count, int64_t n_pix, int C, cudaStream_t s);
+                        float* gb, double count, int64_t n_pix, int C, int frozen, cudaStream_t s);
 
 // ---- gemm.cu ------------------------------------------------------------------------------------------------
 int launch_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
@@ -123,6 +125,13 @@ int launch_gru_fwd_v3(const float* const gi[2], const float* const w_hh[2], cons
 int launch_gru_bwd_v3(const float* gout, const float* const w_hh[2], const float* const gates[2],
                       const float* const hprev[2], float* const dgi[2], float* const dghn[2], float* const gb_ih[2],
                       float* const gb_hh[2], int B, int T, int zeroed, int variant, cudaStream_t s);
+
+// H = 192: 3-CTA cluster per (row, direction), h / dgh exchanged through DSMEM, one cluster barrier per step
+int launch_gru_fwd_c3(const float* const gi[2], const float* const w_hh[2], const float* const b_hh[2], float* out,
+                      float* const gates[2], float* const hprev[2], int B, int T, int save, cudaStream_t s);
+int launch_gru_bwd_c3(const float* gout, const float* const w_hh[2], const float* const gates[2],
+                      const float* const hprev[2], float* const dgi[2], float* const dghn[2], float* const gb_ih[2],
+                      float* const gb_hh[2], int B, int T, int zeroed, cudaStream_t s);
 
 // ---- heads.cu -----------------------------------------------------------------------------------------------
 int launch_heads_fwd(const float* x, const float* dw, const float* db, const float* sw, const float* sb,

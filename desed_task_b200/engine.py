@@ -211,11 +211,30 @@ class TrainEngine:
                                  ptr(labels_weak) if n_w > 0 else None, B, self.C, strong.shape[2], n_s, n_w,
                                  self.cons_row0, self.cons_kind, 0.0, ptr(self.cw), ptr(self.losses), ptr(self.gstrong),
                                  ptr(self.gweak), s), "sedk_sed_loss_ex")
-        self.student.backward_direct(ws, self.gstrong, self.gweak)
+        if self.world > 1 and self.graph_optimizer:
+            # data parallel: the RNN / head half of the flat gradient is final after phase 1 - its all-reduce runs on a
+            # side stream (a parallel branch of the graph) underneath the CNN backward; the CNN half follows at the end
+            n_cnn = self.student.cnn_param_count()
+            self.student.backward_direct(ws, self.gstrong, self.gweak, phases=1)
+            cur = torch.cuda.current_stream(self.dev)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.teacher_stream.wait_event(ev)
+            with torch.cuda.stream(self.teacher_stream):
+                ddp.allreduce_sum_(ws.gflat[n_cnn:], self.pg)
+                ev_ar = torch.cuda.Event()
+                ev_ar.record(self.teacher_stream)
+            self.student.backward_direct(ws, self.gstrong, self.gweak, phases=2)
+            ddp.allreduce_sum_(ws.gflat[:n_cnn], self.pg)
+            cur.wait_event(ev_ar)
+            self._reduced = True
+        else:
+            self.student.backward_direct(ws, self.gstrong, self.gweak)
+            self._reduced = False
 
     def _optimizer_part(self):
         ws = self.ws
-        if self.world > 1:
+        if self.world > 1 and not getattr(self, "_reduced", False):
             ddp.allreduce_sum_(ws.gflat, self.pg)
         if self.grad_clip and self.grad_clip > 0:
             # 2024 recipe: gradient_clip 5.0 (pretrained.yaml:17) - norm of the (averaged) gradient, on device

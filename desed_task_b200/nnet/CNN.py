@@ -64,10 +64,20 @@ class CNN(_KernelOnly):
             cnn.add_module("pooling{0}".format(i), nn.AvgPool2d(pooling[i]))
         self.cnn = cnn
 
+    _ACT = {"glu": 0, "cg": 1, "relu": 2, "leakyrelu": 3}
+
+    def activation_code(self):
+        """sedk_crnn_plan.activation (CNN.py:81-88); an unknown name adds no activation module in the reference either."""
+        return self._ACT.get(self.activation.lower(), -1)
+
+    def gate_name(self):
+        a = self.activation.lower()
+        return a if a in ("glu", "cg") else None
+
     def unsupported_reason(self):
         """None if the sm_100a kernels cover this configuration, else a human-readable reason."""
-        if self.activation.lower() != "glu":
-            return "activation=%r (kernels implement the shipped 'glu' gate)" % self.activation
+        if self.activation.lower() not in self._ACT:
+            return "activation=%r (kernels implement 'glu', 'cg', 'relu', 'leakyrelu')" % self.activation
         if self.normalization != "batch":
             return "normalization=%r (kernels implement 'batch')" % self.normalization
         if self.n_in_channel != 1:

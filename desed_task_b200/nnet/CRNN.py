@@ -109,8 +109,10 @@ class _Workspace:
             L.gb = _vp(self.gviews[pre + "conv%d.bias" % i])
             L.ggamma = _vp(self.gviews[pre + "batchnorm%d.weight" % i])
             L.gbeta = _vp(self.gviews[pre + "batchnorm%d.bias" % i])
-            L.gglu_w = _vp(self.gviews[pre + "glu%d.linear.weight" % i])
-            L.gglu_b = _vp(self.gviews[pre + "glu%d.linear.bias" % i])
+            gate = cnn.gate_name()            # "glu" / "cg" (ContextGating) or None for the plain (leaky) ReLU activations
+            if gate is not None:
+                L.gglu_w = _vp(self.gviews[pre + "%s%d.linear.weight" % (gate, i)])
+                L.gglu_b = _vp(self.gviews[pre + "%s%d.linear.bias" % (gate, i)])
             self.conv.append(d)
             T, F, cin = T // pt, F // pf, C
         if F != 1:
@@ -172,7 +174,10 @@ class _Workspace:
             L.running_mean = _vp(sd[pre + "batchnorm%d.running_mean" % i])
             L.running_var = _vp(sd[pre + "batchnorm%d.running_var" % i])
             L.num_batches = _vp(sd[pre + "batchnorm%d.num_batches_tracked" % i])
-            L.glu_w, L.glu_b = _vp(sd[pre + "glu%d.linear.weight" % i]), _vp(sd[pre + "glu%d.linear.bias" % i])
+            gate = model.cnn.gate_name()
+            if gate is not None:
+                L.glu_w = _vp(sd[pre + "%s%d.linear.weight" % (gate, i)])
+                L.glu_b = _vp(sd[pre + "%s%d.linear.bias" % (gate, i)])
         for l in range(plan.n_gru):
             G = plan.gru[l]
             for di, suf in enumerate(("", "_reverse")):
@@ -188,22 +193,6 @@ class _Workspace:
             if p.dtype != torch.float32 or not p.is_contiguous():
                 raise _lib.SedkError("CRNN parameters must be contiguous fp32 tensors")
         self.param_sig = sig
-
-
-class _NoBackward(torch.autograd.Function):
-    """Eval-mode forward with autograd enabled: the outputs stay attached to the graph (as in the reference) but a backward
-    through the eval-mode network (BatchNorm on running statistics) has no kernel - it raises instead of silently yielding
-    no gradients."""
-
-    @staticmethod
-    def forward(ctx, strong, weak, *params):
-        return strong.view_as(strong), weak.view_as(weak)
-
-    @staticmethod
-    def backward(ctx, gstrong, gweak):
-        raise NotImplementedError("desed_task_b200 CRNN: backward through an eval-mode forward (BatchNorm on running "
-                                  "statistics) is not implemented; call .train() (or freeze_bn=True) before a forward "
-                                  "that needs gradients, or wrap inference in torch.no_grad()")
 
 
 class _CRNNFunction(torch.autograd.Function):
@@ -360,8 +349,6 @@ class CRNN(nn.Module):
             return "multi-head nclass"
         if self.nclass > 32:
             return "nclass > 32"
-        if self.freeze_bn:
-            return "freeze_bn=True"
         if self.dropstep_recurrent and not self.use_embeddings:
             return "dropstep_recurrent > 0 without embeddings (CRNN.py:295-301)"
         if self.use_embeddings and self.aggregation_type != "pool1d":
@@ -416,16 +403,21 @@ class CRNN(nn.Module):
         return self._spans(ws.dropstep_buf, B, frames, prm, frames, prm, seed, 301)
 
     # ------------------------------------------------------------------------------------------------------------
-    def _launch_forward(self, ws, x, minmax, embeddings, classes_mask, specaug, dropstep, training, seed):
+    def _launch_forward(self, ws, x, minmax, embeddings, classes_mask, specaug, dropstep, training, seed, save=None):
         plan = ws.plan
         ws.bind_params(self)
         ws.generation += 1
         B = ws.B
-        plan.training = 1 if training else 0
+        # plan.training = "save what the backward needs"; dropout / SpecAugment follow the module's mode, BatchNorm uses
+        # the running statistics in eval mode and under freeze_bn (CRNN.py:308-323: BatchNorm2d.eval() inside train())
+        save = training if save is None else save
+        plan.training = 1 if (training or save) else 0
+        plan.bn_eval = 1 if (not training or self.freeze_bn) else 0
         plan.precision = self._precision()
+        plan.activation = self.cnn.activation_code()
         plan.seed = seed
         plan.seed_dev = _vp(getattr(self, "seed_dev", None))
-        plan.dropout_p = float(self.dropout.p)
+        plan.dropout_p = float(self.dropout.p) if training else 0.0
         plan.x = _vp(x)
         plan.x_sb, plan.x_sm, plan.x_st = x.stride(0), x.stride(1), x.stride(2)
         plan.minmax = _vp(minmax)
@@ -485,16 +477,15 @@ class CRNN(nn.Module):
         dropstep = None
         if training and self.use_embeddings and self.dropstep_recurrent:
             dropstep = self._dropstep_spans(ws, B, ws.Tp, seed)
-        args = (x, minmax, embeddings, classes_mask, specaug, dropstep, training, seed)
-        want_grad = torch.is_grad_enabled() and training and any(p.requires_grad for p in self.parameters())
+        # autograd works in both modes, as in the reference: an eval-mode forward with grad enabled (BN-frozen fine-tuning,
+        # saliency, THOP-style profiling) saves its activations and backpropagates through running-statistics BatchNorm
+        want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if autograd is not None:
             want_grad = autograd
+        args = (x, minmax, embeddings, classes_mask, specaug, dropstep, training, seed, training or want_grad)
         if want_grad:
             return _CRNNFunction.apply(self, ws, args, *list(self.parameters()))
-        out = self._launch_forward(ws, *args)
-        if autograd is None and not training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            return _NoBackward.apply(out[0], out[1], *[p for p in self.parameters() if p.requires_grad])
-        return out
+        return self._launch_forward(ws, *args)
 
     def forward(self, x, pad_mask=None, embeddings=None, classes_mask=None):
         return self.run(x, None, embeddings, classes_mask, pad_mask)
@@ -506,14 +497,20 @@ class CRNN(nn.Module):
                None if not self.use_embeddings else (embeddings.shape[1], embeddings.shape[2]))
         return strong, weak, self._ws[key]
 
-    def backward_direct(self, ws, gstrong, gweak):
-        """Runs sedk_crnn_backward; returns the flat gradient buffer (parameters() order, overwritten each call)."""
+    def backward_direct(self, ws, gstrong, gweak, phases=3):
+        """Runs sedk_crnn_backward (phases = 3) or one half of it (1: heads + BiGRU + fusion, 2: CNN; include/sedk.h);
+        returns the flat gradient buffer (parameters() order, overwritten each call)."""
         plan = ws.plan
         ws.bind_params(self)
         plan.gstrong, plan.gweak = _vp(gstrong), _vp(gweak)
         ws.keep_g = (gstrong, gweak)
-        check(lib().sedk_crnn_backward(ctypes.byref(plan), stream_ptr()), "sedk_crnn_backward")
+        check(lib().sedk_crnn_backward_phase(ctypes.byref(plan), int(phases), stream_ptr()), "sedk_crnn_backward_phase")
         return ws.gflat
+
+    def cnn_param_count(self):
+        """Number of leading entries of the flat parameter / gradient buffers that belong to the CNN (parameters() order:
+        cnn, rnn, dense, dense_softmax, [cat_tf])."""
+        return sum(p.numel() for p in self.cnn.parameters())
 
     def train(self, mode=True):
         """Override the default train() to freeze the BN parameters (CRNN.py:308-323; returns None like the reference)."""

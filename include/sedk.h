@@ -241,6 +241,9 @@ typedef struct {
     int32_t nclass;
     int32_t training;               /* 1: batch-stat BN + dropout + saves for backward         */
     int32_t precision;              /* 0: TF32 tensor cores; 1: 3xTF32 (fp32-equivalent)       */
+    int32_t bn_eval;                /* 1: BatchNorm uses (and does not update) the running statistics although training = 1:
+                                       `freeze_bn` (CRNN.py:308-323) and autograd through an eval-mode forward */
+    int32_t activation;             /* CNN.py:81-88: 0 "glu", 1 "cg" (ContextGating), 2 "relu", 3 "leakyrelu" (slope 0.2) */
     float dropout_p;                /* CNN.py:90-91, CRNN.py:103                               */
     float bn_eps, bn_momentum;      /* CNN.py:76 (1e-3, 0.99)                                  */
     uint64_t seed;                  /* dropout Philox seed for this forward                    */
@@ -293,6 +296,10 @@ typedef struct {
 
 SEDK_API int sedk_crnn_forward(const sedk_crnn_plan* plan, void* stream);
 SEDK_API int sedk_crnn_backward(const sedk_crnn_plan* plan, void* stream);
+/* The backward in two halves, for callers that overlap a collective with it: phases = 1: heads + BiGRU (+ embedding fusion);
+ * every gradient of those parameters is final when the call's work completes.  phases = 2: the CNN (must follow phase 1 of
+ * the same forward).  phases = 3: both (= sedk_crnn_backward). */
+SEDK_API int sedk_crnn_backward_phase(const sedk_crnn_plan* plan, int phases, void* stream);
 SEDK_API int sedk_sizeof_crnn_plan(void);
 
 /* Losses of SEDTask4.training_step (sed_trainer.py:309-342): BCE(strong rows [0,n_strong)) + BCE(weak rows

@@ -130,8 +130,9 @@ def apply_specaugment(x, spec):
     return x
 
 
-def cnn_forward(x, params, cfg, training, bn_state=None, drop_masks=None, collect=None):
-    """CNN.py:66-98: conv -> BN -> act -> dropout -> avgpool, per layer.  x: (B, Cin, T, F)."""
+def cnn_forward(x, params, cfg, training, bn_state=None, drop_masks=None, collect=None, bn_eval=False):
+    """CNN.py:66-98: conv -> BN -> act -> dropout -> avgpool, per layer.  x: (B, Cin, T, F).
+    bn_eval: BatchNorm on its running statistics although `training` (freeze_bn, CRNN.py:308-323)."""
     for i, nout in enumerate(cfg.nb_filters):
         p = "cnn.cnn."
         x = F.conv2d(x, params[f"{p}conv{i}.weight"], params[f"{p}conv{i}.bias"],
@@ -141,11 +142,12 @@ def cnn_forward(x, params, cfg, training, bn_state=None, drop_masks=None, collec
         if cfg.normalization == "batch":
             rm = params[f"{p}batchnorm{i}.running_mean"]
             rv = params[f"{p}batchnorm{i}.running_var"]
-            if training:
+            bn_train = training and not bn_eval
+            if bn_train:
                 rm, rv = rm.clone(), rv.clone()
             x = F.batch_norm(x, rm, rv, params[f"{p}batchnorm{i}.weight"], params[f"{p}batchnorm{i}.bias"],
-                             training, cfg.bn_momentum, cfg.bn_eps)
-            if training and bn_state is not None:
+                             bn_train, cfg.bn_momentum, cfg.bn_eps)
+            if bn_train and bn_state is not None:
                 bn_state[f"{p}batchnorm{i}.running_mean"] = rm
                 bn_state[f"{p}batchnorm{i}.running_var"] = rv
         elif cfg.normalization == "layer":
@@ -199,7 +201,7 @@ def heads(x, params, cfg, classes_mask=None):
 
 def crnn_forward(params, x, cfg=CFG_2023, training=False, embeddings=None, classes_mask=None,
                  specaug=None, drop_masks=None, rnn_drop_mask=None, emb_drop_mask=None,
-                 dropstep=None, bn_state=None, collect=None, gru_impl="loop"):
+                 dropstep=None, bn_state=None, collect=None, gru_impl="loop", bn_eval=False):
     """CRNN.forward (CRNN.py:221-306).  x: [B, n_mels, T] scaled log-mel.
 
     drop_masks: list of 0/1 keep masks (B,C,T,F) per conv layer; rnn_drop_mask: [B,T',2H] keep mask for
@@ -209,7 +211,7 @@ def crnn_forward(params, x, cfg=CFG_2023, training=False, embeddings=None, class
     if training:
         x = apply_specaugment(x, specaug)
     x = x.transpose(1, 2).unsqueeze(1)                     # (B,1,T,F)  CRNN.py:224
-    x = cnn_forward(x, params, cfg, training, bn_state, drop_masks, collect)
+    x = cnn_forward(x, params, cfg, training, bn_state, drop_masks, collect, bn_eval)
     bs, chan, frames, freq = x.shape
     assert freq == 1, "oracle covers the shipped configs (freq pooled to 1)"
     x = x.squeeze(-1).permute(0, 2, 1)                     # [B,T',C]  CRNN.py:244-245

@@ -181,6 +181,59 @@ def main():
     gold["emb_seed"] = 7
     np.savez(os.path.join(OUT, "crnn.npz"), **gold)
 
+    # ------------------------------------------------------------------ constructor alternates
+    # activation in {cg, relu, leakyrelu} (CNN.py:81-88), freeze_bn in train mode (CRNN.py:308-323) and autograd through an
+    # eval-mode forward: the oracle restatement against the reference, RNG-free (dropout 0, SpecAugment off)
+    import dataclasses
+    vgold = {}
+    g = torch.Generator().manual_seed(11)
+    ys_v = (torch.rand(2, 10, 156, generator=g) < 0.1).float()
+    yw_v = (ys_v.sum(-1) > 0).float()
+    for vname, over, ocfg_over, mode in [("cg", dict(activation="cg"), dict(activation="cg"), "train"),
+                                         ("relu", dict(activation="Relu"), dict(activation="relu"), "train"),
+                                         ("leakyrelu", dict(activation="leakyrelu"), dict(activation="leakyrelu"), "train"),
+                                         ("freeze_bn", dict(freeze_bn=True), {}, "train"),
+                                         ("eval_grad", {}, {}, "eval")]:
+        ocfg_v = dataclasses.replace(ocrnn.CFG_2023, dropout=0.0, **ocfg_over)
+        P = ocrnn.init_params(ocfg_v, seed=42, trained_like=True)
+        net_v = CRNN(**dict(cfg23["net"], dropout=0.0, specaugm_t_p=0.0, specaugm_f_p=0.0, **over))
+        net_v.load_state_dict(P, strict=True)
+        assert [n for n, _ in net_v.named_parameters()] == ocrnn.param_names(P), vname
+        net_v.train() if mode == "train" else net_v.eval()
+        s_ref, w_ref = net_v(feats)
+        loss_ref = torch.nn.BCELoss()(s_ref, ys_v) + torch.nn.BCELoss()(w_ref, yw_v)
+        loss_ref.backward()
+        Pt = {k: (v.clone().requires_grad_(True) if ocrnn.is_float_param(k) else v.clone()) for k, v in P.items()}
+        frozen = vname == "freeze_bn"
+        s_or, w_or = ocrnn.crnn_forward(Pt, feats, ocfg_v, mode == "train", bn_eval=frozen)
+        loss_or = otr.bce(s_or, ys_v) + otr.bce(w_or, yw_v)
+        loss_or.backward()
+        assert abs(loss_ref.item() - loss_or.item()) < 1e-6, vname
+        gscale = max(p.grad.abs().max().item() for p in net_v.parameters() if p.grad is not None)
+        gmax = 0.0
+        for n, p in net_v.named_parameters():
+            if p.grad is None:                                   # freeze_bn: BatchNorm affine has requires_grad False
+                assert frozen and "batchnorm" in n, n
+                continue
+            bn_batch = mode == "train" and not frozen
+            if re.fullmatch(r"cnn\.cnn\.conv\d\.bias", n) and bn_batch:
+                continue                                         # exact 0 through a batch-statistics BatchNorm
+            rel = (p.grad - Pt[n].grad).abs().max().item() / max(p.grad.abs().max().item(), 1e-2 * gscale)
+            gmax = max(gmax, rel)
+        assert gmax < 2e-4, (vname, gmax)
+        # running statistics must not move under freeze_bn / eval
+        if not (mode == "train" and not frozen):
+            assert torch.equal(dict(net_v.named_buffers())["cnn.cnn.batchnorm3.running_var"],
+                               P["cnn.cnn.batchnorm3.running_var"]), vname
+        vgold[f"strong_{vname}"] = s_ref.detach().numpy()
+        vgold[f"weak_{vname}"] = w_ref.detach().numpy()
+        vgold[f"loss_{vname}"] = np.float32(loss_ref.item())
+        vgold[f"grad_conv3_w_{vname}"] = net_v.cnn.cnn.conv3.weight.grad[::8, ::8].numpy()
+        vgold[f"grad_conv0_b_{vname}"] = net_v.cnn.cnn.conv0.bias.grad.numpy()
+        report[f"variant_{vname}"] = f"loss equal, max rel grad diff = {gmax:.2e}"
+    vgold["labels_strong"] = ys_v.numpy()
+    np.savez(os.path.join(OUT, "variants.npz"), **vgold)
+
     # specaugment draw parity (torchaudio mask_along_axis_iid via CRNN.apply_specaugment)
     net = CRNN(**cfg23["net"])
     net.train()

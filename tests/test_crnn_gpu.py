@@ -140,8 +140,9 @@ def test_tcgen05_conv_matches_legacy_mma_path(dev, feats):
 
 
 def test_dropout_and_specaugment_statistics(dev, feats):
-    """Train mode with the shipped dropout 0.5 + SpecAugment: outputs stay finite, differ run to run, backward runs, the
-    same seed reproduces the same masks in backward (finite-difference check on one weight)."""
+    """Train mode with the shipped dropout 0.5 + SpecAugment: outputs stay finite and differ run to run, a backward through
+    an overwritten workspace raises, the live one runs.  (The forward/backward mask consistency is the finite-difference test
+    in test_variants_gpu.py; SpecAugment parity against the oracle is test_specaugment_spans_parity below.)"""
     cfg = ocrnn.CFG_2023
     P = ocrnn.init_params(cfg, seed=42, trained_like=True)
     net = build(cfg, P, dev, 1)
@@ -151,12 +152,44 @@ def test_dropout_and_specaugment_statistics(dev, feats):
     s2, w2 = net(x)
     assert torch.isfinite(s1).all() and torch.isfinite(w1).all()
     assert (s1 - s2).abs().max().item() > 1e-4
-    (s1.mean() + w1.mean()).backward  # graph of the first call was overwritten by the second: must raise
+    # the workspace of the first call was overwritten by the second: its backward must raise
     with pytest.raises(RuntimeError):
         (s1.mean() + w1.mean()).backward()
     (s2.mean() + w2.mean()).backward()
     gsum = sum(p.grad.abs().sum().item() for p in net.parameters())
     assert np.isfinite(gsum) and gsum > 0
+
+
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [(1, 2e-5, 2e-3), (0, 1e-3, 5e-2)])
+def test_specaugment_spans_parity(dev, precision, tol_out, tol_grad):
+    """SpecAugment end to end (CRNN.apply_specaugment, CRNN.py:207-219): the spans the device drew (sedk_mask_spans, read
+    back from the workspace) are injected into the oracle's forward - posteriors and gradients must agree, i.e. the mask is
+    applied on the right axes, after the scaler, with fill value 0, in forward and backward."""
+    cfg = dataclasses.replace(ocrnn.CFG_2023, dropout=0.0)
+    P = ocrnn.init_params(cfg, seed=42, trained_like=True)
+    net = build(cfg, P, dev, precision, specaugm_t_p=0.2, specaugm_f_p=0.2)      # the 2023 recipe's effective defaults
+    net.train()
+    x = ofe.features(gen_wave(5, 6))
+    s, w = net(x.to(dev))
+    wgt = torch.linspace(0.5, 1.5, 156)
+    ((s * wgt.to(dev)).mean() + w.mean()).backward()
+    spans = list(net._ws.values())[0].specaug_buf.cpu().long()                   # [B, 4] = f_start, f_end, t_start, t_end
+    assert (spans[:, 1] - spans[:, 0]).max() > 0 and (spans[:, 3] - spans[:, 2]).max() > 0
+    assert (spans[:, 1] - spans[:, 0]).max() < 10 and (spans[:, 3] - spans[:, 2]).max() < 5 and spans.min() >= 0
+    spec = dict(f_start=spans[:, 0], f_end=spans[:, 1], t_start=spans[:, 2], t_end=spans[:, 3])
+    Pt = {k: (v.clone().requires_grad_(True) if ocrnn.is_float_param(k) else v.clone()) for k, v in P.items()}
+    so, wo = ocrnn.crnn_forward(Pt, x, cfg, True, specaug=spec)
+    assert maxdiff(s, so) < tol_out and maxdiff(w, wo) < tol_out
+    # the masks matter: without them the oracle's output is measurably different
+    with torch.no_grad():
+        s_plain, _ = ocrnn.crnn_forward(P, x, cfg, True)
+    assert maxdiff(so, s_plain) > 20 * tol_out
+    ((so * wgt).mean() + wo.mean()).backward()
+    gscale = max(Pt[n].grad.abs().max().item() for n in ocrnn.param_names(P))
+    for n, p in net.named_parameters():
+        ref = Pt[n].grad
+        err = (p.grad.cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-2 * gscale)
+        assert err < tol_grad, (n, err)
 
 
 def test_dropout_kernel_rate(dev):
@@ -180,7 +213,7 @@ def test_unsupported_configs_raise(dev):
     from desed_task_b200.nnet.CRNN import CRNN
     x = torch.zeros(1, 128, 626, device=dev)
     with pytest.raises(NotImplementedError):
-        CRNN(activation="relu", nb_filters=[16, 32, 64, 128, 128, 128, 128], kernel_size=[3] * 7, padding=[1] * 7,
+        CRNN(normalization="layer", nb_filters=[16, 32, 64, 128, 128, 128, 128], kernel_size=[3] * 7, padding=[1] * 7,
              stride=[1] * 7, pooling=[[2, 2], [2, 2], [1, 2], [1, 2], [1, 2], [1, 2], [1, 2]]).to(dev)(x)
     with pytest.raises(AttributeError):
         CRNN(nclass=(10, 17))                                     # same failure as the reference (CRNN.py:113)

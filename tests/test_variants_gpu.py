@@ -131,3 +131,79 @@ def test_dropout_masks_agree_between_forward_and_backward(dev, feats, small, pre
             assert abs(loss_at(101).item() - loss.item()) > 1e-6
     finally:
         lib().sedk_set_option(b"bnglu_small", 1)
+
+
+@pytest.mark.parametrize("vname,over,ocfg_over,mode", [
+    ("cg", dict(activation="cg"), dict(activation="cg"), "train"),
+    ("relu", dict(activation="Relu"), dict(activation="relu"), "train"),
+    ("leakyrelu", dict(activation="leakyrelu"), dict(activation="leakyrelu"), "train"),
+    ("freeze_bn", dict(freeze_bn=True), {}, "train"),
+    ("eval_grad", {}, {}, "eval")])
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [(1, 2e-5, 2e-3), (0, 1e-3, 5e-2)])
+def test_constructor_alternates_match_the_reference(dev, vname, over, ocfg_over, mode, precision, tol_out, tol_grad):
+    """SURVEY.md 8f.4 / a14 with kernels, not raises: ContextGating, ReLU, LeakyReLU(0.2) (CNN.py:81-88), freeze_bn
+    (CRNN.py:308-323: BatchNorm on running statistics inside a training forward, frozen affine) and autograd through an
+    eval-mode forward - posteriors / loss against fixtures minted from the live reference (tests/golden/variants.npz),
+    every gradient against the oracle's autograd (itself pinned to the reference in oracle/make_golden.py)."""
+    from oracle import trainer as otr
+    from tests.util import golden
+    g = golden("variants")
+    cfg = dataclasses.replace(ocrnn.CFG_2023, dropout=0.0, **ocfg_over)
+    P = ocrnn.init_params(cfg, seed=42, trained_like=True)
+    net = build(cfg, P, dev, precision, specaugm_t_p=0.0, specaugm_f_p=0.0, **over)
+    net.train() if mode == "train" else net.eval()
+    x = ofe.features(gen_wave(0, 2))
+    ys = torch.from_numpy(g["labels_strong"])
+    yw = (ys.sum(-1) > 0).float()
+    rv_before = net.state_dict()["cnn.cnn.batchnorm3.running_var"].clone()
+    s, w = net(x.to(dev))
+    assert maxdiff(s, torch.from_numpy(g["strong_" + vname])) < tol_out
+    assert maxdiff(w, torch.from_numpy(g["weak_" + vname])) < tol_out
+    loss = torch.nn.functional.binary_cross_entropy(s, ys.to(dev)) + torch.nn.functional.binary_cross_entropy(w, yw.to(dev))
+    assert abs(loss.item() - float(g["loss_" + vname])) < 10 * tol_out
+    loss.backward()
+    frozen = vname in ("freeze_bn", "eval_grad")
+    if frozen:
+        assert torch.equal(net.state_dict()["cnn.cnn.batchnorm3.running_var"], rv_before)       # running stats untouched
+    Pt = {k: (v.clone().requires_grad_(True) if ocrnn.is_float_param(k) else v.clone()) for k, v in P.items()}
+    so, wo = ocrnn.crnn_forward(Pt, x, cfg, mode == "train", bn_eval=vname == "freeze_bn")
+    (otr.bce(so, ys) + otr.bce(wo, yw)).backward()
+    gscale = max(Pt[n].grad.abs().max().item() for n in ocrnn.param_names(P))
+    for n, p in net.named_parameters():
+        if vname == "freeze_bn" and "batchnorm" in n:
+            assert p.grad is None and not p.requires_grad, n       # frozen affine (CRNN.py:320-322)
+            continue
+        ref = Pt[n].grad
+        if ".conv" in n and n.endswith(".bias") and not frozen:
+            assert p.grad.abs().max().item() == 0.0, n              # cancels inside a batch-statistics BatchNorm
+            continue
+        err = (p.grad.cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-2 * gscale)
+        assert err < tol_grad, (vname, n, err)
+    if frozen:
+        # through a frozen BatchNorm the conv bias DOES receive a gradient (fixture from the live reference)
+        assert maxdiff(net.cnn.cnn.conv0.bias.grad, torch.from_numpy(g["grad_conv0_b_" + vname])) < tol_grad * gscale
+    assert maxdiff(net.cnn.cnn.conv3.weight.grad[::8, ::8], torch.from_numpy(g["grad_conv3_w_" + vname])) < tol_grad * gscale
+
+
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [(1, 2e-5, 2e-3), (0, 5e-4, 3e-2)])
+def test_gru_192_cluster_kernel_agrees_with_first_generation(dev, precision, tol_out, tol_grad):
+    """2024 recipe (H = 192): the 3-CTA-cluster recurrence of csrc/gru3.cu (weights in registers, h / dgh exchanged through
+    DSMEM, one cluster barrier per step) against the first-generation cluster kernel - forward, every gradient."""
+    from desed_task_b200._lib import lib
+    cfg = dataclasses.replace(ocrnn.CFG_2024, dropout=0.0)
+    P = ocrnn.init_params(cfg, seed=42, trained_like=True)
+    g = torch.Generator().manual_seed(7)
+    emb = torch.randn(3, 768, 496, generator=g).to(dev)
+    x = ofe.features(gen_wave(0, 3)).to(dev)
+    res = {}
+    for on in (1, 0):
+        lib().sedk_set_option(b"gru_v3", on)
+        try:
+            net = build(cfg, P, dev, precision, specaugm_t_p=0.0, specaugm_f_p=0.0, dropstep_recurrent=0.0)
+            net.train()
+            s, w = net(x, embeddings=emb)
+            ((s * torch.linspace(0.5, 1.5, s.shape[-1], device=dev)).mean() + w.mean()).backward()
+            res[on] = (s.detach().clone(), w.detach().clone(), {n: p.grad.clone() for n, p in net.named_parameters()})
+        finally:
+            lib().sedk_set_option(b"gru_v3", 1)
+    _compare(res[1], res[0], tol_out, tol_grad)
