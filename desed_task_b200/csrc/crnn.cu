@@ -193,7 +193,11 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
                                p->emb_T, pdrop, p->seed, p->seed_dev, STREAM_EMB, s);
         if (rc) return rc;
         const int W = nb + p->emb_dim;
-        rc = launch_gemm(0, 1, B * Tp, nb, W, 1.f, p->cat_in, W, p->cat_w, W, 0.f, p->fused, nb, p->cat_b, p->precision, s);
+        // cat_tf (CRNN.py:294): [B T', nb + emb] x [nb, nb + emb]^T - on tcgen05 in the TF32 mode (K = 896 for BEATs embeddings)
+        if (gemm_tc5_ok(B * Tp, nb, W, p->precision) && all_aligned16(p->cat_in, p->cat_w, p->cat_b, p->fused))
+            rc = launch_gemm_tc5_nt1(p->cat_in, p->cat_w, p->cat_b, p->fused, B * Tp, nb, W, s);
+        else
+            rc = launch_gemm(0, 1, B * Tp, nb, W, 1.f, p->cat_in, W, p->cat_w, W, 0.f, p->fused, nb, p->cat_b, p->precision, s);
         if (rc) return rc;
         xr = p->fused;
     }

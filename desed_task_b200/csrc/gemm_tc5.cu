@@ -208,6 +208,28 @@ int launch_gemm_tc5_nt2(const float* A, const float* const B[2], const float* co
     return SEDK_OK;
 }
 
+// C[M, N] = A[M, K] B[N, K]^T + bias   (one problem of the kernel above; lda = K, ldb = K, ldc = N)
+int launch_gemm_tc5_nt1(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, cudaStream_t s) {
+    char pname[64];
+    snprintf(pname, sizeof(pname), "gemm_tc5_NT_%dx%dx%d_x1", M, N, K);
+    SEDK_PROF(pname, s);
+    SEDK_REQUIRE(aligned16(A) && aligned16(B) && aligned16(C) && (bias == nullptr || aligned16(bias)),
+                 "gemm_tc5: operands must be 16-byte aligned");
+    CUtensorMap ta, tb;
+    int rc = map_2d(&ta, A, M, K, K, 128, false);
+    if (rc) return rc;
+    rc = map_2d(&tb, B, N, K, K, 128, false);
+    if (rc) return rc;
+    static bool cfg = false;
+    auto kern = gemm_tc5_kernel<false, 0>;
+    rc = opt_in_once(kern, cfg);
+    if (rc) return rc;
+    dim3 grid(cdiv(M, 128), cdiv(N, 128), 1);
+    kern<<<grid, GM_THREADS, GM_SMEM, s>>>(ta, tb, ta, tb, C, C, bias, bias, M, N, K, N);
+    SEDK_LAUNCH_CHECK("gemm_tc5_kernel<NT1>");
+    return SEDK_OK;
+}
+
 // C[M, N] = A0[M, K] B0[K, N] + A1[M, K] B1[K, N]   (lda = K, ldb = N, ldc = N)
 int launch_gemm_tc5_nn_pair(const float* const A[2], const float* const B[2], float* C, int M, int N, int K, cudaStream_t s) {
     char pname[64];

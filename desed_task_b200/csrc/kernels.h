@@ -105,6 +105,7 @@ int launch_gemm_batched(int transA, int transB, int M, int N, int K, float alpha
 bool gemm_tc5_ok(int M, int N, int K, int precision);
 int launch_gemm_tc5_nt2(const float* A, const float* const B[2], const float* const bias[2], float* const C[2], int M, int N,
                         int K, cudaStream_t s);
+int launch_gemm_tc5_nt1(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, cudaStream_t s);
 int launch_gemm_tc5_nn_pair(const float* const A[2], const float* const B[2], float* C, int M, int N, int K, cudaStream_t s);
 // column sums: out[n] (+)= sum_m A[m*lda + n]
 int launch_colsum(const float* A, int M, int N, int lda, float* out, int accumulate, cudaStream_t s);

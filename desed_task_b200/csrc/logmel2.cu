@@ -1,4 +1,15 @@
-// Fused waveform -> |STFT| -> mel -> (log) kernel for sm_100a.
+// Fused waveform -> |STFT| -> mel -> (log) kernel for sm_100a, second generation (same decomposition as logmel.cu, which
+// stays in the library as the A/B baseline behind option "logmel_v2" = 0).  What changed, from the ncu profile of the first
+// generation (168 registers and 94 KB of shared memory per 4-warp CTA -> 8 warps per SM, issue slots 34 % busy, 3 460
+// warp-instructions per frame):
+//   * 3 CTAs (12 warps) per SM: the Hamming window and the W_2048 untangle twiddles are read through L1 (__ldg, coalesced)
+//     instead of living in every CTA's shared memory, and the magnitude buffer aliases the FFT exchange buffer
+//     -> 61 KB per CTA;
+//   * packed fp32 arithmetic (FADD2 / FFMA2 / FMUL2) for the 160 butterflies of the two in-register 32-point FFTs and the
+//     window multiply: half the issue slots for the same flops;
+//   * the real-FFT untangle works on conjugate pairs: X[k] and X[1024 - k] share Xe[k] and T = W^k Xo[k]
+//     (|X[k]| = |Xe + T|, |X[1024 - k]| = |Xe - T|), 16 pair-iterations per lane instead of 32 single bins, magnitudes
+//     through rsqrt.approx (2 ulp; the log-mel budget is 1.2e-5 relative).
 //
 // Replaces torchaudio MelSpectrogram(n_fft=win=2048, hop, center=True/reflect, hamming, power=1, HTK fb) and
 // AmplitudeToDB + clamp as used at recipes/dcase2023_task4_baseline/local/sed_trainer.py:79-91,253-264,282.
@@ -17,6 +28,7 @@
 
 namespace sedk {
 namespace {
+namespace v2 {
 
 constexpr int kNfft = 2048;
 constexpr int kHalf = 1024;
@@ -82,9 +94,9 @@ __device__ __forceinline__ void dif_stage(float2 (&v)[32]) {
             constexpr int base = decltype(blk)::value * 2 * S;
             constexpr int j = decltype(jj)::value;
             constexpr int m = j * (16 / S);
-            float2 a = v[base + j], b = v[base + j + S];
-            v[base + j] = make_float2(a.x + b.x, a.y + b.y);
-            v[base + j + S] = mul_w32<m>(make_float2(a.x - b.x, a.y - b.y));
+            const float2 a = v[base + j], b = v[base + j + S];
+            v[base + j] = __fadd2_rn(a, b);
+            v[base + j + S] = mul_w32<m>(__ffma2_rn(b, make_float2(-1.0f, -1.0f), a));
         });
     });
 }
@@ -109,47 +121,41 @@ __device__ __forceinline__ int reflect_idx(int i, int L) {
 
 struct SmemLayout {
     int chunk_floats;
-    size_t off_window, off_tw2048, off_tw32, off_chunk, off_tile, off_warp, off_bar, total;
+    size_t off_tw32, off_chunk, off_tile, off_warp, off_bar, total;
 };
 __host__ __device__ inline SmemLayout make_layout(int hop, int n_mels) {
     SmemLayout s;
     s.chunk_floats = ((FR - 1) * hop + kNfft + 8 + 3) & ~3;
     size_t o = 0;
     s.off_bar = o;     o += 16;
-    s.off_window = o;  o += kNfft * 4;
-    s.off_tw2048 = o;  o += kHalf * 8;
     s.off_tw32 = o;    o += kHalf * 8;
     s.off_chunk = o;   o += (size_t)s.chunk_floats * 4;
     s.off_tile = o;    o += (size_t)FR * n_mels * 4;
     o = (o + 15) & ~(size_t)15;
-    s.off_warp = o;    o += (size_t)NW * (32 * SROW * 8 + 1028 * 4);
+    s.off_warp = o;    o += (size_t)NW * (32 * SROW * 8);
     s.total = o;
     return s;
 }
 
-__global__ void __launch_bounds__(NW * 32, 2)
-logmel_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tables tab, float* __restrict__ out,
+__global__ void __launch_bounds__(NW * 32, 3)
+logmel2_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tables tab, float* __restrict__ out,
               int64_t out_sb, int64_t out_sm, int64_t out_st, int log_mode, float amin, float db_lo, float db_hi,
               uint32_t* __restrict__ minmax, int n_groups_per_clip) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int hop = tab.hop, n_mels = tab.n_mels;
     const SmemLayout lay = make_layout(hop, n_mels);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lay.off_bar);
-    float* s_window = reinterpret_cast<float*>(smem + lay.off_window);
-    float2* s_tw2048 = reinterpret_cast<float2*>(smem + lay.off_tw2048);
+    const float2* g_window2 = reinterpret_cast<const float2*>(tab.window);      // read through L1 (coalesced)
+    const float2* g_tw2048 = reinterpret_cast<const float2*>(tab.tw2048);
     float2* s_tw32 = reinterpret_cast<float2*>(smem + lay.off_tw32);
     float* s_chunk = reinterpret_cast<float*>(smem + lay.off_chunk);
     float* s_tile = reinterpret_cast<float*>(smem + lay.off_tile);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* wbase = smem + lay.off_warp + (size_t)warp * (32 * SROW * 8 + 1028 * 4);
+    unsigned char* wbase = smem + lay.off_warp + (size_t)warp * (32 * SROW * 8);
     float2* s_x = reinterpret_cast<float2*>(wbase);                   // 32 x 33 exchange, later Z[1024]
-    float* s_mag = reinterpret_cast<float*>(wbase + 32 * SROW * 8);   // |X[k]|, k = 0..1024
+    float* s_mag = reinterpret_cast<float*>(wbase);                   // |X[k]|, k = 0..1024: aliases s_x once Z is in registers
 
-    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) s_window[i] = tab.window[i];
-    for (int i = threadIdx.x; i < kHalf; i += blockDim.x) {
-        s_tw2048[i] = reinterpret_cast<const float2*>(tab.tw2048)[i];
-        s_tw32[i] = reinterpret_cast<const float2*>(tab.tw32x32)[i];
-    }
+    for (int i = threadIdx.x; i < kHalf; i += blockDim.x) s_tw32[i] = reinterpret_cast<const float2*>(tab.tw32x32)[i];
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -191,12 +197,8 @@ logmel_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tabl
             const bool interior = (s0 >= 0) && (s0 + kNfft <= L) && (((s0 - c0) & 1) == 0);
             if (interior) {
                 const float2* xs = reinterpret_cast<const float2*>(s_chunk + (s0 - c0));
-                const float2* ws = reinterpret_cast<const float2*>(s_window);
 #pragma unroll
-                for (int n1 = 0; n1 < 32; n1++) {
-                    float2 x = xs[32 * n1 + lane], w = ws[32 * n1 + lane];
-                    v[n1] = make_float2(x.x * w.x, x.y * w.y);
-                }
+                for (int n1 = 0; n1 < 32; n1++) v[n1] = __fmul2_rn(xs[32 * n1 + lane], __ldg(g_window2 + 32 * n1 + lane));
             } else {
 #pragma unroll
                 for (int n1 = 0; n1 < 32; n1++) {
@@ -204,7 +206,8 @@ logmel_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tabl
                     int i0 = reflect_idx(s0 + j, L) - c0, i1 = reflect_idx(s0 + j + 1, L) - c0;
                     i0 = min(max(i0, 0), n_chunk - 1);
                     i1 = min(max(i1, 0), n_chunk - 1);
-                    v[n1] = make_float2(s_chunk[i0] * s_window[j], s_chunk[i1] * s_window[j + 1]);
+                    const float2 w = __ldg(g_window2 + (j >> 1));
+                    v[n1] = make_float2(s_chunk[i0] * w.x, s_chunk[i1] * w.y);
                 }
             }
             // ---- step 1: lane = n2, FFT over n1; twiddle W_1024^{n2 k1}; transpose through smem
@@ -228,23 +231,41 @@ logmel_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tabl
                 s_x[lane + 32 * k2] = v[i];
             });
             __syncwarp();
-            // ---- untangle: X[k] = Xe[k] + W_2048^k Xo[k], k = 0..1024; store |X[k]|
-#pragma unroll 4
-            for (int j = 0; j < 32; j++) {
+            // ---- untangle on conjugate pairs.  With A = Z[k], B = Z[1024 - k] (k = 1..511):
+            //   2 Xe[k] = A + conj(B),  2 Xo[k] = -i (A - conj(B)),  T = W_2048^k Xo[k]
+            //   X[k] = Xe + T,  X[1024 - k] = conj(Xe - T)   ->   |X[k]| = |Xe + T|, |X[1024 - k]| = |Xe - T|
+            // Every Z value a lane needs is read into registers first, so the magnitudes can overwrite the Z buffer.
+            float2 za[16], zb[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
                 const int k = lane + 32 * j;
-                float2 a = s_x[k], bb = s_x[(kHalf - k) & (kHalf - 1)];
-                float2 w = s_tw2048[k];
-                float xer = 0.5f * (a.x + bb.x), xei = 0.5f * (a.y - bb.y);
-                float xor_ = 0.5f * (a.y + bb.y), xoi = -0.5f * (a.x - bb.x);
-                float re = xer + (w.x * xor_ - w.y * xoi);
-                float im = xei + (w.x * xoi + w.y * xor_);
-                s_mag[k] = sqrtf(re * re + im * im);
+                za[j] = s_x[k];
+                zb[j] = s_x[(kHalf - k) & (kHalf - 1)];
             }
-            if (lane == 0) {
-                float2 a = s_x[0];
-                // k = 1024: Xe[0] - Xo[0] = Re Z[0] - Im Z[0] (purely real)
-                s_mag[kHalf] = fabsf(a.x - a.y);
+            const float2 z512 = s_x[512];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int k = lane + 32 * j;
+                const float2 a = za[j], bb = zb[j];
+                const float2 w = __ldg(g_tw2048 + k);
+                const float er = a.x + bb.x, ei = a.y - bb.y;          // 2 Xe
+                const float orr = a.y + bb.y, oi = bb.x - a.x;         // 2 Xo
+                const float tr = w.x * orr - w.y * oi, ti = w.x * oi + w.y * orr;      // 2 T
+                const float pr = er + tr, pi = ei + ti, mr = er - tr, mi = ei - ti;
+                const float sp = pr * pr + pi * pi, sm = mr * mr + mi * mi;
+                const float mp = sp > 0.f ? 0.5f * sp * rsqrtf(sp) : 0.f;
+                const float mm = sm > 0.f ? 0.5f * sm * rsqrtf(sm) : 0.f;
+                if (k == 0) {
+                    // Z[0]: X[0] = Re + Im, X[1024] = Re - Im (both purely real)
+                    s_mag[0] = fabsf(a.x + a.y);
+                    s_mag[kHalf] = fabsf(a.x - a.y);
+                } else {
+                    s_mag[k] = mp;
+                    s_mag[kHalf - k] = mm;
+                }
             }
+            if (lane == 0) s_mag[512] = sqrtf(z512.x * z512.x + z512.y * z512.y);      // self-paired bin: X[512] = conj(Z[512])
             __syncwarp();
             // ---- mel triangles
             for (int m = lane; m < n_mels; m += 32) {
@@ -294,38 +315,30 @@ logmel_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tabl
     }
 }
 
+}  // namespace v2
 }  // namespace
-}  // namespace sedk
 
-namespace sedk {
 int launch_logmel_v2(const float* wave, int B, int L, const sedk_mel_tables* tab, float* out, int64_t out_sb, int64_t out_sm,
-                     int64_t out_st, int log_mode, float amin, float db_lo, float db_hi, uint32_t* minmax, cudaStream_t stream);
-}
-
-extern "C" int sedk_logmel_fwd(const float* wave, int B, int L, const sedk_mel_tables* tab, float* out, int64_t out_sb,
-                               int64_t out_sm, int64_t out_st, int log_mode, float amin, float db_lo, float db_hi,
-                               uint32_t* minmax, void* stream) {
-    using namespace sedk;
-    SEDK_PROF("logmel", (cudaStream_t)stream);
-    SEDK_REQUIRE(wave && tab && out, "sedk_logmel_fwd: null pointer");
-    SEDK_REQUIRE(B > 0, "sedk_logmel_fwd: B must be positive (got %d)", B);
-    SEDK_REQUIRE(L > kHalf, "sedk_logmel_fwd: reflect padding needs L > %d samples (got %d)", kHalf, L);
-    SEDK_REQUIRE(tab->hop > 0 && tab->hop <= kNfft, "sedk_logmel_fwd: hop %d out of range", tab->hop);
-    SEDK_REQUIRE(tab->n_mels > 0 && tab->n_mels <= 256, "sedk_logmel_fwd: n_mels %d out of range", tab->n_mels);
-    if (get_option("logmel_v2", 1) != 0)
-        return launch_logmel_v2(wave, B, L, tab, out, out_sb, out_sm, out_st, log_mode, amin, db_lo, db_hi, minmax,
-                                (cudaStream_t)stream);
+                     int64_t out_st, int log_mode, float amin, float db_lo, float db_hi, uint32_t* minmax, cudaStream_t stream) {
+    using namespace v2;
     const int T = 1 + L / tab->hop;
     const int groups = cdiv(T, FR);
     SmemLayout lay = make_layout(tab->hop, tab->n_mels);
     SEDK_REQUIRE(lay.total <= 227 * 1024, "sedk_logmel_fwd: hop %d needs %zu B of shared memory", tab->hop, lay.total);
-    int rc = opt_in_smem(logmel_kernel, lay.total);
+    int rc = opt_in_smem(logmel2_kernel, lay.total);
     if (rc != SEDK_OK) return rc;
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int o = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, logmel2_kernel, NW * 32, lay.total);
+        per_sm = o < 1 ? 1 : o;
+    }
     long long total = (long long)B * groups;
-    int per_sm = lay.total <= 110 * 1024 ? 2 : 1;
     int grid = (int)(total < (long long)num_sms() * per_sm ? total : (long long)num_sms() * per_sm);
-    logmel_kernel<<<grid, NW * 32, lay.total, (cudaStream_t)stream>>>(wave, B, L, T, *tab, out, out_sb, out_sm, out_st,
-                                                                    log_mode, amin, db_lo, db_hi, minmax, groups);
-    SEDK_LAUNCH_CHECK("logmel_kernel");
+    logmel2_kernel<<<grid, NW * 32, lay.total, stream>>>(wave, B, L, T, *tab, out, out_sb, out_sm, out_st, log_mode, amin,
+                                                        db_lo, db_hi, minmax, groups);
+    SEDK_LAUNCH_CHECK("logmel2_kernel");
     return SEDK_OK;
 }
+
+}  // namespace sedk

@@ -61,17 +61,17 @@ class _Workspace:
         # let the library clear each with a single memset.
         chans = [1] + list(cnn.nb_filters)
         gw_sizes = [0] + [9 * chans[i + 1] * chans[i] for i in range(1, n_conv)]
-        n_grad = (sum(sizes) + 3) // 4 * 4
+        from ..optim import flat_layout
+        g_offs, n_grad = flat_layout(sizes)       # the same 16-byte-aligned layout as the flat parameter buffer
         self.zero_bwd = new(n_grad + sum(gw_sizes), zero=True)
-        self.gflat = self.zero_bwd[:sum(sizes)]
+        self.gflat = self.zero_bwd[:n_grad]
+        self.g_offs = g_offs
         gw_off = [n_grad + sum(gw_sizes[:i]) for i in range(n_conv)]
         self.zero_fwd = new(sum(4 * c for c in cnn.nb_filters), dtype=torch.float64, zero=True)
         st_off = [sum(4 * c for c in cnn.nb_filters[:i]) for i in range(n_conv)]
         self.gviews = {}
-        off = 0
-        for (n, p), sz in zip(params, sizes):
+        for (n, p), sz, off in zip(params, sizes, g_offs):
             self.gviews[n] = self.gflat[off:off + sz].view(p.shape)
-            off += sz
 
         plan = CrnnPlan()
         plan.B, plan.n_mels, plan.n_frames = B, n_mels, n_frames
@@ -508,9 +508,10 @@ class CRNN(nn.Module):
         return ws.gflat
 
     def cnn_param_count(self):
-        """Number of leading entries of the flat parameter / gradient buffers that belong to the CNN (parameters() order:
-        cnn, rnn, dense, dense_softmax, [cat_tf])."""
-        return sum(p.numel() for p in self.cnn.parameters())
+        """Number of leading entries of the flat parameter / gradient buffers (optim.flat_layout) that belong to the CNN
+        (parameters() order: cnn, rnn, dense, dense_softmax, [cat_tf])."""
+        from ..optim import flat_layout
+        return flat_layout([p.numel() for p in self.cnn.parameters()])[1]
 
     def train(self, mode=True):
         """Override the default train() to freeze the BN parameters (CRNN.py:308-323; returns None like the reference)."""

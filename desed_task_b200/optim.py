@@ -9,25 +9,32 @@ import torch
 from ._lib import check, lib, ptr, stream_ptr
 
 
+def flat_layout(sizes):
+    """Offsets of tensors of `sizes` elements inside a flat fp32 buffer: parameters() order, every tensor starting on a
+    16-byte boundary (TMA / 128-bit loads read parameters and gradients straight out of the flat buffers).  Returns
+    (offsets, total).  The parameter, gradient, Adam-moment and teacher buffers all use this ONE layout."""
+    offs, off = [], 0
+    for n in sizes:
+        offs.append(off)
+        off += (int(n) + 3) // 4 * 4
+    return offs, off
+
+
 def flatten_parameters(module):
-    """Re-point every parameter of `module` at a view of ONE contiguous fp32 buffer (parameters() order).
+    """Re-point every parameter of `module` at a view of ONE contiguous fp32 buffer (parameters() order, flat_layout).
     Returns the flat buffer.  Values, names, shapes and state_dict are unchanged."""
     params = list(module.parameters())
     if getattr(module, "_sedk_flat", None) is not None:
         flat = module._sedk_flat
         if all(p.data_ptr() == flat.data_ptr() + off * 4 for p, off in zip(params, module._sedk_offsets)):
             return flat
-    total = sum(p.numel() for p in params)
+    offs, total = flat_layout([p.numel() for p in params])
     dev = params[0].device
-    flat = torch.empty(total, device=dev, dtype=torch.float32)
-    offs = []
-    off = 0
-    for p in params:
+    flat = torch.zeros(total, device=dev, dtype=torch.float32)
+    for p, off in zip(params, offs):
         n = p.numel()
         flat[off:off + n].copy_(p.data.reshape(-1))
         p.data = flat[off:off + n].view(p.shape)
-        offs.append(off)
-        off += n
     module._sedk_flat = flat
     module._sedk_offsets = offs
     return flat
@@ -101,7 +108,11 @@ class FusedAdam(torch.optim.Optimizer):
         loss = closure() if closure is not None else None
         self._ensure()
         params = [p for p in self.param_groups[0]["params"]]
-        gflat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params])
+        offs, total = flat_layout([p.numel() for p in params])
+        gflat = torch.zeros(total, device=self.flat.device, dtype=torch.float32)
+        for p, off in zip(params, offs):
+            if p.grad is not None:
+                gflat[off:off + p.numel()].copy_(p.grad.reshape(-1))
         self.step_flat(gflat)
         return loss
 

@@ -18,7 +18,12 @@ def main():
         peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    for B in (24, 48, 256, 1024):
+    from desed_task_b200._lib import lib
+    variants = [("v2", 1), ("v1", 0)] if "--ab" in sys.argv else [("default", None)]
+    for tag, opt in variants:
+      if opt is not None:
+        lib().sedk_set_option(b"logmel_v2", opt)
+      for B in (24, 64, 256, 1024):
         wave = torch.randn(B, 160000, device=dev) * 0.1
         mm = new_minmax(B, dev)
         for _ in range(3):
@@ -33,7 +38,7 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
         gbs = B * 960512 / ms / 1e6
-        print(json.dumps({"kernel": "logmel", "B": B, "ms": round(ms, 4), "clips_per_s": round(B / ms * 1e3, 1),
+        print(json.dumps({"kernel": "logmel", "variant": tag, "B": B, "ms": round(ms, 4), "clips_per_s": round(B / ms * 1e3, 1),
                           "GBps": round(gbs, 1), "frac_of_measured_hbm": round(gbs / peak, 4)}))
 
 

@@ -16,6 +16,10 @@ if has newtests; then
     timeout 900 python -m pytest tests/test_trainer_gpu.py tests/test_variants_gpu.py -x -q -m gpu > $OUT/${TAG}_pytest_new.log 2>&1
     stamp "pytest new exit $? : $(tail -1 $OUT/${TAG}_pytest_new.log)"
 fi
+if has fe; then
+    timeout 200 python tools/bench_frontend.py --ab > $OUT/${TAG}_frontend.txt 2>&1
+    stamp "front-end A/B exit $?"
+fi
 if has ab; then
     timeout 300 python tools/bench_ab.py gru_v3 gru_v3=2 > $OUT/${TAG}_ab.txt 2>&1
     stamp "A/B exit $?"
