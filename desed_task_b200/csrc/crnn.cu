@@ -239,9 +239,10 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
                             p->sof, p->hsum, B, Tp, in_dim, p->nclass, s);
 }
 
-// phases: 1 = heads + BiGRU (+ embedding fusion), 2 = CNN, 3 = both.  Each phase joins its own side-stream work before it
-// returns, so after phase 1 every RNN / head / fusion gradient is final (a data-parallel caller can start reducing that
-// part of the flat gradient while phase 2 runs).
+// phases (bit mask): 1 = heads + BiGRU (+ embedding fusion), 4 = conv layers [3, n_conv) (98 % of the CNN parameters), 8 = conv
+// layers [0, 3); 2 = 4 | 8 = the whole CNN, 3 / 15 = everything.  A call that does not run everything joins its side-stream
+// work before it returns, so the gradients of the layers it covered are final (a data-parallel caller reduces that slice of
+// the flat gradient while the next phase runs).
 static int crnn_backward_impl(const sedk_crnn_plan* p, int phases, void* stream) {
     int rc = validate(p, true);
     if (rc) return rc;
@@ -348,9 +349,12 @@ static int crnn_backward_impl(const sedk_crnn_plan* p, int phases, void* stream)
     }  // phase 1
     // split mode: the RNN-side weight-gradient GEMMs (side stream) must be complete when phase 1 returns; in the one-call
     // mode they keep overlapping the CNN backward and are joined at the very end
-    if (!(phases & 2)) return fk.join();
+    if (!(phases & (4 | 8))) return fk.join();
     // ---------------- CNN
-    for (int i = p->n_conv - 1; i >= 0; i--) {
+    constexpr int kSplit = 3;
+    const int i_hi = (phases & 4) ? p->n_conv - 1 : (p->n_conv < kSplit ? p->n_conv : kSplit) - 1;
+    const int i_lo = (phases & 8) ? 0 : kSplit;
+    for (int i = i_hi; i >= i_lo; i--) {
         const sedk_conv_layer& L = p->conv[i];
         const int Cc = L.cout;
         const int64_t npix = (int64_t)B * L.T * L.F;
@@ -396,12 +400,13 @@ static int crnn_backward_impl(const sedk_crnn_plan* p, int phases, void* stream)
     return fk.join();
 }
 
-extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) { return crnn_backward_impl(p, 3, stream); }
+extern "C" int sedk_crnn_backward(const sedk_crnn_plan* p, void* stream) { return crnn_backward_impl(p, 1 | 4 | 8, stream); }
 
 extern "C" int sedk_crnn_backward_phase(const sedk_crnn_plan* p, int phases, void* stream) {
-    if (phases < 1 || phases > 3) {
-        sedk::set_error("sedk_crnn_backward_phase: phases must be 1, 2 or 3 (got %d)", phases);
+    if (phases < 1 || phases > 15) {
+        sedk::set_error("sedk_crnn_backward_phase: phases is a bit mask in [1, 15] (got %d)", phases);
         return SEDK_ERR_INVALID;
     }
+    if (phases & 2) phases = (phases & ~2) | 4 | 8;
     return crnn_backward_impl(p, phases, stream);
 }

@@ -513,6 +513,16 @@ class CRNN(nn.Module):
         from ..optim import flat_layout
         return flat_layout([p.numel() for p in self.cnn.parameters()])[1]
 
+    def cnn_lower_param_count(self, n_layers=3):
+        """Flat-buffer entries of the first `n_layers` conv blocks (phase 8 of sedk_crnn_backward_phase)."""
+        from ..optim import flat_layout
+        names = ("conv%d.", "batchnorm%d.", "glu%d.", "cg%d.", "layernorm%d.")
+        sizes = [p.numel() for n, p in self.cnn.named_parameters()]
+        keep = [any(("cnn." + k % i) in n for i in range(n_layers) for k in names) for n, _ in self.cnn.named_parameters()]
+        # parameters() order is layer by layer, so the lower layers are a prefix
+        assert keep == sorted(keep, reverse=True)
+        return flat_layout(sizes[:sum(keep)])[1]
+
     def train(self, mode=True):
         """Override the default train() to freeze the BN parameters (CRNN.py:308-323; returns None like the reference)."""
         super(CRNN, self).train(mode)

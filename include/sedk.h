@@ -296,9 +296,10 @@ typedef struct {
 
 SEDK_API int sedk_crnn_forward(const sedk_crnn_plan* plan, void* stream);
 SEDK_API int sedk_crnn_backward(const sedk_crnn_plan* plan, void* stream);
-/* The backward in two halves, for callers that overlap a collective with it: phases = 1: heads + BiGRU (+ embedding fusion);
- * every gradient of those parameters is final when the call's work completes.  phases = 2: the CNN (must follow phase 1 of
- * the same forward).  phases = 3: both (= sedk_crnn_backward). */
+/* The backward in pieces, for callers that overlap a collective with it.  phases is a bit mask: 1 = heads + BiGRU
+ * (+ embedding fusion); 4 = conv layers [3, n_conv); 8 = conv layers [0, 3); 2 = 4 | 8 = the whole CNN.  Pieces must run in
+ * that order after one forward; every gradient of the parameters a call covered is final when its work completes.
+ * phases = 3 or 15: everything (= sedk_crnn_backward). */
 SEDK_API int sedk_crnn_backward_phase(const sedk_crnn_plan* plan, int phases, void* stream);
 SEDK_API int sedk_sizeof_crnn_plan(void);
 

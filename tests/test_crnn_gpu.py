@@ -225,3 +225,27 @@ def test_unsupported_configs_raise(dev):
 def _import_sedk_error():
     from desed_task_b200._lib import SedkError
     return SedkError
+
+
+def test_backward_in_phases_equals_the_one_call_backward(dev, feats):
+    """sedk_crnn_backward_phase (1 = heads + BiGRU, 4 = conv layers >= 3, 8 = conv layers < 3): the pieces a data-parallel
+    step interleaves with its gradient all-reduces add up to the one-call backward."""
+    cfg = dataclasses.replace(ocrnn.CFG_2023, dropout=0.0)
+    P = ocrnn.init_params(cfg, seed=42, trained_like=True)
+    net = build(cfg, P, dev, 0, specaugm_t_p=0.0, specaugm_f_p=0.0)
+    net.train()
+    x = feats.to(dev)
+    res = []
+    for phases in ((15,), (1, 4, 8), (1, 2), (3,)):
+        s, w, ws = net.forward_direct(x)
+        gs = torch.full_like(s, 1.0 / s.numel())
+        gw = torch.full_like(w, 1.0 / w.numel())
+        for ph in phases:
+            g = net.backward_direct(ws, gs, gw, phases=ph)
+        torch.cuda.synchronize()
+        res.append(g.clone())
+    assert res[0].abs().max().item() > 0
+    for r in res[1:]:
+        assert maxdiff(r, res[0]) <= 1e-5 * res[0].abs().max().item()
+    n_cnn, n_low = net.cnn_param_count(), net.cnn_lower_param_count(3)
+    assert 0 < n_low < n_cnn < res[0].numel()
