@@ -363,6 +363,12 @@ __device__ __forceinline__ uint32_t map_to_rank(const void* smem_ptr, uint32_t r
 __device__ __forceinline__ void st_cluster(uint32_t addr, float v) {
     asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory");
 }
+// remote store that signals the destination CTA's mbarrier when it lands (no cluster-wide fence, no L1 flush)
+__device__ __forceinline__ void st_async_f32(uint32_t addr, float v, uint32_t mbar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];\n" ::"r"(addr),
+                 "r"(__float_as_uint(v)), "r"(mbar)
+                 : "memory");
+}
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
 
@@ -373,12 +379,20 @@ gru_fwd_c3_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, 
                   float* __restrict__ hprev0, float* __restrict__ hprev1, int T, int save) {
     constexpr int H = HC, R = 6;
     __shared__ __align__(16) float h_s[2 * HPADC];
+    __shared__ __align__(8) uint64_t mbar[2];     // mbar[i]: "buffer i holds the h of all three CTAs" (H * 4 bytes per phase)
     const int tid = threadIdx.x;
     const int dir = blockIdx.y;
     const int b = blockIdx.x / CSC;
     const uint32_t crank = cluster_rank();
     const int l8 = tid & 7;
     const int ub = (int)crank * HUC + (tid >> 3) * 2;
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        fence_mbar_init();
+        mbar_expect_tx(&mbar[1], H * 4);              // step 0 publishes into buffer 1 (waited for at step 1)
+        mbar_expect_tx(&mbar[0], H * 4);              // step 1 publishes into buffer 0 (waited for at step 2)
+    }
     const float* whh = dir ? whh1 : whh0;
     const float* bhh = dir ? bhh1 : bhh0;
 
@@ -417,9 +431,11 @@ gru_fwd_c3_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, 
     // where sub 0 publishes h_new: the same slot of buffer 1 in each of the three CTAs
     float* hloc = h_s + HPADC + u + 4 * (u / 96);
     uint32_t hw0 = map_to_rank(hloc, 0), hw1 = map_to_rank(hloc, 1), hw2 = map_to_rank(hloc, 2);
+    uint32_t mb0 = map_to_rank(&mbar[1], 0), mb1 = map_to_rank(&mbar[1], 1), mb2 = map_to_rank(&mbar[1], 2);
     float hval = 0.f;
     float gir = gp[0] + bhr, giz = gp[H] + bhz, gin = gp[2 * H];
-    // all three CTAs have zeroed their buffers before anyone writes remotely
+    // all three CTAs have zeroed their buffers and initialised their mbarriers before anyone writes remotely (the only
+    // cluster-wide barrier of the kernel; per step the hand-over is st.async -> mbarrier, see below)
     cluster_arrive();
     cluster_wait();
 
@@ -428,6 +444,13 @@ gru_fwd_c3_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, 
         if (step + 1 < T) {
             gp += gstep;
             nir = gp[0]; niz = gp[H]; nin = gp[2 * H];
+        }
+        if (step > 0) {
+            // buffer (step & 1) is complete when the 3 x 64 st.async of step - 1 have landed.  No "buffer free" signal is
+            // needed the other way: a CTA can only publish step s + 1 after it has received every CTA's step-s values,
+            // which each CTA sends after its own step-s reads of the buffer being overwritten.
+            mbar_wait(&mbar[step & 1], (uint32_t)((step - 1) >> 1) & 1u);
+            if (tid == 0 && step + 2 < T) mbar_expect_tx(&mbar[step & 1], H * 4);     // re-arm: waited for again at step + 2
         }
         float2 acc[R];
 #pragma unroll
@@ -458,12 +481,11 @@ gru_fwd_c3_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, 
         const float zg = lean_sigmoid(giz + sz);
         const float n = lean_tanh(fmaf(r, ghn, gin));
         const float hnew = fmaf(zg, hval - n, n);
-        if (sub == 0) {
-            st_cluster(hw0, hnew);
-            st_cluster(hw1, hnew);
-            st_cluster(hw2, hnew);
+        if (sub == 0 && step + 1 < T) {                          // nobody reads the h of the last step from shared memory
+            st_async_f32(hw0, hnew, mb0);
+            st_async_f32(hw1, hnew, mb1);
+            st_async_f32(hw2, hnew, mb2);
         }
-        cluster_arrive();
         if (do_a) *pa = sub == 0 ? hnew : (sub == 1 ? r : n);
         if (do_b) *pb = sub == 0 ? hval : (sub == 1 ? zg : ghn);
         pa += sa;
@@ -471,10 +493,12 @@ gru_fwd_c3_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, 
         hval = hnew;
         gir = nir + bhr; giz = niz + bhz; gin = nin;
         const int flip = (step & 1) ? -HPADC : HPADC;             // readers move to the buffer just written
+        const int mflip = (step & 1) ? 8 : -8;                    // mbar[1] -> mbar[0] -> mbar[1] ... (byte addresses)
         hrd += flip;
         hw0 -= 4 * flip; hw1 -= 4 * flip; hw2 -= 4 * flip;        // byte addresses
-        cluster_wait();
+        mb0 += mflip; mb1 += mflip; mb2 += mflip;
     }
+    // every st.async aimed at this CTA has been waited for (the last step publishes nothing): safe to exit
 }
 
 __global__ void __launch_bounds__(256, 1)
@@ -485,12 +509,20 @@ gru_bwd_c3_kernel(const float* __restrict__ gout, const float* __restrict__ whh0
                   float* __restrict__ gbih1, float* __restrict__ gbhh0, float* __restrict__ gbhh1, int T) {
     constexpr int H = HC, UPW = 8;
     __shared__ __align__(16) float dgh_s[2 * 3 * H];
+    __shared__ __align__(8) uint64_t mbar[2];     // mbar[i]: "buffer i holds d(r, z, hn) of all three CTAs" (3 H * 4 bytes)
     const int tid = threadIdx.x;
     const int dir = blockIdx.y;
     const int b = blockIdx.x / CSC;
     const uint32_t crank = cluster_rank();
     const int lane = tid & 31;
     const int ub = (int)crank * HUC + (tid >> 5) * UPW;
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        fence_mbar_init();
+        mbar_expect_tx(&mbar[0], 3 * H * 4);
+        mbar_expect_tx(&mbar[1], 3 * H * 4);
+    }
     const float* whh = dir ? whh1 : whh0;
     float* gbih = dir ? gbih1 : gbih0;
     float* gbhh = dir ? gbhh1 : gbhh0;
@@ -528,6 +560,7 @@ gru_bwd_c3_kernel(const float* __restrict__ gout, const float* __restrict__ whh0
     const ptrdiff_t sa = ts * 3 * H, sbs = ts * (sub == 0 ? 3 * H : H);
     const bool do_g = sub < 2;
     uint32_t dw0 = map_to_rank(dgh_s + um, 0), dw1 = map_to_rank(dgh_s + um, 1), dw2 = map_to_rank(dgh_s + um, 2);
+    uint32_t mb0 = map_to_rank(&mbar[0], 0), mb1 = map_to_rank(&mbar[0], 1), mb2 = map_to_rank(&mbar[0], 2);
     const float* drd = dgh_s + 18 * lane;
     float dh = 0.f;
     float p_go = gop[0], p_r = gsp[0], p_z = gsp[H], p_n = gsp[2 * H], p_ghn = gsp[3 * H], p_hp = hpp[0];
@@ -553,11 +586,10 @@ gru_bwd_c3_kernel(const float* __restrict__ gout, const float* __restrict__ whh0
         const float dr_pre = dn_pre * p_ghn * p_r * (1.0f - p_r);
         const float dhn = dn_pre * p_r;
         if (sub == 2) {
-            st_cluster(dw0, dr_pre); st_cluster(dw0 + 4 * H, dz_pre); st_cluster(dw0 + 8 * H, dhn);
-            st_cluster(dw1, dr_pre); st_cluster(dw1 + 4 * H, dz_pre); st_cluster(dw1 + 8 * H, dhn);
-            st_cluster(dw2, dr_pre); st_cluster(dw2 + 4 * H, dz_pre); st_cluster(dw2 + 8 * H, dhn);
+            st_async_f32(dw0, dr_pre, mb0); st_async_f32(dw0 + 4 * H, dz_pre, mb0); st_async_f32(dw0 + 8 * H, dhn, mb0);
+            st_async_f32(dw1, dr_pre, mb1); st_async_f32(dw1 + 4 * H, dz_pre, mb1); st_async_f32(dw1 + 8 * H, dhn, mb1);
+            st_async_f32(dw2, dr_pre, mb2); st_async_f32(dw2 + 4 * H, dz_pre, mb2); st_async_f32(dw2 + 8 * H, dhn, mb2);
         }
-        cluster_arrive();
         if (do_g) {
             *pa = sub == 0 ? dr_pre : dn_pre;
             *pb = sub == 0 ? dz_pre : dhn;
@@ -566,7 +598,14 @@ gru_bwd_c3_kernel(const float* __restrict__ gout, const float* __restrict__ whh0
         pb += sbs;
         sb_r += dr_pre; sb_z += dz_pre; sb_n += dn_pre; sb_hn += dhn;
         p_go = n_go; p_r = n_r; p_z = n_z; p_n = n_n; p_ghn = n_ghn; p_hp = n_hp;
-        cluster_wait();
+        {
+            // processed-step counter k = T - 1 - step: buffer k & 1, phase parity (k >> 1) & 1; re-armed for step k + 2.
+            // (No "buffer free" signal needed: a CTA publishes step k + 2 only after it has consumed every CTA's step k + 1
+            // values, which each CTA sends after its own step-k reads of this buffer.)
+            const int k = T - 1 - step;
+            mbar_wait(&mbar[k & 1], (uint32_t)(k >> 1) & 1u);
+            if (tid == 0 && k + 2 < T) mbar_expect_tx(&mbar[k & 1], 3 * H * 4);
+        }
         float2 acc[UPW];
 #pragma unroll
         for (int i = 0; i < UPW; i++) acc[i] = make_float2(0.f, 0.f);
@@ -586,8 +625,10 @@ gru_bwd_c3_kernel(const float* __restrict__ gout, const float* __restrict__ whh0
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         dh = dh_direct + s;
         const int flip = ((T - 1 - step) & 1) ? -3 * H : 3 * H;   // the next step's writes go to the other buffer
+        const int mflip = ((T - 1 - step) & 1) ? -8 : 8;
         drd += flip;
         dw0 += 4 * flip; dw1 += 4 * flip; dw2 += 4 * flip;
+        mb0 += mflip; mb1 += mflip; mb2 += mflip;
     }
     if (sub == 0 && gbih != nullptr) {
         atomicAdd(&gbih[um], sb_r);
