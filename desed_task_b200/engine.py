@@ -78,7 +78,9 @@ class TrainEngine:
         self.mel_buf = self.mel_bufs[0]
         self.logmel = torch.empty_like(self.mel_buf)
         self.labels_dev = None
-        self.emb_dev = torch.empty(B, *emb_shape, device=dev) if emb_shape else None
+        # embeddings are the largest per-step input (1.52 MB per clip): double-buffered like the audio, copied on the copy stream
+        self.emb_devs = [torch.empty(B, *emb_shape, device=dev) for _ in range(2)] if emb_shape else None
+        self.emb_dev = self.emb_devs[0] if emb_shape else None
         self.emb_mixed = torch.empty_like(self.emb_dev) if (emb_shape and self.recipe == "2024" and mixup_type) else None
         self.minmaxs = [torch.empty(B, 2, dtype=torch.int32, device=dev) for _ in range(2)]
         self.minmax = self.minmaxs[0]
@@ -172,7 +174,7 @@ class TrainEngine:
         if do_mix:
             check(L.sedk_minmax_init(ptr(self.minmax), B, s), "sedk_minmax_init")
         n = self.mel_buf[0].numel()
-        emb = self.emb_dev
+        emb = self.emb_dev = self.emb_devs[slot] if self.emb_devs is not None else None
         if do_mix:
             # mixup on the LINEAR mel (sed_trainer.py:296-301), fused with take_log + per-clip min/max
             check(L.sedk_feat_mix_log(ptr(self.mel_buf), ptr(self.perm), ptr(self.coef), ptr(self.logmel), B, n, 1, 1e-5,
@@ -327,6 +329,17 @@ class TrainEngine:
             fe.wait_event(ev_in)
         elif not inputs_ready:
             fe.wait_stream(cur)
+        ev_emb = None
+        if emb_host is not None:
+            if emb_host.is_cuda:
+                self.emb_devs[slot].copy_(emb_host, non_blocking=True)
+            else:
+                with torch.cuda.stream(self.copy_stream):
+                    if self.buf_free_ev[slot] is not None:
+                        self.copy_stream.wait_event(self.buf_free_ev[slot])     # the graph that last read this slot is done
+                    self.emb_devs[slot].copy_(emb_host, non_blocking=True)
+                    ev_emb = torch.cuda.Event()
+                    ev_emb.record(self.copy_stream)
         if self.labels_dev is None:
             self.labels_dev = torch.empty(labels_host.shape, device=dev)
             fe.wait_stream(cur)                                   # first step: allocations / table uploads on `cur`
@@ -349,10 +362,10 @@ class TrainEngine:
             self.slot_ev[slot] = ev_fe
         # ---- per-step device scalars (ONE copy of the pinned block) and labels / embeddings (current stream)
         self.labels_dev.copy_(labels_host, non_blocking=True)
-        if emb_host is not None:
-            self.emb_dev.copy_(emb_host, non_blocking=True)
         self.scal_dev.copy_(self.host_scal[r], non_blocking=True)
         cur.wait_event(ev_fe)
+        if ev_emb is not None:
+            cur.wait_event(ev_emb)
         # ---- forward / loss / backward (/ all-reduce / optimiser)
         in_graph_opt = self.graph_optimizer
         if not self.use_graph:
