@@ -53,7 +53,7 @@ class CrnnPlan(C.Structure):
                 ("x", vp), ("x_sb", i64), ("x_sm", i64), ("x_st", i64), ("minmax", vp), ("scaler_eps", f32),
                 ("specaug", vp), ("x0", vp),
                 ("conv", ConvLayer * SEDK_MAX_CONV), ("gru", GruLayer * SEDK_MAX_GRU_LAYERS),
-                ("emb", vp), ("emb_dim", C.c_int32), ("emb_T", C.c_int32), ("cat_w", vp), ("cat_b", vp),
+                ("emb", vp), ("emb_dim", C.c_int32), ("emb_T", C.c_int32), ("emb_mode", C.c_int32), ("cat_w", vp), ("cat_b", vp),
                 ("gcat_w", vp), ("gcat_b", vp), ("cat_in", vp), ("fused", vp), ("gfused", vp), ("dropstep", vp),
                 ("dense_w", vp), ("dense_b", vp), ("soft_w", vp), ("soft_b", vp),
                 ("gdense_w", vp), ("gdense_b", vp), ("gsoft_w", vp), ("gsoft_b", vp),

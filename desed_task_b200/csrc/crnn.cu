@@ -189,8 +189,9 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
     // ---------------- embedding fusion
     if (p->emb != nullptr) {
         SEDK_REQUIRE(p->cat_w && p->cat_b && p->cat_in && p->fused, "crnn: embedding fusion buffers missing");
+        SEDK_REQUIRE(p->emb_mode == 0 || p->emb_mode == 1, "crnn: unknown emb_mode %d", p->emb_mode);
         rc = launch_emb_concat(xr, p->emb, p->training ? p->dropstep : nullptr, p->cat_in, B, Tp, nb, p->emb_dim,
-                               p->emb_T, pdrop, p->seed, p->seed_dev, STREAM_EMB, s);
+                               p->emb_T, p->emb_mode, pdrop, p->seed, p->seed_dev, STREAM_EMB, s);
         if (rc) return rc;
         const int W = nb + p->emb_dim;
         // cat_tf (CRNN.py:294): [B T', nb + emb] x [nb, nb + emb]^T - on tcgen05 in the TF32 mode (K = 896 for BEATs embeddings)
@@ -200,6 +201,13 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
             rc = launch_gemm(0, 1, B * Tp, nb, W, 1.f, p->cat_in, W, p->cat_w, W, 0.f, p->fused, nb, p->cat_b, p->precision, s);
         if (rc) return rc;
         xr = p->fused;
+    } else if (p->training && p->dropstep != nullptr) {
+        // no embeddings (CRNN.py:295-301): dropstep span mask + dropout on the CNN output feed the GRU
+        SEDK_REQUIRE(p->cat_in, "crnn: dropstep without embeddings needs the cat_in workspace [B, T', nb]");
+        rc = launch_emb_concat(xr, nullptr, p->dropstep, p->cat_in, B, Tp, nb, 0, 0, 0, pdrop, p->seed, p->seed_dev,
+                               STREAM_EMB, s);
+        if (rc) return rc;
+        xr = p->cat_in;
     }
     // ---------------- BiGRU
     for (int l = 0; l < p->n_gru; l++) {
@@ -285,8 +293,9 @@ static int crnn_backward_impl(const sedk_crnn_plan* p, int phases, void* stream)
         SEDK_REQUIRE(G.gb_ih[0] && G.gb_ih[1] && G.gb_hh[0] && G.gb_hh[1], "crnn backward: GRU bias grads null");
         rc = launch_gru_seq_bwd(G.gout, G.w_hh, G.gates, G.hprev, G.gi, G.dghn, G.gb_ih, G.gb_hh, B, Tp, H, zb ? 1 : 0, s);
         if (rc) return rc;
-        const float* xin = l > 0 ? p->gru[l - 1].out : (p->emb ? p->fused : last.out);
-        float* gin = l > 0 ? p->gru[l - 1].gout : (p->emb ? p->gfused : last.gout);
+        const bool drop_only = p->emb == nullptr && p->dropstep != nullptr;      // CRNN.py:295-301
+        const float* xin = l > 0 ? p->gru[l - 1].out : (p->emb ? p->fused : (drop_only ? p->cat_in : last.out));
+        float* gin = l > 0 ? p->gru[l - 1].gout : ((p->emb || drop_only) ? p->gfused : last.gout);
         SEDK_REQUIRE(gin, "crnn backward: input-gradient buffer of GRU layer %d missing", l);
         // the weight-gradient GEMMs only feed the optimiser: side stream
         rc = l == p->n_gru - 1 ? fk.begin() : fk.sync_side_to_main();
@@ -331,6 +340,11 @@ static int crnn_backward_impl(const sedk_crnn_plan* p, int phases, void* stream)
         }
     }
     // ---------------- embedding fusion
+    if (p->emb == nullptr && p->dropstep != nullptr) {
+        SEDK_REQUIRE(p->gfused && last.gout, "crnn backward: dropstep gradient buffers missing");
+        rc = launch_emb_concat_bwd(p->gfused, p->dropstep, last.gout, B, Tp, nb, 0, pdrop, p->seed, p->seed_dev, STREAM_EMB, s);
+        if (rc) return rc;
+    }
     if (p->emb != nullptr) {
         SEDK_REQUIRE(p->gcat_w && p->gcat_b && p->gfused && last.gout, "crnn backward: fusion gradient buffers missing");
         const int W = nb + p->emb_dim;

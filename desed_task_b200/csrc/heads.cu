@@ -335,8 +335,8 @@ __global__ void sed_loss_finalize(float* losses, const float* sums, int B, int C
 // cat[b,t,:] = dropout( [ x[b,t,:] (x-span masked) , mean_{tau in window(t)} emb[b,:,tau] (e-span masked) ] )
 __global__ void __launch_bounds__(256)
 emb_concat_kernel(const float* __restrict__ x, const float* __restrict__ emb, const int32_t* __restrict__ dropstep,
-                  float* __restrict__ cat, int T, int nb, int E, int Te, uint32_t thresh, float inv_keep, uint64_t seed,
-                  const uint64_t* __restrict__ seed_dev, uint64_t stream_id) {
+                  float* __restrict__ cat, int T, int nb, int E, int Te, int mode, uint32_t thresh, float inv_keep,
+                  uint64_t seed, const uint64_t* __restrict__ seed_dev, uint64_t stream_id) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int W = nb + E;
@@ -353,12 +353,21 @@ emb_concat_kernel(const float* __restrict__ x, const float* __restrict__ emb, co
             const int e = e0 + r, t = t0 + tx;
             float v = 0.f;
             if (e < E && t < T) {
-                const int st = (int)(((int64_t)t * Te) / T);
-                const int en = (int)((((int64_t)(t + 1)) * Te + T - 1) / T);
                 const float* ep = emb + ((size_t)b * E + e) * Te;
-                float s = 0.f;
-                for (int q = st; q < en; q++) s += ep[q];
-                v = s / (float)(en - st);
+                if (mode == 1) {
+                    // aggregation_type="interpolate" (CRNN.py:270-278): F.interpolate(mode="nearest-exact") along time,
+                    // src = min(floor((dst + 0.5) * (float)(Te / T)), Te - 1) with ATen's float scale
+                    const float scale = (float)Te / (float)T;
+                    int q = (int)floorf((float)(((double)t + 0.5) * (double)scale));
+                    v = ep[q < Te - 1 ? q : Te - 1];
+                } else {
+                    // aggregation_type="pool1d" (CRNN.py:280-283): adaptive_avg_pool1d windows
+                    const int st = (int)(((int64_t)t * Te) / T);
+                    const int en = (int)((((int64_t)(t + 1)) * Te + T - 1) / T);
+                    float s = 0.f;
+                    for (int q = st; q < en; q++) s += ep[q];
+                    v = s / (float)(en - st);
+                }
                 if (t >= es && t < ee) v = 0.f;
             }
             tile[r][tx] = v;
@@ -466,14 +475,14 @@ int launch_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, 
 }
 
 int launch_emb_concat(const float* x, const float* emb, const int32_t* dropstep, float* cat, int B, int T, int nb,
-                      int emb_dim, int emb_T, float p, uint64_t seed, const uint64_t* seed_dev, uint64_t stream_id,
+                      int emb_dim, int emb_T, int mode, float p, uint64_t seed, const uint64_t* seed_dev, uint64_t stream_id,
                       cudaStream_t s) {
     SEDK_PROF("emb_concat", s);
     const uint32_t thresh = p > 0.f ? drop_threshold(p) : 0u;
     const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
     dim3 grid(cdiv(T, 32), cdiv(emb_dim, 32) + cdiv(nb, 32), B);
-    emb_concat_kernel<<<grid, 256, 0, s>>>(x, emb, dropstep, cat, T, nb, emb_dim, emb_T, thresh, inv_keep, seed, seed_dev,
-                                           stream_id);
+    emb_concat_kernel<<<grid, 256, 0, s>>>(x, emb, dropstep, cat, T, nb, emb_dim, emb_T, mode, thresh, inv_keep, seed,
+                                           seed_dev, stream_id);
     SEDK_LAUNCH_CHECK("emb_concat_kernel");
     return SEDK_OK;
 }

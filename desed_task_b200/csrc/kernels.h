@@ -144,9 +144,11 @@ int launch_heads_bwd(const float* x, const float* dw, const float* sw, const uin
 // y = keep ? x/(1-p) : 0 (stream-indexed Philox mask); used forward and backward
 int launch_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev,
                    uint64_t stream_id, cudaStream_t s);
-// adaptive_avg_pool1d + concat + dropout for the embedding fusion (CRNN.py:280-294) and its backward (x part only)
+// time-aggregation (mode 0: adaptive_avg_pool1d, 1: nearest-exact interpolate) + dropstep span masks + concat + dropout for
+// the embedding fusion (CRNN.py:270-294) and its backward (x part only).  emb_dim = 0: the embedding-free branch
+// (CRNN.py:295-301: dropstep mask + dropout on the CNN output)
 int launch_emb_concat(const float* x, const float* emb, const int32_t* dropstep, float* cat, int B, int T, int nb,
-                      int emb_dim, int emb_T, float p, uint64_t seed, const uint64_t* seed_dev, uint64_t stream_id,
+                      int emb_dim, int emb_T, int mode, float p, uint64_t seed, const uint64_t* seed_dev, uint64_t stream_id,
                       cudaStream_t s);
 int launch_emb_concat_bwd(const float* gcat, const int32_t* dropstep, float* gx, int B, int T, int nb, int emb_dim,
                           float p, uint64_t seed, const uint64_t* seed_dev, uint64_t stream_id, cudaStream_t s);

@@ -120,9 +120,15 @@ class _Workspace:
                                       "reference only warns and flattens (CRNN.py:237-242)" % F)
         self.Tp, self.nb = T, cin
         in_dim = cin
+        if emb_shape is None and model.dropstep_recurrent:
+            # CRNN.py:295-301: dropstep mask + dropout on the CNN output, no embeddings
+            self.cat_in = new(B, T, cin)
+            self.gfused = new(B, T, cin)
+            plan.cat_in, plan.gfused = _vp(self.cat_in), _vp(self.gfused)
         if emb_shape is not None:
             E, Te = emb_shape
             plan.emb_dim, plan.emb_T = E, Te
+            plan.emb_mode = 1 if model.aggregation_type == "interpolate" else 0
             self.cat_in = new(B, T, cin + E)
             self.fused = new(B, T, cin)
             self.gfused = new(B, T, cin)
@@ -349,10 +355,8 @@ class CRNN(nn.Module):
             return "multi-head nclass"
         if self.nclass > 32:
             return "nclass > 32"
-        if self.dropstep_recurrent and not self.use_embeddings:
-            return "dropstep_recurrent > 0 without embeddings (CRNN.py:295-301)"
-        if self.use_embeddings and self.aggregation_type != "pool1d":
-            return "aggregation_type=%r (kernels implement the shipped 'pool1d')" % self.aggregation_type
+        if self.use_embeddings and self.aggregation_type not in ("pool1d", "interpolate"):
+            return "aggregation_type=%r (kernels implement 'pool1d' and 'interpolate')" % self.aggregation_type
         return None
 
     def _precision(self):
@@ -475,7 +479,8 @@ class CRNN(nn.Module):
         seed = (torch.initial_seed() * 1000003 + self._fwd_count * 7919 + self._instance * 104729) & 0xFFFFFFFFFFFFFFFF
         specaug = self._specaug_spans(ws, B, n_mels, n_frames, seed) if training else None
         dropstep = None
-        if training and self.use_embeddings and self.dropstep_recurrent:
+        if training and self.dropstep_recurrent:
+            # with embeddings: spans for x and for the embeddings (CRNN.py:288-293); without: the x span only (:295-301)
             dropstep = self._dropstep_spans(ws, B, ws.Tp, seed)
         # autograd works in both modes, as in the reference: an eval-mode forward with grad enabled (BN-frozen fine-tuning,
         # saliency, THOP-style profiling) saves its activations and backpropagates through running-statistics BatchNorm

@@ -261,13 +261,16 @@ typedef struct {
     /* optional embedding fusion (aggregation_type="pool1d", CRNN.py:280-294) */
     const float* emb;               /* [B, emb_dim, emb_T] or NULL                             */
     int32_t emb_dim, emb_T;
+    int32_t emb_mode;               /* aggregation_type: 0 "pool1d" (CRNN.py:280-283), 1 "interpolate" (nearest-exact, :270-278) */
     const float* cat_w;             /* [nb, nb+emb_dim]                                        */
     const float* cat_b;
     float *gcat_w, *gcat_b;
     float* cat_in;                  /* [B,T',nb+emb_dim] workspace (after dropout)             */
     float* fused;                   /* [B,T',nb] workspace                                     */
     float* gfused;
-    const int32_t* dropstep;        /* int32 [B][4] x_start,x_end,e_start,e_end or NULL        */
+    const int32_t* dropstep;        /* int32 [B][4] x_start,x_end,e_start,e_end or NULL.  Without embeddings (emb NULL) the
+                                       x span + dropout are applied to the CNN output (CRNN.py:295-301; needs cat_in
+                                       [B,T',nb] and gfused) */
     /* heads (CRNN.py:152-178) */
     const float* dense_w;           /* [C, 2H] */
     const float* dense_b;

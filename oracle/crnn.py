@@ -115,6 +115,21 @@ def draw_specaugment(B, n_f, n_t, f_l=10, f_p=0.2, t_l=5, t_p=0.2, device=None):
     return spec
 
 
+def draw_dropstep(B, frames, length, p, with_embeddings, device=None):
+    """The span draws of the `dropstep` TimeMasking(length, iid_masks=True, p) in CRNN.forward (CRNN.py:288-301), in the
+    reference's RNG order: the span for x first, then (embedding branch only) the span for the embeddings.
+    Returns dict(x_start, x_end[, e_start, e_end]) or None when the mask parameter rounds to < 1 (no draw happens)."""
+    param = length if p == 1.0 else min(length, int(frames * p))
+    if param < 1:
+        return None
+    out = {}
+    for tag in ("x", "e") if with_embeddings else ("x",):
+        value = torch.rand(B, device=device) * param
+        min_value = torch.rand(B, device=device) * (frames - value)
+        out[tag + "_start"], out[tag + "_end"] = min_value.long(), min_value.long() + value.long()
+    return out
+
+
 def apply_specaugment(x, spec):
     """CRNN.py:207-219: 'freq' mask (TimeMasking on the transposed tensor) then time mask, fill 0.0.
     spec = dict(f_start, f_end, t_start, t_end) int64 [B] (already drawn)."""
@@ -218,8 +233,12 @@ def crnn_forward(params, x, cfg=CFG_2023, training=False, embeddings=None, class
     if collect is not None:
         collect["cnn_out"] = x
     if cfg.use_embeddings:
-        assert cfg.aggregation_type == "pool1d"
-        emb = F.adaptive_avg_pool1d(embeddings, frames).transpose(1, 2)   # CRNN.py:280-283
+        if cfg.aggregation_type == "interpolate":                           # CRNN.py:270-278
+            emb = F.interpolate(embeddings.unsqueeze(1), size=(embeddings.shape[1], frames),
+                                mode="nearest-exact").squeeze(1).transpose(1, 2)
+        else:
+            assert cfg.aggregation_type == "pool1d"
+            emb = F.adaptive_avg_pool1d(embeddings, frames).transpose(1, 2)   # CRNN.py:280-283
         if training and cfg.dropstep_recurrent and dropstep is not None:
             xm = span_mask(frames, dropstep["x_start"], dropstep["x_end"])
             em = span_mask(frames, dropstep["e_start"], dropstep["e_end"])
@@ -234,6 +253,11 @@ def crnn_forward(params, x, cfg=CFG_2023, training=False, embeddings=None, class
         x = F.linear(cat, params["cat_tf.weight"], params["cat_tf.bias"])  # CRNN.py:294
         if collect is not None:
             collect["fused"] = x
+    elif training and cfg.dropstep_recurrent and dropstep is not None:     # CRNN.py:295-301 (no embeddings)
+        xm = span_mask(frames, dropstep["x_start"], dropstep["x_end"])
+        x = x.masked_fill(xm[:, :, None], 0.0)
+        if cfg.dropout > 0:
+            x = x * emb_drop_mask / (1.0 - cfg.dropout) if emb_drop_mask is not None else F.dropout(x, cfg.dropout, True)
     gru = gru_loop if gru_impl == "loop" else gru_aten
     x = gru(x, params, "rnn.rnn.", cfg.n_RNN_cell, cfg.n_layers_RNN)       # CRNN.py:303
     if collect is not None:

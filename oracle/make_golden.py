@@ -231,6 +231,51 @@ def main():
         vgold[f"grad_conv3_w_{vname}"] = net_v.cnn.cnn.conv3.weight.grad[::8, ::8].numpy()
         vgold[f"grad_conv0_b_{vname}"] = net_v.cnn.cnn.conv0.bias.grad.numpy()
         report[f"variant_{vname}"] = f"loss equal, max rel grad diff = {gmax:.2e}"
+    # aggregation_type="interpolate" (CRNN.py:270-278) and dropstep_recurrent with / without embeddings (CRNN.py:288-301);
+    # dropstep draws: the reference under torch.manual_seed(s), the oracle's draw_dropstep under the same seed
+    gE = torch.Generator().manual_seed(7)
+    emb_v = torch.randn(2, 768, 496, generator=gE)
+    for vname, ycfg_base, ocfg_base, over, ocfg_over, use_emb in [
+            ("interpolate", cfg24, ocrnn.CFG_2024, dict(aggregation_type="interpolate"), dict(aggregation_type="interpolate"), True),
+            ("dropstep_emb", cfg24, ocrnn.CFG_2024, dict(dropstep_recurrent=0.3, dropstep_recurrent_len=16),
+             dict(dropstep_recurrent=0.3), True),
+            ("dropstep_noemb", cfg23, ocrnn.CFG_2023, dict(dropstep_recurrent=0.3, dropstep_recurrent_len=16),
+             dict(dropstep_recurrent=0.3), False)]:
+        ocfg_v = dataclasses.replace(ocfg_base, dropout=0.0, **ocfg_over)
+        P = ocrnn.init_params(ocfg_v, seed=42, trained_like=True)
+        net_v = CRNN(**dict(ycfg_base["net"], dropout=0.0, specaugm_t_p=0.0, specaugm_f_p=0.0,
+                            **dict(dict(dropstep_recurrent=0.0), **over)))
+        net_v.load_state_dict(P, strict=True)
+        net_v.train()
+        kw = dict(embeddings=emb_v) if use_emb else {}
+        torch.manual_seed(99)
+        s_ref, w_ref = net_v(feats, **kw)
+        torch.manual_seed(99)
+        ds = ocrnn.draw_dropstep(2, 156, 16, 0.3, use_emb) if "dropstep" in vname else None
+        yv = (torch.rand(s_ref.shape, generator=torch.Generator().manual_seed(11)) < 0.1).float()
+        loss_ref = torch.nn.BCELoss()(s_ref, yv) + torch.nn.BCELoss()(w_ref, (yv.sum(-1) > 0).float())
+        loss_ref.backward()
+        Pt = {k: (v.clone().requires_grad_(True) if ocrnn.is_float_param(k) else v.clone()) for k, v in P.items()}
+        s_or, w_or = ocrnn.crnn_forward(Pt, feats, ocfg_v, True, dropstep=ds, **kw)
+        loss_or = otr.bce(s_or, yv) + otr.bce(w_or, (yv.sum(-1) > 0).float())
+        loss_or.backward()
+        assert (s_ref - s_or).abs().max().item() < 2e-6 and abs(loss_ref.item() - loss_or.item()) < 1e-6, vname
+        gscale = max(p.grad.abs().max().item() for p in net_v.parameters())
+        gmax = 0.0
+        for n, p in net_v.named_parameters():
+            if re.fullmatch(r"cnn\.cnn\.conv\d\.bias", n):
+                continue
+            gmax = max(gmax, (p.grad - Pt[n].grad).abs().max().item() / max(p.grad.abs().max().item(), 1e-2 * gscale))
+        assert gmax < 2e-4, (vname, gmax)
+        if ds is not None:
+            assert int((ds["x_end"] - ds["x_start"]).max()) > 0
+            for k, v in ds.items():
+                vgold[f"{vname}_{k}"] = v.numpy()
+        vgold[f"strong_{vname}"] = s_ref.detach().numpy()
+        vgold[f"weak_{vname}"] = w_ref.detach().numpy()
+        vgold[f"loss_{vname}"] = np.float32(loss_ref.item())
+        vgold[f"labels_{vname}"] = yv.numpy()
+        report[f"variant_{vname}"] = f"posteriors / loss equal, max rel grad diff = {gmax:.2e}"
     vgold["labels_strong"] = ys_v.numpy()
     np.savez(os.path.join(OUT, "variants.npz"), **vgold)
 

@@ -231,7 +231,17 @@ def test_modules_deepcopy_and_pickle_after_use():
     assert b._instance == a._instance + 1 and copy.deepcopy(a)._instance > b._instance
 
 
-def test_silently_diverging_configurations_raise():
+def test_configuration_coverage_is_explicit():
+    """What the kernels cover is accepted, everything else is named by _unsupported() (and raises at the first forward): no
+    configuration silently computes something else than the reference."""
     from desed_task_b200.nnet.CRNN import CRNN
-    net = CRNN(**dict(CONTRACT["nets"]["2023"]["config"], dropstep_recurrent=0.3))
-    assert "dropstep_recurrent" in net._unsupported()
+    c23, c24 = CONTRACT["nets"]["2023"]["config"], CONTRACT["nets"]["2024"]["config"]
+    for cfg in (c23, c24, dict(c23, dropstep_recurrent=0.3), dict(c24, dropstep_recurrent=0.3),
+                dict(c24, aggregation_type="interpolate"), dict(c23, activation="cg"), dict(c23, activation="Relu"),
+                dict(c23, activation="leakyrelu"), dict(c23, freeze_bn=True), dict(c23, train_cnn=False)):
+        assert CRNN(**cfg)._unsupported() is None, cfg
+    for cfg, word in ((dict(c24, aggregation_type="frame"), "aggregation_type"), (dict(c23, normalization="layer"), "normalization"),
+                      (dict(c23, rnn_type="BLSTM"), "rnn_type"), (dict(c23, attention=False), "attention"),
+                      (dict(c23, n_RNN_cell=100), "n_RNN_cell"), (dict(c23, dropout_recurrent=0.1), "dropout_recurrent"),
+                      (dict(c23, activation="tanh"), "activation")):
+        assert word in CRNN(**cfg)._unsupported(), cfg

@@ -214,3 +214,57 @@ def test_gru_192_cluster_kernel_agrees_with_first_generation(dev, precision, tol
         finally:
             lib().sedk_set_option(b"gru_v3", 1)
     _compare(res[1], res[0], tol_out, tol_grad)
+
+
+@pytest.mark.parametrize("vname", ["interpolate", "dropstep_emb", "dropstep_noemb"])
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [(1, 2e-5, 2e-3), (0, 1e-3, 5e-2)])
+def test_embedding_aggregation_and_dropstep_variants(dev, vname, precision, tol_out, tol_grad):
+    """aggregation_type="interpolate" (nearest-exact, CRNN.py:270-278) and dropstep_recurrent with (CRNN.py:288-293) and
+    without (CRNN.py:295-301) embeddings.  interpolate: posteriors / loss against the fixture minted from the live reference.
+    dropstep: the device draws its own spans (sedk_mask_spans); they are read back and injected into the oracle (whose
+    dropstep branch is pinned to the reference under a shared torch seed in oracle/make_golden.py)."""
+    from oracle import trainer as otr
+    from tests.util import golden
+    g = golden("variants")
+    use_emb = vname != "dropstep_noemb"
+    base = ocrnn.CFG_2024 if use_emb else ocrnn.CFG_2023
+    over = dict(aggregation_type="interpolate") if vname == "interpolate" else dict(dropstep_recurrent=0.3)
+    cfg = dataclasses.replace(base, dropout=0.0, **over)
+    P = ocrnn.init_params(cfg, seed=42, trained_like=True)
+    kw = dict(specaugm_t_p=0.0, specaugm_f_p=0.0, dropstep_recurrent=0.0)
+    kw.update(over)
+    if "dropstep" in vname:
+        kw["dropstep_recurrent_len"] = 16
+    net = build(cfg, P, dev, precision, **kw)
+    net.train()
+    x = ofe.features(gen_wave(0, 2))
+    emb = torch.randn(2, 768, 496, generator=torch.Generator().manual_seed(7)) if use_emb else None
+    ys = torch.from_numpy(g["labels_" + vname])
+    yw = (ys.sum(-1) > 0).float()
+    s, w = net(x.to(dev), embeddings=None if emb is None else emb.to(dev))
+    loss = torch.nn.functional.binary_cross_entropy(s, ys.to(dev)) + torch.nn.functional.binary_cross_entropy(w, yw.to(dev))
+    loss.backward()
+    ds = None
+    if vname == "interpolate":
+        assert maxdiff(s, torch.from_numpy(g["strong_interpolate"])) < tol_out
+        assert maxdiff(w, torch.from_numpy(g["weak_interpolate"])) < tol_out
+        assert abs(loss.item() - float(g["loss_interpolate"])) < 10 * tol_out
+    else:
+        sp = list(net._ws.values())[0].dropstep_buf.cpu().long()            # [B, 4] = x_start, x_end, e_start, e_end
+        ds = dict(x_start=sp[:, 0], x_end=sp[:, 1], e_start=sp[:, 2], e_end=sp[:, 3])
+        assert 0 < int((sp[:, 1] - sp[:, 0]).max()) < 16 and sp.min() >= 0 and sp.max() <= 156
+    Pt = {k: (v.clone().requires_grad_(True) if ocrnn.is_float_param(k) else v.clone()) for k, v in P.items()}
+    so, wo = ocrnn.crnn_forward(Pt, x, cfg, True, embeddings=emb, dropstep=ds)
+    assert maxdiff(s, so) < tol_out and maxdiff(w, wo) < tol_out
+    if ds is not None:
+        with torch.no_grad():
+            s_plain, _ = ocrnn.crnn_forward(P, x, cfg, True, embeddings=emb)
+        assert maxdiff(so, s_plain) > 20 * tol_out                            # the spans matter
+    (otr.bce(so, ys) + otr.bce(wo, yw)).backward()
+    gscale = max(Pt[n].grad.abs().max().item() for n in ocrnn.param_names(P))
+    for n, p in net.named_parameters():
+        ref = Pt[n].grad
+        if ".conv" in n and n.endswith(".bias"):
+            continue
+        err = (p.grad.cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-2 * gscale)
+        assert err < tol_grad, (vname, n, err)
