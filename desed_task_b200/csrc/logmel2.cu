@@ -2,9 +2,9 @@
 // stays in the library as the A/B baseline behind option "logmel_v2" = 0).  What changed, from the ncu profile of the first
 // generation (168 registers and 94 KB of shared memory per 4-warp CTA -> 8 warps per SM, issue slots 34 % busy, 3 460
 // warp-instructions per frame):
-//   * 3 CTAs (12 warps) per SM: the Hamming window and the W_2048 untangle twiddles are read through L1 (__ldg, coalesced)
-//     instead of living in every CTA's shared memory, and the magnitude buffer aliases the FFT exchange buffer
-//     -> 61 KB per CTA;
+//   * 4 CTAs (16 warps) per SM: 128 registers per thread (no spills), and the Hamming window, the W_1024 step twiddles and
+//     the W_2048 untangle twiddles are read through L1 (__ldg, coalesced, 24 KB shared by every warp of the SM) instead
+//     of living in every CTA's shared memory; the magnitude buffer aliases the FFT exchange buffer -> 53 KB per CTA;
 //   * packed fp32 arithmetic (FADD2 / FFMA2 / FMUL2) for the 160 butterflies of the two in-register 32-point FFTs and the
 //     window multiply: half the issue slots for the same flops;
 //   * the real-FFT untangle works on conjugate pairs: X[k] and X[1024 - k] share Xe[k] and T = W^k Xo[k]
@@ -121,14 +121,13 @@ __device__ __forceinline__ int reflect_idx(int i, int L) {
 
 struct SmemLayout {
     int chunk_floats;
-    size_t off_tw32, off_chunk, off_tile, off_warp, off_bar, total;
+    size_t off_chunk, off_tile, off_warp, off_bar, total;
 };
 __host__ __device__ inline SmemLayout make_layout(int hop, int n_mels) {
     SmemLayout s;
     s.chunk_floats = ((FR - 1) * hop + kNfft + 8 + 3) & ~3;
     size_t o = 0;
     s.off_bar = o;     o += 16;
-    s.off_tw32 = o;    o += kHalf * 8;
     s.off_chunk = o;   o += (size_t)s.chunk_floats * 4;
     s.off_tile = o;    o += (size_t)FR * n_mels * 4;
     o = (o + 15) & ~(size_t)15;
@@ -137,7 +136,7 @@ __host__ __device__ inline SmemLayout make_layout(int hop, int n_mels) {
     return s;
 }
 
-__global__ void __launch_bounds__(NW * 32, 3)
+__global__ void __launch_bounds__(NW * 32, 4)
 logmel2_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tables tab, float* __restrict__ out,
               int64_t out_sb, int64_t out_sm, int64_t out_st, int log_mode, float amin, float db_lo, float db_hi,
               uint32_t* __restrict__ minmax, int n_groups_per_clip) {
@@ -147,7 +146,7 @@ logmel2_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tab
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lay.off_bar);
     const float2* g_window2 = reinterpret_cast<const float2*>(tab.window);      // read through L1 (coalesced)
     const float2* g_tw2048 = reinterpret_cast<const float2*>(tab.tw2048);
-    float2* s_tw32 = reinterpret_cast<float2*>(smem + lay.off_tw32);
+    const float2* g_tw32 = reinterpret_cast<const float2*>(tab.tw32x32);
     float* s_chunk = reinterpret_cast<float*>(smem + lay.off_chunk);
     float* s_tile = reinterpret_cast<float*>(smem + lay.off_tile);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -155,7 +154,6 @@ logmel2_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tab
     float2* s_x = reinterpret_cast<float2*>(wbase);                   // 32 x 33 exchange, later Z[1024]
     float* s_mag = reinterpret_cast<float*>(wbase);                   // |X[k]|, k = 0..1024: aliases s_x once Z is in registers
 
-    for (int i = threadIdx.x; i < kHalf; i += blockDim.x) s_tw32[i] = reinterpret_cast<const float2*>(tab.tw32x32)[i];
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -215,7 +213,7 @@ logmel2_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tab
             static_for<0, 32>([&](auto ii) {
                 constexpr int i = decltype(ii)::value;
                 constexpr int k1 = bitrev5(i);
-                float2 w = s_tw32[k1 * 32 + lane];
+                const float2 w = __ldg(g_tw32 + k1 * 32 + lane);
                 float2 a = v[i];
                 s_x[k1 * SROW + lane] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
             });

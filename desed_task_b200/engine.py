@@ -65,6 +65,12 @@ class TrainEngine:
             self.world = torch.distributed.get_world_size(process_group)
         # the gradient all-reduce and the fused EMA + Adam kernel are captured in the same CUDA graph as forward / backward
         self.graph_optimizer = bool(graph_optimizer) and use_graph
+        # data-parallel all-reduce schedule: "split" = three slices overlapped with the backward (sedk_crnn_backward_phase),
+        # "single" = one all-reduce of the flat gradient after the backward (both inside the graph); env SEDK_AR_MODE
+        import os
+        self.ar_mode = os.environ.get("SEDK_AR_MODE", "split")
+        if self.ar_mode == "eager":
+            self.graph_optimizer = False
         self.grad_clip = grad_clip
         self.emb_shape = emb_shape
         self.class_masks = class_masks
@@ -213,7 +219,7 @@ class TrainEngine:
                                  ptr(labels_weak) if n_w > 0 else None, B, self.C, strong.shape[2], n_s, n_w,
                                  self.cons_row0, self.cons_kind, 0.0, ptr(self.cw), ptr(self.losses), ptr(self.gstrong),
                                  ptr(self.gweak), s), "sedk_sed_loss_ex")
-        if self.world > 1 and self.graph_optimizer:
+        if self.world > 1 and self.graph_optimizer and self.ar_mode == "split":
             # data parallel: the RNN / head half of the flat gradient is final after phase 1 - its all-reduce runs on a
             # side stream (a parallel branch of the graph) underneath the CNN backward; the CNN half follows at the end
             # (2 MB), then the 128-channel conv layers (98 % of the CNN parameters) under the backward of the three
