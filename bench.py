@@ -381,13 +381,18 @@ def run_ours(args):
 
     def timed(use_host, steps, warm, sample=True):
         src = (host_a, host_y, host_e) if use_host else (dev_a, dev_y, dev_e)
+        # the clock sampler (an nvidia-smi child polling every 100 ms) is started BEFORE the warm-up: its start-up (NVML
+        # initialisation, driver locks) perturbs the first ~50 ms, which would otherwise be the whole timed region
+        sampler = ClockSampler(local)
+        if rank == 0 and sample:
+            sampler.start()
+            t_wait = time.time()
+            while not sampler.rows and time.time() - t_wait < 3.0:
+                time.sleep(0.02)
         for i in range(warm):
             one(eng, src, i)
         barrier()
         launches0, replays0 = L.sedk_launch_count(), eng.replays
-        sampler = ClockSampler(local)
-        if rank == 0 and sample:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
@@ -482,8 +487,9 @@ def run_ours(args):
                              "heads, losses, optimizer fp32",
                 "l2": "inputs rotate over %d distinct batches (%.0f MB > L2); per-step activations ~0.6 GB"
                       % (NBUF, NBUF * B * L_SAMPLES * 4 / 1e6),
-                "cuda_graph": "forward + loss + backward + gradient all-reduce + fused EMA/Adam: one graph replay per step",
-                "settle_steps": args.settle, "allreduce": os.environ.get("SEDK_AR_MODE", "split"),
+                "cuda_graph": "forward + loss + backward (+ fused EMA/Adam at N = 1): one graph replay per step; at N > 1 the "
+                              "NCCL all-reduce and the optimizer kernel follow the graph as eager launches",
+                "settle_steps": args.settle, "allreduce": os.environ.get("SEDK_AR_MODE", "eager"),
                 "overlap": "front end of step k+1 runs on its own stream concurrently with step k's graph (ping-pong "
                            "log-mel buffers); weight-gradient GEMMs on a side branch of the graph"}
         out = {

@@ -65,11 +65,17 @@ class TrainEngine:
             self.world = torch.distributed.get_world_size(process_group)
         # the gradient all-reduce and the fused EMA + Adam kernel are captured in the same CUDA graph as forward / backward
         self.graph_optimizer = bool(graph_optimizer) and use_graph
-        # data-parallel all-reduce schedule: "split" = three slices overlapped with the backward (sedk_crnn_backward_phase),
-        # "single" = one all-reduce of the flat gradient after the backward (both inside the graph); env SEDK_AR_MODE
+        # data-parallel all-reduce schedule (env SEDK_AR_MODE).  "eager" (default): the graph ends with the backward, one NCCL
+        # all-reduce of the flat gradient and the fused EMA + Adam kernel follow as eager launches (issued while the graph
+        # still runs).  "split": three slices reduced inside the graph underneath the rest of the backward
+        # (sedk_crnn_backward_phase); "single": one in-graph all-reduce after the backward.  Measured on 2 x B200
+        # (profiles/r2_allreduce_modes.txt): eager +24 us per step over N = 1, split +42 us, single +48 us - NCCL kernels
+        # captured into the graph cost more than they hide on a 2.2 ms step, so the overlapped schedules stay optional.
         import os
-        self.ar_mode = os.environ.get("SEDK_AR_MODE", "split")
-        if self.ar_mode == "eager":
+        self.ar_mode = os.environ.get("SEDK_AR_MODE", "eager")
+        if self.ar_mode not in ("eager", "split", "single"):
+            raise ValueError("SEDK_AR_MODE must be eager, split or single")
+        if self.world > 1 and self.ar_mode == "eager":
             self.graph_optimizer = False
         self.grad_clip = grad_clip
         self.emb_shape = emb_shape
