@@ -267,12 +267,14 @@ def family_table(prof, NP, B, net, pk):
     return out
 
 
-def make_batches(nbuf, B, seed, pin, nclass=10, emb=False):
+def make_batches(nbuf, B, seed, pin, nclass=10, emb=False, pcm16=False, emb_pooled=False):
     g = torch.Generator().manual_seed(seed)
     n_s = B // 2
     audio, labels, embs = [], [], []
     for _ in range(nbuf):
         a = torch.randn(B, L_SAMPLES, generator=g) * 0.1
+        if pcm16:                                              # the stored format of the datasets: 16-bit PCM
+            a = (a * 32768.0).round().clamp(-32768, 32767).to(torch.int16)
         y = (torch.rand(B, nclass, 156, generator=g) < 0.1).float()
         y[n_s:, :, 1:] = 0.0                                   # weak clips: clip-level tags live in frame 0
         if pin:
@@ -280,7 +282,8 @@ def make_batches(nbuf, B, seed, pin, nclass=10, emb=False):
         audio.append(a)
         labels.append(y)
         if emb:
-            e = torch.randn(B, *EMB_SHAPE, generator=g)
+            # reference storage: fp32 [768, 496]; --emb-pooled: pre-pooled to the CRNN's 156 frames, bf16 (embeddings.py)
+            e = torch.randn(B, EMB_SHAPE[0], 156, generator=g).bfloat16() if emb_pooled else torch.randn(B, *EMB_SHAPE, generator=g)
             embs.append(e.pin_memory() if pin else e)
     if emb:
         return audio, labels, embs
@@ -347,19 +350,23 @@ def run_ours(args):
         sched = ExponentialWarmup(opt, 1e-3, 50 * 250)
 
     def new_engine(use_graph, distributed=True):
+        adt = torch.int16 if args.pcm16 else torch.float32
         if is_inf:
-            return InferEngine(student, mel, B, L_SAMPLES, median_window=7, use_graph=use_graph)
+            return InferEngine(student, mel, B, L_SAMPLES, median_window=7, use_graph=use_graph, audio_dtype=adt)
         if is_2024:
             return TrainEngine(student, mel, split, L_SAMPLES, opt=opt, scheduler=sched, teacher=teacher,
                                mixup_type="soft", use_graph=use_graph, distributed=distributed, grad_clip=5.0,
-                               emb_shape=EMB_SHAPE, class_masks=class_masks_2024(split).to(dev), recipe="2024")
+                               emb_shape=(EMB_SHAPE[0], 156) if args.emb_pooled else EMB_SHAPE,
+                               emb_dtype=torch.bfloat16 if args.emb_pooled else torch.float32,
+                               class_masks=class_masks_2024(split).to(dev), recipe="2024", audio_dtype=adt)
         return TrainEngine(student, mel, split, L_SAMPLES, opt=opt, scheduler=sched, teacher=teacher,
                            mixup_type="soft" if teacher is not None else None, use_graph=use_graph,
-                           distributed=distributed)
+                           distributed=distributed, audio_dtype=adt)
 
     eng = new_engine(True)
     NBUF = max(4, -(-192 // B) + 1) if not is_2024 else 4          # distinct batches: > 126 MB of audio (+ embeddings) > L2
-    mk = make_batches(NBUF, B, 42 + rank, pin=True, nclass=nclass, emb=is_2024)
+    mk = make_batches(NBUF, B, 42 + rank, pin=True, nclass=nclass, emb=is_2024, pcm16=args.pcm16,
+                      emb_pooled=args.emb_pooled)
     host_a, host_y = mk[0], mk[1]
     host_e = mk[2] if is_2024 else [None] * NBUF
     dev_a = [a.to(dev) for a in host_a]
@@ -480,7 +487,7 @@ def run_ours(args):
         if world == 1 and not args.quick:
             cpu = cpu_baseline(wl, B, budget_s=20.0)
             lib_bar = library_bar(dev, wl, B, dev_a, dev_y)
-        h2d = B * L_SAMPLES * 4 + (0 if is_inf else B * nclass * 156 * 4 + 64) + (B * EMB_SHAPE[0] * EMB_SHAPE[1] * 4 if is_2024 else 0)
+        h2d = B * L_SAMPLES * (2 if args.pcm16 else 4) + (0 if is_inf else B * nclass * 156 * 4 + 64) + ((B * EMB_SHAPE[0] * 156 * 2 if args.emb_pooled else B * EMB_SHAPE[0] * EMB_SHAPE[1] * 4) if is_2024 else 0)
         d2h = (B * nclass * 156 * 4 + B * nclass * 4) if is_inf else 64
         cfg = workload_config(wl, B, world)             # identical in both arms; arm-specific detail goes to `implementation`
         impl = {"precision": "front end fp32; CRNN GEMMs TF32 (fp32 storage / accumulate); recurrence, BN statistics, "
@@ -489,6 +496,8 @@ def run_ours(args):
                       % (NBUF, NBUF * B * L_SAMPLES * 4 / 1e6),
                 "cuda_graph": "forward + loss + backward (+ fused EMA/Adam at N = 1): one graph replay per step; at N > 1 the "
                               "NCCL all-reduce and the optimizer kernel follow the graph as eager launches",
+                "embeddings": ("pre-pooled bf16 [768, 156]" if args.emb_pooled else "fp32 [768, 496]") if is_2024 else None,
+                "audio_input": "int16 PCM (x / 32768 in the front end)" if args.pcm16 else "fp32 waveform",
                 "settle_steps": args.settle, "allreduce": os.environ.get("SEDK_AR_MODE", "eager"),
                 "overlap": "front end of step k+1 runs on its own stream concurrently with step k's graph (ping-pong "
                            "log-mel buffers); weight-gradient GEMMs on a side branch of the graph"}
@@ -537,6 +546,8 @@ def library_bar(dev, workload, B, dev_a, dev_y):
         return {"unavailable": "the 2024 library leg is not wired (needs the Lightning trainer's batch plumbing)"}
     try:
         from baseline import reference_arm
+        if dev_a[0].dtype == torch.int16:               # the reference consumes the normalised fp32 waveform
+            dev_a = [a.float() / 32768.0 for a in dev_a]
         res = reference_arm.gpu_library_baseline(dev, workload, B, dev_a, dev_y, steps=15, warmup=4)
     except Exception as e:                                           # noqa: BLE001
         return {"unavailable": str(e).splitlines()[0][:200]}
@@ -671,6 +682,9 @@ def main():
     ap.add_argument("--workload", default="supervised", choices=sorted(DEFAULT_BATCH))
     ap.add_argument("--batch", type=int, default=None, help="clips per GPU (default: 24 / 48 / 24 / 64 by workload)")
     ap.add_argument("--repeats", type=int, default=5, help="extra timed K-step blocks for the min / median spread")
+    ap.add_argument("--pcm16", action="store_true", help="feed 16-bit PCM audio (bit-identical front end, half the H2D bytes)")
+    ap.add_argument("--emb-pooled", action="store_true", dest="emb_pooled",
+                    help="dcase2024: feed embeddings in the pre-pooled bf16 storage format (240 KB instead of 1.52 MB per clip)")
     ap.add_argument("--settle", type=int, default=20, help="extra untimed steps before the warm-up (after graph capture)")
     ap.add_argument("--quick", action="store_true", help="development runs: skip the CPU / GPU-library baseline legs")
     args = ap.parse_args()

@@ -75,6 +75,7 @@ _SIGS = {
     "sedk_profile_enable": (i32, [i32]),
     "sedk_profile_report": (i32, [C.c_char_p, i32]),
     "sedk_logmel_fwd": (i32, [vp, i32, i32, C.POINTER(MelTables), vp, i64, i64, i64, i32, f32, f32, f32, vp, vp]),
+    "sedk_logmel_fwd_i16": (i32, [vp, i32, i32, C.POINTER(MelTables), vp, i64, i64, i64, i32, f32, f32, f32, vp, vp]),
     "sedk_minmax_init": (i32, [vp, i32, vp]),
     "sedk_minmax_decode": (i32, [vp, vp, i32, vp]),
     "sedk_feat_mix_log": (i32, [vp, vp, vp, vp, i32, i64, i32, f32, f32, f32, vp, vp]),
@@ -90,6 +91,9 @@ _SIGS = {
     "sedk_sumsq": (i32, [vp, i64, vp, vp]),
     "sedk_mask_spans": (i32, [vp, i32, i32, i32, i32, i32, u64, vp, u64, vp]),
     "sedk_median_filter": (i32, [vp, vp, i32, i32, i32, i64, i64, i64, i64, i64, i64, vp, vp]),
+    "sedk_pool_embeddings": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "sedk_bf16_to_f32": (i32, [vp, vp, i64, vp]),
+    "sedk_encode_strong": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     "sedk_decode_events": (i32, [vp, i32, i32, i32, i64, i64, i64, vp, i32, vp, vp, vp, i32, vp]),
     "sedk_crnn_forward": (i32, [C.POINTER(CrnnPlan), vp]),
     "sedk_crnn_backward": (i32, [C.POINTER(CrnnPlan), vp]),

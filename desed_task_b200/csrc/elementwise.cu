@@ -2,6 +2,7 @@
 // additive noise, fused Adam + EMA over a flat parameter buffer, median filter.
 // All are streaming kernels: 128-bit loads/stores where alignment allows, grid sized in multiples of the SM count.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace sedk {
 namespace {
@@ -321,6 +322,62 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(int32_t* __restric
     if (tid == 1023) v[n] = part[1023];
 }
 
+// ---- strong-label encoding (ManyHotEncoder.encode_strong_df, desed_task/utils/encoder.py:80-171) ------------------------
+// One CTA per clip: labels[b] (C x T, zeroed first) <- for every event of the clip IN ORDER: labels[b][class][onset:offset] =
+// value (a later event overwrites an earlier one, as the reference's sequential `y[onset:offset, i] = ...` does).
+__global__ void __launch_bounds__(256)
+encode_strong_kernel(const int32_t* __restrict__ ev, const float* __restrict__ val, const int32_t* __restrict__ clip_off,
+                     float* __restrict__ labels, int C, int T) {
+    const int b = blockIdx.x;
+    float* y = labels + (size_t)b * C * T;
+    for (int i = threadIdx.x; i < C * T; i += blockDim.x) y[i] = 0.f;
+    __syncthreads();
+    for (int e = clip_off[b]; e < clip_off[b + 1]; e++) {
+        const int c = ev[4 * e + 1];
+        int on = ev[4 * e + 2], off = ev[4 * e + 3];
+        on = on < 0 ? 0 : on;
+        off = off > T ? T : off;
+        const float v = val != nullptr ? val[e] : 1.0f;
+        if (c >= 0 && c < C)
+            for (int t = on + (int)threadIdx.x; t < off; t += blockDim.x) y[(size_t)c * T + t] = v;
+        __syncthreads();
+    }
+}
+
+// ---- embedding storage format --------------------------------------------------------------------------
+// Time-aggregation of frame embeddings [B, E, Te] -> [B, E, T] with exactly the arithmetic of the fusion kernel
+// (emb_concat_kernel: adaptive_avg_pool1d windows summed left to right, or nearest-exact), written as fp32 or bf16.
+// Stored this way (768 x 156 bf16 = 240 KB per clip instead of 768 x 496 fp32 = 1.52 MB) the embeddings are read by the
+// unchanged fusion path: pooling a [.., 156] input to 156 frames is the identity.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+pool_embeddings_kernel(const float* __restrict__ emb, void* __restrict__ out, int E, int Te, int T, int mode, int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i % T);
+        const int64_t be = i / T;
+        const float* ep = emb + be * Te;
+        float v;
+        if (mode == 1) {
+            const float scale = (float)Te / (float)T;
+            int q = (int)floorf((float)(((double)t + 0.5) * (double)scale));
+            v = ep[q < Te - 1 ? q : Te - 1];
+        } else {
+            const int st = (int)(((int64_t)t * Te) / T);
+            const int en = (int)((((int64_t)(t + 1)) * Te + T - 1) / T);
+            float s = 0.f;
+            for (int q = st; q < en; q++) s += ep[q];
+            v = s / (float)(en - st);
+        }
+        if (BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+        else reinterpret_cast<float*>(out)[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __bfloat162float(in[i]);
+}
+
 inline dim3 grid2(int64_t n, int B, int per_thread = 4) {
     int64_t blocks = (n + (int64_t)EW_THREADS * per_thread - 1) / ((int64_t)EW_THREADS * per_thread);
     int64_t cap = (int64_t)num_sms() * 8 / (B > 0 ? B : 1) + 1;
@@ -536,5 +593,38 @@ extern "C" int sedk_decode_events(const float* scores, int B, int C, int T, int6
     decode_events_kernel<false><<<blocks, EW_THREADS, 0, s>>>(scores, B, C, T, sb, sc, st, thresholds, n_th, n_frames,
                                                              nullptr, offsets, events, capacity);
     SEDK_LAUNCH_CHECK("decode_events_kernel<write>");
+    return SEDK_OK;
+}
+
+extern "C" int sedk_encode_strong(const int32_t* events, const float* values, const int32_t* clip_offsets, float* labels, int B,
+                                  int C, int T, void* stream) {
+    using namespace sedk;
+    SEDK_REQUIRE(events && clip_offsets && labels && B > 0 && C > 0 && T > 0, "sedk_encode_strong: bad arguments");
+    SEDK_PROF("encode_strong", (cudaStream_t)stream);
+    encode_strong_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(events, values, clip_offsets, labels, C, T);
+    SEDK_LAUNCH_CHECK("encode_strong_kernel");
+    return SEDK_OK;
+}
+
+extern "C" int sedk_pool_embeddings(const float* emb, void* out, int B, int E, int Te, int T, int mode, int out_bf16,
+                                    void* stream) {
+    using namespace sedk;
+    SEDK_REQUIRE(emb && out && B > 0 && E > 0 && Te > 0 && T > 0 && (mode == 0 || mode == 1), "sedk_pool_embeddings: bad arguments");
+    SEDK_PROF("pool_embeddings", (cudaStream_t)stream);
+    const int64_t total = (int64_t)B * E * T;
+    if (out_bf16)
+        pool_embeddings_kernel<true><<<grid1(total, 1), EW_THREADS, 0, (cudaStream_t)stream>>>(emb, out, E, Te, T, mode, total);
+    else
+        pool_embeddings_kernel<false><<<grid1(total, 1), EW_THREADS, 0, (cudaStream_t)stream>>>(emb, out, E, Te, T, mode, total);
+    SEDK_LAUNCH_CHECK("pool_embeddings_kernel");
+    return SEDK_OK;
+}
+
+extern "C" int sedk_bf16_to_f32(const void* in, float* out, int64_t n, void* stream) {
+    using namespace sedk;
+    SEDK_REQUIRE(in && out && n > 0, "sedk_bf16_to_f32: bad arguments");
+    SEDK_PROF("bf16_to_f32", (cudaStream_t)stream);
+    bf16_to_f32_kernel<<<grid1(n, 4), EW_THREADS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, n);
+    SEDK_LAUNCH_CHECK("bf16_to_f32_kernel");
     return SEDK_OK;
 }

@@ -300,6 +300,23 @@ logmel_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tabl
 namespace sedk {
 int launch_logmel_v2(const float* wave, int B, int L, const sedk_mel_tables* tab, float* out, int64_t out_sb, int64_t out_sm,
                      int64_t out_st, int log_mode, float amin, float db_lo, float db_hi, uint32_t* minmax, cudaStream_t stream);
+int launch_logmel_v2_i16(const int16_t* wave, int B, int L, const sedk_mel_tables* tab, float* out, int64_t out_sb,
+                         int64_t out_sm, int64_t out_st, int log_mode, float amin, float db_lo, float db_hi, uint32_t* minmax,
+                         cudaStream_t stream);
+}
+
+extern "C" int sedk_logmel_fwd_i16(const int16_t* wave, int B, int L, const sedk_mel_tables* tab, float* out, int64_t out_sb,
+                                   int64_t out_sm, int64_t out_st, int log_mode, float amin, float db_lo, float db_hi,
+                                   uint32_t* minmax, void* stream) {
+    using namespace sedk;
+    SEDK_PROF("logmel", (cudaStream_t)stream);
+    SEDK_REQUIRE(wave && tab && out, "sedk_logmel_fwd_i16: null pointer");
+    SEDK_REQUIRE(B > 0, "sedk_logmel_fwd_i16: B must be positive (got %d)", B);
+    SEDK_REQUIRE(L > kHalf, "sedk_logmel_fwd_i16: reflect padding needs L > %d samples (got %d)", kHalf, L);
+    SEDK_REQUIRE(tab->hop > 0 && tab->hop <= kNfft, "sedk_logmel_fwd_i16: hop %d out of range", tab->hop);
+    SEDK_REQUIRE(tab->n_mels > 0 && tab->n_mels <= 256, "sedk_logmel_fwd_i16: n_mels %d out of range", tab->n_mels);
+    return launch_logmel_v2_i16(wave, B, L, tab, out, out_sb, out_sm, out_st, log_mode, amin, db_lo, db_hi, minmax,
+                                (cudaStream_t)stream);
 }
 
 extern "C" int sedk_logmel_fwd(const float* wave, int B, int L, const sedk_mel_tables* tab, float* out, int64_t out_sb,

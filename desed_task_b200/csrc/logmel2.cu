@@ -136,8 +136,20 @@ __host__ __device__ inline SmemLayout make_layout(int hop, int n_mels) {
     return s;
 }
 
+// PCM sample types: fp32 waveforms, or the int16 the datasets are stored in (f2, input pipeline): torchaudio.load hands the
+// reference x / 32768 as fp32 (an exact power-of-two scale), so converting in the load path is bit-identical and halves
+// both the H2D copy and the HBM read (320 KB instead of 640 KB per clip).
+__device__ __forceinline__ float pcm(float v) { return v; }
+__device__ __forceinline__ float pcm(int16_t v) { return (float)v * (1.0f / 32768.0f); }
+__device__ __forceinline__ float2 pcm_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 pcm_pair(const int16_t* p) {
+    const short2 q = *reinterpret_cast<const short2*>(p);
+    return make_float2((float)q.x * (1.0f / 32768.0f), (float)q.y * (1.0f / 32768.0f));
+}
+
+template <typename TS>
 __global__ void __launch_bounds__(NW * 32, 4)
-logmel2_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tables tab, float* __restrict__ out,
+logmel2_kernel(const TS* __restrict__ wave, int B, int L, int T, sedk_mel_tables tab, float* __restrict__ out,
               int64_t out_sb, int64_t out_sm, int64_t out_st, int log_mode, float amin, float db_lo, float db_hi,
               uint32_t* __restrict__ minmax, int n_groups_per_clip) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -147,7 +159,8 @@ logmel2_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tab
     const float2* g_window2 = reinterpret_cast<const float2*>(tab.window);      // read through L1 (coalesced)
     const float2* g_tw2048 = reinterpret_cast<const float2*>(tab.tw2048);
     const float2* g_tw32 = reinterpret_cast<const float2*>(tab.tw32x32);
-    float* s_chunk = reinterpret_cast<float*>(smem + lay.off_chunk);
+    TS* s_chunk = reinterpret_cast<TS*>(smem + lay.off_chunk);
+    constexpr int AL = 16 / (int)sizeof(TS);          // samples per 16-byte unit of the bulk copy
     float* s_tile = reinterpret_cast<float*>(smem + lay.off_tile);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* wbase = smem + lay.off_warp + (size_t)warp * (32 * SROW * 8);
@@ -166,20 +179,23 @@ logmel2_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tab
         const int b = grp / n_groups_per_clip;
         const int f0 = (grp - b * n_groups_per_clip) * FR;
         const int nfr = min(FR, T - f0);
-        const float* clip = wave + (size_t)b * L;
+        const TS* clip = wave + (size_t)b * L;
         // samples [c0, c1) of this clip cover every (reflected) index the group's frames touch
-        int c0 = f0 * hop - kHalf - 4;
-        c0 = c0 < 0 ? 0 : (c0 & ~3);
+        int c0 = f0 * hop - kHalf - AL;
+        c0 = c0 < 0 ? 0 : (c0 & ~(AL - 1));
         int c1 = min(L, (f0 + nfr - 1) * hop + kHalf);
-        if (c1 - c0 > lay.chunk_floats) c1 = c0 + lay.chunk_floats;   // cannot happen for hop % 4 == 0; guards odd hops
+        // capacity of the staging buffer in samples (int16 samples take half the bytes); cannot be exceeded for hop % 4 == 0,
+        // the clamp guards odd hops
+        const int cap = lay.chunk_floats * (4 / (int)sizeof(TS));
+        if (c1 - c0 > cap) c1 = c0 + cap;
         const int n_chunk = c1 - c0;
-        const float* src = clip + c0;
+        const TS* src = clip + c0;
         const bool bulk_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-        const int n_bulk = bulk_ok ? (n_chunk & ~3) : 0;
+        const int n_bulk = bulk_ok ? (n_chunk & ~(AL - 1)) : 0;
         if (n_bulk > 0 && threadIdx.x == 0) {
             fence_proxy_async();
-            mbar_expect_tx(bar, (uint32_t)n_bulk * 4u);
-            bulk_g2s(s_chunk, src, (uint32_t)n_bulk * 4u, bar);
+            mbar_expect_tx(bar, (uint32_t)n_bulk * (uint32_t)sizeof(TS));
+            bulk_g2s(s_chunk, src, (uint32_t)n_bulk * (uint32_t)sizeof(TS), bar);
         }
         for (int i = n_bulk + threadIdx.x; i < n_chunk; i += blockDim.x) s_chunk[i] = src[i];
         if (n_bulk > 0) {
@@ -194,9 +210,10 @@ logmel2_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tab
             float2 v[32];
             const bool interior = (s0 >= 0) && (s0 + kNfft <= L) && (((s0 - c0) & 1) == 0);
             if (interior) {
-                const float2* xs = reinterpret_cast<const float2*>(s_chunk + (s0 - c0));
+                const TS* xs = s_chunk + (s0 - c0);
 #pragma unroll
-                for (int n1 = 0; n1 < 32; n1++) v[n1] = __fmul2_rn(xs[32 * n1 + lane], __ldg(g_window2 + 32 * n1 + lane));
+                for (int n1 = 0; n1 < 32; n1++)
+                    v[n1] = __fmul2_rn(pcm_pair(xs + 2 * (32 * n1 + lane)), __ldg(g_window2 + 32 * n1 + lane));
             } else {
 #pragma unroll
                 for (int n1 = 0; n1 < 32; n1++) {
@@ -205,7 +222,7 @@ logmel2_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tab
                     i0 = min(max(i0, 0), n_chunk - 1);
                     i1 = min(max(i1, 0), n_chunk - 1);
                     const float2 w = __ldg(g_window2 + (j >> 1));
-                    v[n1] = make_float2(s_chunk[i0] * w.x, s_chunk[i1] * w.y);
+                    v[n1] = make_float2(pcm(s_chunk[i0]) * w.x, pcm(s_chunk[i1]) * w.y);
                 }
             }
             // ---- step 1: lane = n2, FFT over n1; twiddle W_1024^{n2 k1}; transpose through smem
@@ -316,27 +333,42 @@ logmel2_kernel(const float* __restrict__ wave, int B, int L, int T, sedk_mel_tab
 }  // namespace v2
 }  // namespace
 
-int launch_logmel_v2(const float* wave, int B, int L, const sedk_mel_tables* tab, float* out, int64_t out_sb, int64_t out_sm,
-                     int64_t out_st, int log_mode, float amin, float db_lo, float db_hi, uint32_t* minmax, cudaStream_t stream) {
+template <typename TS>
+static int launch_logmel_v2_t(const TS* wave, int B, int L, const sedk_mel_tables* tab, float* out, int64_t out_sb,
+                              int64_t out_sm, int64_t out_st, int log_mode, float amin, float db_lo, float db_hi,
+                              uint32_t* minmax, cudaStream_t stream) {
     using namespace v2;
     const int T = 1 + L / tab->hop;
     const int groups = cdiv(T, FR);
     SmemLayout lay = make_layout(tab->hop, tab->n_mels);
     SEDK_REQUIRE(lay.total <= 227 * 1024, "sedk_logmel_fwd: hop %d needs %zu B of shared memory", tab->hop, lay.total);
-    int rc = opt_in_smem(logmel2_kernel, lay.total);
+    auto kern = logmel2_kernel<TS>;
+    int rc = opt_in_smem(kern, lay.total);
     if (rc != SEDK_OK) return rc;
     static int per_sm = 0;
     if (per_sm == 0) {
         int o = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, logmel2_kernel, NW * 32, lay.total);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, NW * 32, lay.total);
         per_sm = o < 1 ? 1 : o;
     }
     long long total = (long long)B * groups;
     int grid = (int)(total < (long long)num_sms() * per_sm ? total : (long long)num_sms() * per_sm);
-    logmel2_kernel<<<grid, NW * 32, lay.total, stream>>>(wave, B, L, T, *tab, out, out_sb, out_sm, out_st, log_mode, amin,
-                                                        db_lo, db_hi, minmax, groups);
+    kern<<<grid, NW * 32, lay.total, stream>>>(wave, B, L, T, *tab, out, out_sb, out_sm, out_st, log_mode, amin, db_lo, db_hi,
+                                              minmax, groups);
     SEDK_LAUNCH_CHECK("logmel2_kernel");
     return SEDK_OK;
+}
+
+int launch_logmel_v2(const float* wave, int B, int L, const sedk_mel_tables* tab, float* out, int64_t out_sb, int64_t out_sm,
+                     int64_t out_st, int log_mode, float amin, float db_lo, float db_hi, uint32_t* minmax, cudaStream_t stream) {
+    return launch_logmel_v2_t<float>(wave, B, L, tab, out, out_sb, out_sm, out_st, log_mode, amin, db_lo, db_hi, minmax, stream);
+}
+
+int launch_logmel_v2_i16(const int16_t* wave, int B, int L, const sedk_mel_tables* tab, float* out, int64_t out_sb,
+                         int64_t out_sm, int64_t out_st, int log_mode, float amin, float db_lo, float db_hi, uint32_t* minmax,
+                         cudaStream_t stream) {
+    return launch_logmel_v2_t<int16_t>(wave, B, L, tab, out, out_sb, out_sm, out_st, log_mode, amin, db_lo, db_hi, minmax,
+                                       stream);
 }
 
 }  // namespace sedk

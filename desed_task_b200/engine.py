@@ -30,8 +30,10 @@ class TrainEngine:
     def __init__(self, student, mel_spec, batch_sizes, n_samples, opt=None, scheduler=None, teacher=None,
                  ema_factor=0.999, const_max=2.0, mixup_type=None, use_graph=True, process_group=None,
                  grad_clip=0.0, emb_shape=None, class_masks=None, distributed=True, recipe="2023", mixup_prob=0.5,
-                 self_sup_loss="mse", graph_optimizer=True):
+                 self_sup_loss="mse", graph_optimizer=True, audio_dtype=torch.float32, emb_dtype=torch.float32):
         self.student, self.teacher, self.mel_spec = student, teacher, mel_spec
+        if audio_dtype not in (torch.float32, torch.int16):
+            raise ValueError("audio_dtype must be torch.float32 or torch.int16 (16-bit PCM, used as x / 32768)")
         self.batch_sizes = list(batch_sizes)
         self.recipe = str(recipe)
         if self.recipe == "2024":
@@ -84,7 +86,7 @@ class TrainEngine:
         dev, B = self.dev, self.B
         self.C = student.nclass
         self.T = mel_spec.n_frames(n_samples)
-        self.audio_dev = [torch.empty(B, n_samples, device=dev), torch.empty(B, n_samples, device=dev)]
+        self.audio_dev = [torch.empty(B, n_samples, device=dev, dtype=audio_dtype) for _ in range(2)]
         # the front end runs on its own stream into ping-pong buffers, so that step k+1's log-mel overlaps step k's graph
         self.mel_bufs = [torch.empty(B, mel_spec.n_mels, self.T, device=dev) for _ in range(2)]
         self.mel_buf = self.mel_bufs[0]
@@ -92,6 +94,9 @@ class TrainEngine:
         self.labels_dev = None
         # embeddings are the largest per-step input (1.52 MB per clip): double-buffered like the audio, copied on the copy stream
         self.emb_devs = [torch.empty(B, *emb_shape, device=dev) for _ in range(2)] if emb_shape else None
+        # bf16 storage format (desed_task_b200.embeddings.pool_embeddings): staged as bf16, upcast on the copy stream
+        self.emb_stage = [torch.empty(B, *emb_shape, device=dev, dtype=torch.bfloat16) for _ in range(2)] \
+            if (emb_shape and emb_dtype == torch.bfloat16) else None
         self.emb_dev = self.emb_devs[0] if emb_shape else None
         self.emb_mixed = torch.empty_like(self.emb_dev) if (emb_shape and self.recipe == "2024" and mixup_type) else None
         self.minmaxs = [torch.empty(B, 2, dtype=torch.int32, device=dev) for _ in range(2)]
@@ -343,13 +348,25 @@ class TrainEngine:
             fe.wait_stream(cur)
         ev_emb = None
         if emb_host is not None:
+            bf16 = emb_host.dtype == torch.bfloat16
+            if bf16 and self.emb_stage is None:
+                raise ValueError("bf16 embeddings need TrainEngine(emb_dtype=torch.bfloat16)")
             if emb_host.is_cuda:
-                self.emb_devs[slot].copy_(emb_host, non_blocking=True)
+                if bf16:
+                    check(lib().sedk_bf16_to_f32(ptr(emb_host.contiguous()), ptr(self.emb_devs[slot]), emb_host.numel(),
+                                                 stream_ptr()), "sedk_bf16_to_f32")
+                else:
+                    self.emb_devs[slot].copy_(emb_host, non_blocking=True)
             else:
                 with torch.cuda.stream(self.copy_stream):
                     if self.buf_free_ev[slot] is not None:
                         self.copy_stream.wait_event(self.buf_free_ev[slot])     # the graph that last read this slot is done
-                    self.emb_devs[slot].copy_(emb_host, non_blocking=True)
+                    if bf16:
+                        self.emb_stage[slot].copy_(emb_host, non_blocking=True)
+                        check(lib().sedk_bf16_to_f32(ptr(self.emb_stage[slot]), ptr(self.emb_devs[slot]),
+                                                     emb_host.numel(), stream_ptr()), "sedk_bf16_to_f32")
+                    else:
+                        self.emb_devs[slot].copy_(emb_host, non_blocking=True)
                     ev_emb = torch.cuda.Event()
                     ev_emb.record(self.copy_stream)
         if self.labels_dev is None:
@@ -423,9 +440,9 @@ class TrainEngine:
     def mel_spec_run(self, audio, log):
         tab = self.mel_spec.tables(audio.device)
         out = self.mel_buf
-        check(lib().sedk_logmel_fwd(ptr(audio), self.B, self.L, tab.struct, ptr(out), out.stride(0), out.stride(1),
-                                    out.stride(2), 1 if log else 0, 1e-5, -50.0, 80.0,
-                                    ptr(self.minmax) if log else None, stream_ptr()), "sedk_logmel_fwd")
+        fn = lib().sedk_logmel_fwd_i16 if audio.dtype == torch.int16 else lib().sedk_logmel_fwd
+        check(fn(ptr(audio), self.B, self.L, tab.struct, ptr(out), out.stride(0), out.stride(1), out.stride(2),
+                 1 if log else 0, 1e-5, -50.0, 80.0, ptr(self.minmax) if log else None, stream_ptr()), "sedk_logmel_fwd")
 
     def _snapshot(self):
         """Everything a step mutates besides its own outputs - BN running statistics, the seed counter, and (when the
@@ -463,7 +480,8 @@ class InferEngine:
     buffers) overlap the forward graph of batch k; the filtered scores [B, C, T'] and the clip-level posteriors [B, C] are
     read back into a ring of pinned host buffers.  Clips shard over ranks with no collective (ddp.shard_clip_range)."""
 
-    def __init__(self, model, mel_spec, batch, n_samples, median_window=7, use_graph=True, emb_shape=None, class_masks=None):
+    def __init__(self, model, mel_spec, batch, n_samples, median_window=7, use_graph=True, emb_shape=None, class_masks=None,
+                 audio_dtype=torch.float32):
         from .utils.postprocess import median_filter
         self._median = median_filter
         self.model, self.mel_spec = model, mel_spec
@@ -478,7 +496,7 @@ class InferEngine:
         self.win = torch.tensor(wins, dtype=torch.int32, device=dev)
         self.emb_shape, self.class_masks = emb_shape, class_masks
         B = self.B
-        self.audio_dev = [torch.empty(B, n_samples, device=dev) for _ in range(2)]
+        self.audio_dev = [torch.empty(B, n_samples, device=dev, dtype=audio_dtype) for _ in range(2)]
         self.mel_bufs = [torch.empty(B, mel_spec.n_mels, self.T, device=dev) for _ in range(2)]
         self.minmaxs = [torch.empty(B, 2, dtype=torch.int32, device=dev) for _ in range(2)]
         self.emb_dev = torch.empty(B, *emb_shape, device=dev) if emb_shape else None
@@ -525,9 +543,10 @@ class InferEngine:
             tab = self.mel_spec.tables(dev)
             out, mm = self.mel_bufs[slot], self.minmaxs[slot]
             check(lib().sedk_minmax_init(ptr(mm), B, stream_ptr()), "sedk_minmax_init")
-            check(lib().sedk_logmel_fwd(ptr(audio if resident else self.audio_dev[slot]), B, self.L, tab.struct, ptr(out),
-                                        out.stride(0), out.stride(1), out.stride(2), 1, 1e-5, -50.0, 80.0, ptr(mm),
-                                        stream_ptr()), "sedk_logmel_fwd")
+            src = audio if resident else self.audio_dev[slot]
+            fn = lib().sedk_logmel_fwd_i16 if src.dtype == torch.int16 else lib().sedk_logmel_fwd
+            check(fn(ptr(src), B, self.L, tab.struct, ptr(out), out.stride(0), out.stride(1), out.stride(2), 1, 1e-5, -50.0,
+                     80.0, ptr(mm), stream_ptr()), "sedk_logmel_fwd")
             ev_fe = torch.cuda.Event()
             ev_fe.record(fe)
         if not resident:

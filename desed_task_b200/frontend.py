@@ -145,12 +145,14 @@ class MelSpectrogram(nn.Module):
         return 1 + n_samples // self.hop_length
 
     def run(self, waveform, log=False, amin=1e-5, db_range=(-50.0, 80.0), minmax=None, time_major=False):
-        """waveform [..., L] cuda fp32 -> mel [..., n_mels, T] (a transposed view of a [.., T, n_mels] buffer when
-        time_major).  log=True fuses take_log; minmax (uint32 [B,2], initialised) receives per-clip min/max."""
+        """waveform [..., L] cuda fp32 - or int16 PCM, used as x / 32768 like torchaudio.load's normalisation (bit-identical
+        result, half the bytes) - -> mel [..., n_mels, T] (a transposed view of a [.., T, n_mels] buffer when time_major).
+        log=True fuses take_log; minmax (uint32 [B,2], initialised) receives per-clip min/max."""
         require_cuda(waveform)
         lead = waveform.shape[:-1]
         L = waveform.shape[-1]
-        w = waveform.reshape(-1, L).float().contiguous()
+        pcm16 = waveform.dtype == torch.int16
+        w = waveform.reshape(-1, L).contiguous() if pcm16 else waveform.reshape(-1, L).float().contiguous()
         B = w.shape[0]
         T = self.n_frames(L)
         tab = self.tables(w.device)
@@ -159,9 +161,9 @@ class MelSpectrogram(nn.Module):
             out = buf.transpose(1, 2)
         else:
             out = torch.empty(B, self.n_mels, T, device=w.device, dtype=torch.float32)
-        check(lib().sedk_logmel_fwd(ptr(w), B, L, tab.struct, ptr(out), out.stride(0), out.stride(1), out.stride(2),
-                                    1 if log else 0, amin, db_range[0], db_range[1], ptr(minmax), stream_ptr()),
-              "sedk_logmel_fwd")
+        fn = lib().sedk_logmel_fwd_i16 if pcm16 else lib().sedk_logmel_fwd
+        check(fn(ptr(w), B, L, tab.struct, ptr(out), out.stride(0), out.stride(1), out.stride(2),
+                 1 if log else 0, amin, db_range[0], db_range[1], ptr(minmax), stream_ptr()), "sedk_logmel_fwd")
         return out.reshape(lead + out.shape[1:]) if len(lead) != 1 else out
 
     def forward(self, waveform):

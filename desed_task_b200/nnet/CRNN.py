@@ -467,6 +467,9 @@ class CRNN(nn.Module):
         if self.use_embeddings:
             if embeddings is None:
                 raise ValueError("use_embeddings=True but no embeddings were given")
+            if embeddings.dtype == torch.bfloat16:          # the pre-pooled bf16 storage format (desed_task_b200.embeddings)
+                from ..embeddings import upcast
+                embeddings = upcast(embeddings)
             embeddings = embeddings.float().contiguous()
             emb_shape = (embeddings.shape[1], embeddings.shape[2])
         else:

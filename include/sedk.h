@@ -98,6 +98,13 @@ SEDK_API int sedk_logmel_fwd(const float* wave, int B, int L, const sedk_mel_tab
                     int64_t out_sm, int64_t out_st, int log_mode, float amin, float db_lo, float db_hi,
                     uint32_t* minmax, void* stream);
 
+/* Same front end on 16-bit PCM (the format the datasets are stored in): every sample is used as x / 32768, exactly what
+ * torchaudio.load hands the reference (desed_task/dataio/datasets.py:24-74), so the result is bit-identical to
+ * sedk_logmel_fwd on the normalised fp32 waveform while the H2D copy and the HBM read halve. */
+SEDK_API int sedk_logmel_fwd_i16(const int16_t* wave, int B, int L, const sedk_mel_tables* tab, float* out, int64_t out_sb,
+                        int64_t out_sm, int64_t out_st, int log_mode, float amin, float db_lo, float db_hi,
+                        uint32_t* minmax, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Elementwise feature ops.
  */
@@ -178,6 +185,24 @@ SEDK_API int sedk_median_filter(const float* scores, float* out, int B, int C, i
 SEDK_API int sedk_decode_events(const float* scores, int B, int C, int T, int64_t sb, int64_t sc, int64_t st,
                        const float* thresholds, int n_th, const int32_t* n_frames, int32_t* offsets, int32_t* events,
                        int capacity, void* stream);
+
+/* Embedding storage format.  The 2024 recipe stores BEATs frame embeddings as fp32 [768, 496] per clip
+ * (1.52 MB; recipes/dcase2024_task4_baseline/extract_embeddings.py:48-53, desed_task/dataio/datasets.py:221-228) and the
+ * CRNN pools them to its 156 frames in every forward (CRNN.py:280-283).  sedk_pool_embeddings does that aggregation once
+ * (mode 0: adaptive_avg_pool1d, 1: nearest-exact interpolate; the arithmetic of the fusion kernel, so the fp32 output is
+ * what the forward would compute) and writes [B, E, T] as fp32 or bf16 (240 KB per clip); sedk_bf16_to_f32 restores the
+ * working precision.  A pre-pooled tensor goes through the unchanged fusion path (pooling T -> T frames is the identity). */
+SEDK_API int sedk_pool_embeddings(const float* emb, void* out, int B, int E, int Te, int T, int mode, int out_bf16, void* stream);
+SEDK_API int sedk_bf16_to_f32(const void* in_bf16, float* out, int64_t n, void* stream);
+
+/* Strong-label encoding on the device: replaces the per-item pandas loop of
+ * ManyHotEncoder.encode_strong_df (desed_task/utils/encoder.py:80-171, called from desed_task/dataio/datasets.py:187-237).
+ * events int32 [n][4] = {clip, class, onset_frame, offset_frame} grouped by clip in their original order (frames computed by
+ * the caller exactly as the reference does: int(_time_to_frame(onset)), int(ceil(_time_to_frame(offset)))); values float[n]
+ * (the `confidence` column) or NULL for 1; clip_offsets int32 [B + 1].  labels [B, C, T] is overwritten: zero, then every
+ * event in order labels[b][class][onset:offset] = value (later events win, like the reference's sequential assignment). */
+SEDK_API int sedk_encode_strong(const int32_t* events, const float* values, const int32_t* clip_offsets, float* labels, int B,
+                       int C, int T, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * CRNN (desed_task/nnet/CRNN.py, CNN.py, RNN.py) - whole-network forward / backward on a caller-provided plan.

@@ -408,6 +408,28 @@ def main():
     np.savez(os.path.join(OUT, "decode.npz"), scores=dsc, thresholds=np.array(ths, np.float32),
              events=np.array(flat, np.float64), post=post)
 
+    # ------------------------------------------------------------------ strong-label encoding (f2)
+    rs = np.random.RandomState(21)
+    enc_events, enc_ref = [], []
+    for b in range(6):
+        evs = []
+        for _ in range(rs.randint(0, 9)):
+            on = float(rs.uniform(-0.5, 10.2))
+            evs.append([labels10[rs.randint(10)], on, on + float(rs.uniform(0.01, 4.0))])
+        if b == 1:
+            evs = [[l, o, f, float(rs.uniform(0.1, 1.0))] for l, o, f in evs]          # the `confidence` form
+        if b == 2:
+            evs += [["c3", 0.0, 10.0], ["c3", 2.0, 2.064], ["", 1.0, 2.0], ["c4", 9.99, 12.0], ["c5", 3.2, 3.2]]
+        y_ref = enc.encode_strong_df(evs)
+        y_or = opost.encode_strong(evs, labels10)
+        assert y_ref.shape == (156, 10) and np.array_equal(y_ref, y_or), b
+        enc_events.append(evs)
+        enc_ref.append(y_ref)
+    assert np.array_equal(enc._time_to_frame(np.linspace(-1, 11, 97)), opost.time_to_frame(np.linspace(-1, 11, 97)))
+    import json as _json
+    np.savez(os.path.join(OUT, "encode.npz"), events=np.array(_json.dumps(enc_events)), labels=np.stack(enc_ref))
+    report["encode"] = "oracle encode_strong == reference ManyHotEncoder.encode_strong_df on 6 clips (list and confidence forms)"
+
     with open(os.path.join(OUT, "PINNING.txt"), "w") as f:
         f.write("oracle pinned against the live reference (commit c6bcb45b) + torchaudio %s, torch %s\n"
                 % (__import__("torchaudio").__version__, torch.__version__))

@@ -76,3 +76,22 @@ def batched_decode(strong_preds, labels, thresholds=(0.5,), median_filter=7, **e
             for lab, on, of in decode_strong(c_scores > th, labels, **enc):
                 preds[th].append((j, lab, on, of))
     return np.stack(post), preds
+
+
+def time_to_frame(time, fs=16000, frame_hop=256, net_pooling=4, n_frames=156):
+    """ManyHotEncoder._time_to_frame, desed_task/utils/encoder.py:71-74."""
+    return np.clip(np.asarray(time, dtype=np.float64) * fs / frame_hop / net_pooling, a_min=0, a_max=n_frames)
+
+
+def encode_strong(events, labels, n_frames=156, **enc):
+    """ManyHotEncoder.encode_strong_df for the list-of-lists input ([label, onset, offset(, confidence)], encoder.py:139-159):
+    y[int(t2f(onset)) : int(ceil(t2f(offset))), class] = confidence or 1, events applied in order.  Returns [n_frames, C]."""
+    y = np.zeros((n_frames, len(labels)))
+    for e in events:
+        if e[0] == "":
+            continue
+        i = labels.index(e[0])
+        onset = int(time_to_frame(e[1], n_frames=n_frames, **enc))
+        offset = int(np.ceil(time_to_frame(e[2], n_frames=n_frames, **enc)))
+        y[onset:offset, i] = e[3] if len(e) == 4 else 1
+    return y

@@ -242,3 +242,44 @@ def test_batched_decode_preds_mirror(dev):
         assert list(df.columns) == ["event_label", "onset", "offset", "filename"]
         rows = [(int(f[4:-4]), l, on, of) for l, on, of, f in df.itertuples(index=False)]
         assert rows == want[th]
+
+
+def test_encode_strong_batch_matches_golden(dev):
+    """f2: batched strong-label encoding on the device == ManyHotEncoder.encode_strong_df (fixture from the live reference):
+    list and confidence forms, clipping at both clip ends, overlapping events (later wins), zero-length events, "" labels."""
+    import json
+    from desed_task_b200.dataio import encode_strong_batch
+    g = golden("encode")
+    events = json.loads(str(g["events"]))
+    labels = ["c%d" % i for i in range(10)]
+    y = encode_strong_batch(events, labels, dev)
+    assert y.shape == (len(events), 10, 156) and y.dtype == torch.float32
+    ref = torch.from_numpy(g["labels"]).float().transpose(1, 2)            # [B, T, C] -> [B, C, T]
+    assert torch.equal(y.cpu(), ref)
+    # an empty batch entry and a reused output buffer
+    y2 = encode_strong_batch([[], events[2]], labels, dev, out=torch.full((2, 10, 156), 7.0, device=dev))
+    assert float(y2[0].abs().sum()) == 0.0 and torch.equal(y2[1].cpu(), ref[2])
+
+
+def test_embedding_storage_format(dev):
+    """f3: pre-pooled embeddings.  fp32 pre-pooling reproduces adaptive_avg_pool1d / nearest-exact interpolate (so feeding the
+    pooled tensor to the CRNN is the reference's computation: pooling 156 -> 156 frames is the identity); bf16 storage is
+    that value rounded to nearest bf16 and `upcast` restores fp32 exactly."""
+    import torch.nn.functional as F
+    from desed_task_b200.embeddings import pool_embeddings, upcast
+    g = torch.Generator().manual_seed(3)
+    emb = torch.randn(3, 768, 496, generator=g)
+    p32 = pool_embeddings(emb.to(dev), 156, "pool1d", torch.float32)
+    ref = F.adaptive_avg_pool1d(emb, 156)
+    assert p32.shape == (3, 768, 156) and maxdiff(p32, ref) < 1e-6
+    assert maxdiff(pool_embeddings(p32, 156, "pool1d", torch.float32), p32) == 0.0          # identity on pooled input
+    pi = pool_embeddings(emb.to(dev), 156, "interpolate", torch.float32)
+    assert torch.equal(pi.cpu(), F.interpolate(emb.unsqueeze(1), size=(768, 156), mode="nearest-exact").squeeze(1))
+    p16 = pool_embeddings(emb.to(dev), 156, "pool1d", torch.bfloat16)
+    assert p16.dtype == torch.bfloat16 and torch.equal(p16.cpu(), p32.cpu().bfloat16())
+    assert torch.equal(upcast(p16).cpu(), p16.cpu().float())
+    for Te, T in ((496, 156), (100, 156), (157, 156), (1000, 39)):                          # other ratios, incl. upsampling
+        e = torch.randn(2, 8, Te, generator=g)
+        assert maxdiff(pool_embeddings(e.to(dev), T, "pool1d", torch.float32), F.adaptive_avg_pool1d(e, T)) < 1e-6
+        assert torch.equal(pool_embeddings(e.to(dev), T, "interpolate", torch.float32).cpu(),
+                           F.interpolate(e.unsqueeze(1), size=(8, T), mode="nearest-exact").squeeze(1))

@@ -101,3 +101,21 @@ def test_full_batch_properties(mel, dev):
     assert ((m2 - 2 * m1).abs() / m1.abs().clamp_min(1e-3)).max().item() < 1e-5
     m3 = mel(wave[5:6])
     assert torch.equal(m3[0], m1[5])
+
+
+@pytest.mark.parametrize("L", [160000, 16001, 4099])
+def test_int16_pcm_input_is_bit_identical_to_the_normalised_waveform(mel, dev, L):
+    """f2 (input pipeline): the front end reads the stored 16-bit PCM directly.  torchaudio.load hands the reference
+    x / 32768 in fp32 - an exact scale - so both routes must agree bit for bit (log-mel and per-clip min / max)."""
+    from desed_task_b200.frontend import new_minmax
+    g = torch.Generator().manual_seed(13)
+    pcm = torch.randint(-32768, 32768, (3, L), generator=g, dtype=torch.int32).to(torch.int16)
+    pcm[1] //= 50                                             # a quiet clip
+    wave = pcm.float() / 32768.0
+    mm_a, mm_b = new_minmax(3, dev), new_minmax(3, dev)
+    a = mel.run(pcm.to(dev), log=True, minmax=mm_a)
+    b = mel.run(wave.to(dev), log=True, minmax=mm_b)
+    assert a.dtype == torch.float32 and torch.equal(a, b) and torch.equal(mm_a, mm_b)
+    assert torch.equal(mel.run(pcm.to(dev)), mel.run(wave.to(dev)))          # linear mel too
+    ref = ofe.take_log(ofe.mel_spectrogram(wave))
+    assert maxdiff(a, ref) < TOL_DB

@@ -121,3 +121,12 @@ def test_decode_matches_golden():
     assert np.array_equal(post, g["post"])
     flat = [(ti, j, labels.index(lab), on, of) for ti, th in enumerate(ths) for j, lab, on, of in preds[th]]
     assert np.array_equal(np.array(flat, np.float64), g["events"])
+
+
+def test_encode_strong_matches_golden():
+    import json
+    g = golden("encode")
+    events = json.loads(str(g["events"]))
+    labels = ["c%d" % i for i in range(10)]
+    for evs, ref in zip(events, g["labels"]):
+        assert np.array_equal(opost.encode_strong(evs, labels), ref)

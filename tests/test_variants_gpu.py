@@ -268,3 +268,28 @@ def test_embedding_aggregation_and_dropstep_variants(dev, vname, precision, tol_
             continue
         err = (p.grad.cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-2 * gscale)
         assert err < tol_grad, (vname, n, err)
+
+
+def test_prepooled_embeddings_give_the_reference_forward(dev):
+    """f3: the 2024 network fed with embeddings pre-pooled to 156 frames (fp32) returns what it returns for the raw
+    [768, 496] embeddings (and what the oracle returns); the bf16 storage format equals the oracle run on the bf16-rounded
+    pooled embeddings."""
+    from desed_task_b200.embeddings import pool_embeddings
+    cfg = ocrnn.CFG_2024
+    P = ocrnn.init_params(cfg, seed=42, trained_like=True)
+    net = build(cfg, P, dev, 1)
+    net.eval()
+    x = ofe.features(gen_wave(0, 2))
+    emb = torch.randn(2, 768, 496, generator=torch.Generator().manual_seed(7))
+    with torch.no_grad():
+        s_raw, w_raw = net(x.to(dev), embeddings=emb.to(dev))
+        p32 = pool_embeddings(emb.to(dev), 156, "pool1d", torch.float32)
+        s_p, w_p = net(x.to(dev), embeddings=p32)
+        p16 = pool_embeddings(emb.to(dev), 156, "pool1d", torch.bfloat16)
+        s_b, w_b = net(x.to(dev), embeddings=p16)
+        so, wo = ocrnn.crnn_forward(P, x, cfg, False, embeddings=emb)
+        sb, wb = ocrnn.crnn_forward(P, x, cfg, False, embeddings=p16.cpu().float())
+    assert maxdiff(s_p, s_raw) < 1e-6 and maxdiff(w_p, w_raw) < 1e-6
+    assert maxdiff(s_p, so) < 2e-5 and maxdiff(w_p, wo) < 2e-5
+    assert maxdiff(s_b, sb) < 2e-5 and maxdiff(w_b, wb) < 2e-5
+    assert maxdiff(s_b, so) < 2e-2            # what the storage rounding itself costs (8-bit mantissa on the embeddings)
