@@ -106,15 +106,32 @@ def _reference_root():
     return None
 
 
-def _run_import(stmt, ref, stub):
-    code = ["import sys", "sys.path[:0] = [%r, %r]" % (ROOT, ref)]
+_IMPORT_CACHE = {}
+
+
+def _import_results(ref, stub):
+    """One child process imports every statement (each in a fresh sub-interpreter-like state would cost ~4 s of `import
+    torch` apiece): per statement -> ("FILE", path) | ("ABSENT", module) | ("ERROR", message)."""
+    key = (ref, stub)
+    if key in _IMPORT_CACHE:
+        return _IMPORT_CACHE[key]
+    code = ["import sys, importlib, json", "sys.path[:0] = [%r, %r]" % (ROOT, ref)]
     if stub:
         code += ["from unittest.mock import MagicMock",
                  "for n in %r + ['dcase_util.data']: sys.modules[n] = MagicMock()" % sorted(ABSENT_OK)]
-    mod = stmt.split()[1]
-    code += ["try:", "    " + stmt, "except ModuleNotFoundError as e:", "    print('ABSENT', e.name); sys.exit(0)",
-             "import importlib", "m = importlib.import_module(%r)" % mod, "print('FILE', m.__file__)"]
-    return subprocess.run([sys.executable, "-c", "\n".join(code)], capture_output=True, text=True, cwd="/")
+    code += ["out = {}", "for stmt in %r:" % RECIPE_IMPORTS,
+             "    try:", "        exec(stmt, {})",
+             "        out[stmt] = ['FILE', importlib.import_module(stmt.split()[1]).__file__]",
+             "    except ModuleNotFoundError as e:", "        out[stmt] = ['ABSENT', e.name]",
+             "    except Exception as e:", "        out[stmt] = ['ERROR', repr(e)]",
+             "    for k in [k for k in sys.modules if k.startswith('desed_task.') and k.split('.')[1] in "
+             "('dataio', 'evaluation')]:", "        del sys.modules[k]",      # a failed import must not poison the next
+             "print('RESULT ' + json.dumps(out))"]
+    r = subprocess.run([sys.executable, "-c", "\n".join(code)], capture_output=True, text=True, cwd="/")
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    _IMPORT_CACHE[key] = json.loads(line[7:])
+    return _IMPORT_CACHE[key]
 
 
 @pytest.mark.parametrize("stmt", RECIPE_IMPORTS)
@@ -127,15 +144,11 @@ def test_recipe_import_blocks_resolve(stmt):
             pytest.skip("no reference checkout here (the non-hot modules live in the reference)")
         ref = "/nonexistent"
     mod = stmt.split()[1]
-    out = _run_import(stmt, ref, stub=False)
-    assert out.returncode == 0, out.stderr[-2000:]
-    tag, val = out.stdout.split()[-2:]
+    tag, val = _import_results(ref, False)[stmt]
     if tag == "ABSENT":
-        assert val in ABSENT_OK, out.stdout               # only a third-party module of the reference may be missing
-        out = _run_import(stmt, ref, stub=True)           # ... and with that dependency stubbed the import completes
-        assert out.returncode == 0, out.stderr[-2000:]
-        tag, val = out.stdout.split()[-2:]
-    assert tag == "FILE", out.stdout
+        assert val in ABSENT_OK, (stmt, val)              # only a third-party module of the reference may be missing
+        tag, val = _import_results(ref, True)[stmt]       # ... and with that dependency stubbed the import completes
+    assert tag == "FILE", (stmt, tag, val)
     if mod in HOT:
         assert val.startswith(os.path.join(ROOT, "desed_task") + os.sep), val
     else:
