@@ -16,6 +16,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float
                                    const float* __restrict__ beta, float* __restrict__ rm, float* __restrict__ rv,
                                    int64_t* __restrict__ nb, float* __restrict__ bn, double count, float eps,
                                    float momentum, int training, int C) {
+    pdl_enter();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) {
         float mean, invstd;
@@ -449,6 +450,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(float* __restrict__ gy, const float* __restrict__ z, const float* __restrict__ bn,
                     const double* __restrict__ stats, float* __restrict__ ggamma, float* __restrict__ gbeta,
                     float* __restrict__ gb, float inv_count, int64_t n4, int C, int frozen) {
+    pdl_enter();
     extern __shared__ float sv[];    // scale, mean, invstd, m1, m2
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         sv[c] = bn[c];
@@ -571,8 +573,8 @@ int launch_bn_finalize(const double* stats, const float* gamma, const float* bet
                        float* running_var, int64_t* num_batches, float* bn, double count, float eps, float momentum,
                        int training, int C, cudaStream_t s) {
     SEDK_PROF("bn_finalize", s);
-    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(stats, gamma, beta, running_mean, running_var, num_batches, bn, count,
-                                                    eps, momentum, training, C);
+    SEDK_CUDA(pdl_launch(bn_finalize_kernel, dim3(cdiv(C, 128)), dim3(128), (size_t)(0), s, stats, gamma, beta, running_mean, running_var, num_batches, bn, count,
+                                                    eps, momentum, training, C));
     SEDK_LAUNCH_CHECK("bn_finalize_kernel");
     return SEDK_OK;
 }
@@ -632,8 +634,8 @@ int launch_bn_bwd_apply(float* gy, const float* z, const float* bn, const double
     int64_t cap = (int64_t)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    bn_bwd_apply_kernel<<<(int)blocks, 256, 5 * C * sizeof(float), s>>>(gy, z, bn, stats, ggamma, gbeta, gb,
-                                                                       (float)(1.0 / count), n4, C, frozen);
+    SEDK_CUDA(pdl_launch(bn_bwd_apply_kernel, dim3((int)blocks), dim3(256), (size_t)(5 * C * sizeof(float)), s, gy, z, bn, stats, ggamma, gbeta, gb,
+                                                                       (float)(1.0 / count), n4, C, frozen));
     SEDK_LAUNCH_CHECK("bn_bwd_apply_kernel");
     return SEDK_OK;
 }

@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(256)
 bnglu_small_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, const float* __restrict__ glu_w,
                        const float* __restrict__ glu_b, float* __restrict__ out, SGeom gm, uint32_t thresh16,
                        float inv_keep, uint64_t seed, const uint64_t* __restrict__ seed_dev, uint64_t dstream) {
+    pdl_enter();
     constexpr int Q = C / 16, NF = 2 * Q;
     __shared__ __align__(16) float vec[3 * C];      // scale, shift, gate bias
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
@@ -270,6 +271,7 @@ bnglu_small_bwd_kernel(const float* __restrict__ z, const float* __restrict__ bn
                        float* __restrict__ gglu_w, float* __restrict__ gglu_b, double* __restrict__ stats, SGeom gm,
                        uint32_t thresh16, float inv_keep, uint64_t seed, const uint64_t* __restrict__ seed_dev,
                        uint64_t dstream) {
+    pdl_enter();
     constexpr int Q = C / 16, NF = 2 * Q;
     constexpr int S = C + 8;                                  // row stride of the staging patch (bank-conflict-free reads)
     constexpr int PATCH = 2 * 16 * S;                         // floats per warp: g_lin[16][S], y[16][S]
@@ -517,13 +519,13 @@ int run_small_fwd(const float* z, const float* bn, const float* glu_w, const flo
         static int grid_cap = 0;
         if (grid_cap == 0) grid_cap = small_grid(k, 1 << 30);
         const int need = cdiv(gm.total, 8);
-        k<<<grid_cap < need ? grid_cap : need, 256, 0, s>>>(z, bn, glu_w, glu_b, out, gm, th, inv_keep, seed, seed_dev, dstream);
+        SEDK_CUDA(pdl_launch(k, dim3(grid_cap < need ? grid_cap : need), dim3(256), (size_t)(0), s, z, bn, glu_w, glu_b, out, gm, th, inv_keep, seed, seed_dev, dstream));
     } else {
         auto k = bnglu_small_fwd_kernel<C, false>;
         static int grid_cap = 0;
         if (grid_cap == 0) grid_cap = small_grid(k, 1 << 30);
         const int need = cdiv(gm.total, 8);
-        k<<<grid_cap < need ? grid_cap : need, 256, 0, s>>>(z, bn, glu_w, glu_b, out, gm, th, inv_keep, seed, seed_dev, dstream);
+        SEDK_CUDA(pdl_launch(k, dim3(grid_cap < need ? grid_cap : need), dim3(256), (size_t)(0), s, z, bn, glu_w, glu_b, out, gm, th, inv_keep, seed, seed_dev, dstream));
     }
     SEDK_LAUNCH_CHECK("bnglu_small_fwd_kernel");
     return SEDK_OK;
@@ -540,15 +542,15 @@ int run_small_bwd(const float* z, const float* bn, const float* glu_w, const flo
         static int grid_cap = 0;
         if (grid_cap == 0) grid_cap = small_grid(k, 1 << 30);
         const int need = cdiv(gm.total, 8);
-        k<<<grid_cap < need ? grid_cap : need, 256, 0, s>>>(z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, gm, th,
-                                                          inv_keep, seed, seed_dev, dstream);
+        SEDK_CUDA(pdl_launch(k, dim3(grid_cap < need ? grid_cap : need), dim3(256), (size_t)(0), s, z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, gm, th,
+                                                          inv_keep, seed, seed_dev, dstream));
     } else {
         auto k = bnglu_small_bwd_kernel<C, false>;
         static int grid_cap = 0;
         if (grid_cap == 0) grid_cap = small_grid(k, 1 << 30);
         const int need = cdiv(gm.total, 8);
-        k<<<grid_cap < need ? grid_cap : need, 256, 0, s>>>(z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, gm, th,
-                                                          inv_keep, seed, seed_dev, dstream);
+        SEDK_CUDA(pdl_launch(k, dim3(grid_cap < need ? grid_cap : need), dim3(256), (size_t)(0), s, z, bn, glu_w, glu_b, gout, gy, gglu_w, gglu_b, stats, gm, th,
+                                                          inv_keep, seed, seed_dev, dstream));
     }
     SEDK_LAUNCH_CHECK("bnglu_small_bwd_kernel");
     return SEDK_OK;

@@ -48,6 +48,7 @@ glu_prep_kernel(const double* __restrict__ stats, const float* __restrict__ gamm
                 float* __restrict__ rm, float* __restrict__ rv, int64_t* __restrict__ nb, float* __restrict__ bn,
                 const float* __restrict__ glu_w, const float* __restrict__ glu_b, float* __restrict__ pack, double count,
                 float eps, float momentum, int training) {
+    pdl_enter();
     constexpr int M = GT_C;
     __shared__ float red[M / 32];
     // pack row m = (h, n), column j = (h', k); the blocks h != h' of the two 128 x 128 operands are zero
@@ -126,6 +127,7 @@ bnglu_tc5_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
                      const float* __restrict__ bn, const float* __restrict__ bprime, float* __restrict__ out,
                      float* __restrict__ lin_out, GtGeom gm, int total_tiles, uint32_t thresh16, float inv_keep,
                      uint64_t seed, const uint64_t* __restrict__ seed_dev, uint64_t dstream) {
+    pdl_enter();
     constexpr int CH = C / 32;                                  // 32-channel chunks per half
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -285,6 +287,7 @@ bnglu_tc5_bwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
                      float* __restrict__ gy, float* __restrict__ gglu_b, double* __restrict__ stats, GtGeom gm,
                      int total_tiles, uint32_t thresh16, float inv_keep, uint64_t seed,
                      const uint64_t* __restrict__ seed_dev, uint64_t dstream) {
+    pdl_enter();
     constexpr int CH = C / 32;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -514,10 +517,10 @@ int run_gt_fwd(const CUtensorMap& tmZ, const CUtensorMap& tmW, const float* bn, 
         cfg = true;
     }
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    bnglu_tc5_fwd_kernel<C><<<grid, GT_THREADS, GT_SMEM_FWD, s>>>(tmZ, tmW, bn, pack + GT_PACK_B, out, lin_out, gm, tiles,
+    SEDK_CUDA(pdl_launch(bnglu_tc5_fwd_kernel<C>, dim3(grid), dim3(GT_THREADS), (size_t)(GT_SMEM_FWD), s, tmZ, tmW, bn, pack + GT_PACK_B, out, lin_out, gm, tiles,
                                                                   drop_threshold16(drop_p),
                                                                   drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed,
-                                                                  seed_dev, drop_stream);
+                                                                  seed_dev, drop_stream));
     SEDK_LAUNCH_CHECK("bnglu_tc5_fwd_kernel");
     return SEDK_OK;
 }
@@ -533,10 +536,10 @@ int run_gt_bwd(const CUtensorMap& tmZ, const CUtensorMap& tmW, const float* bn, 
         cfg = true;
     }
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    bnglu_tc5_bwd_kernel<C><<<grid, GT_THREADS, GT_SMEM_BWD, s>>>(tmZ, tmW, bn, gout, lin_glin, gy, gglu_b, stats, gm, tiles,
+    SEDK_CUDA(pdl_launch(bnglu_tc5_bwd_kernel<C>, dim3(grid), dim3(GT_THREADS), (size_t)(GT_SMEM_BWD), s, tmZ, tmW, bn, gout, lin_glin, gy, gglu_b, stats, gm, tiles,
                                                                   drop_threshold16(drop_p),
                                                                   drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f, seed,
-                                                                  seed_dev, drop_stream);
+                                                                  seed_dev, drop_stream));
     SEDK_LAUNCH_CHECK("bnglu_tc5_bwd_kernel");
     return SEDK_OK;
 }
@@ -556,11 +559,11 @@ int launch_glu_prep(const double* stats, const float* gamma, const float* beta, 
     SEDK_PROF("glu_prep", s);
     SEDK_REQUIRE(C == 64 || C == 128, "glu_prep: C must be 64 or 128");
     if (C == 128)
-        glu_prep_kernel<128><<<GT_C, GT_C, 0, s>>>(stats, gamma, beta, running_mean, running_var, num_batches, bn, glu_w, glu_b,
-                                                   pack, count, eps, momentum, training);
+        SEDK_CUDA(pdl_launch(glu_prep_kernel<128>, dim3(GT_C), dim3(GT_C), (size_t)(0), s, stats, gamma, beta, running_mean, running_var, num_batches, bn, glu_w, glu_b,
+                                                   pack, count, eps, momentum, training));
     else
-        glu_prep_kernel<64><<<GT_C, GT_C, 0, s>>>(stats, gamma, beta, running_mean, running_var, num_batches, bn, glu_w, glu_b,
-                                                  pack, count, eps, momentum, training);
+        SEDK_CUDA(pdl_launch(glu_prep_kernel<64>, dim3(GT_C), dim3(GT_C), (size_t)(0), s, stats, gamma, beta, running_mean, running_var, num_batches, bn, glu_w, glu_b,
+                                                  pack, count, eps, momentum, training));
     SEDK_LAUNCH_CHECK("glu_prep_kernel");
     return SEDK_OK;
 }

@@ -81,6 +81,26 @@ inline int opt_in_smem(K kernel, size_t bytes) {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+#ifdef __CUDACC__
+// launch on the dependency chain with programmatic stream serialisation (option "pdl", default 1; 0 = plain launch order).
+// ONLY for kernels whose first statement is pdl_enter().
+template <class... KArgs, class... Args>
+inline cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    const int on = get_option("pdl", 1) != 0 ? 1 : 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = on;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // order-preserving float <-> uint32 map (for atomicMin / atomicMax on floats)
 __host__ __device__ __forceinline__ uint32_t f2ord(float f) {
@@ -101,6 +121,18 @@ __host__ __device__ __forceinline__ float ord2f(uint32_t o) {
 }
 
 #ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The kernels on the step's dependency chain are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (pdl_launch below): such a kernel may be scheduled while its
+// predecessor in the stream is still draining, so its FIRST statement must be pdl_enter(): it lets ITS successor start
+// launching (launch_dependents) and then blocks until every prerequisite grid has completed and flushed its memory
+// (griddepcontrol.wait).  Nothing before that line may touch global memory.  The launch latency / CTA scheduling of
+// kernel k+1 thereby overlaps the tail of kernel k (~80 dependent launches per training step).
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // warp helpers
 __device__ __forceinline__ float warp_sum(float v) {

@@ -81,6 +81,7 @@ conv0_fwd_kernel(const float* __restrict__ x, int64_t sb, int64_t sm, int64_t st
                  float scaler_eps, const int32_t* __restrict__ specaug, const float* __restrict__ w,
                  const float* __restrict__ bias, float* __restrict__ x0, float* __restrict__ z,
                  double* __restrict__ stats, int T, int F) {
+    pdl_enter();
     constexpr int TPP = COUT / 8;            // threads per pixel (8 channels each)
     constexpr int FW = 256 / TPP;            // pixel columns per CTA
     __shared__ float hal[(C0_TT + 2) * C0_HS];
@@ -213,6 +214,7 @@ template <int COUT, bool X3>
 __global__ void __launch_bounds__(256)
 conv0_wgrad_kernel(const float* __restrict__ x0, const float* __restrict__ gz, float* __restrict__ gw, int B, int T,
                    int F, int total_tiles) {
+    pdl_enter();
     constexpr int MF = COUT / 16;
     constexpr int GS = COUT + 8;
     constexpr int HS = W0_FW + 3;
@@ -309,6 +311,7 @@ template <int CIN, int NT, int TT, int TF, bool X3>
 __global__ void __launch_bounds__(256, 1)
 conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ wp, const float* __restrict__ bias,
                float* __restrict__ out, double* __restrict__ stats, int T, int F, int COUT) {
+    pdl_enter();
     using Cfg = ConvCfg<CIN, NT, TT, TF>;
     constexpr int KC = Cfg::KC, HS = Cfg::HS, BS = Cfg::BS, HW = Cfg::HW, HP = Cfg::HP;
     constexpr int WN = Cfg::WN, MF = Cfg::MF, NF = Cfg::NF;
@@ -595,8 +598,8 @@ int launch_conv0_fwd(const float* x, int64_t sb, int64_t sm, int64_t st, const u
     {                                                                                                            \
         const int FW = 256 / (CO / 8);                                                                           \
         dim3 grid(B * nTt * cdiv(F, FW));                                                                        \
-        conv0_fwd_kernel<CO><<<grid, 256, 0, s>>>(x, sb, sm, st, minmax, scaler_eps, specaug, w, bias, x0, z,    \
-                                                  stats, T, F);                                                  \
+        SEDK_CUDA(pdl_launch(conv0_fwd_kernel<CO>, dim3(grid), dim3(256), (size_t)(0), s, x, sb, sm, st, minmax, scaler_eps, specaug, w, bias, x0, z,    \
+                                                  stats, T, F));                                                  \
     }
     if (cout == 16) SEDK_C0(16)
     else if (cout == 32) SEDK_C0(32)
@@ -617,7 +620,7 @@ int launch_conv0_wgrad(const float* x0, const float* gz, float* gw, int B, int T
         size_t smem = (size_t)(W0_TT * W0_FW * (CO + 8) + (W0_TT + 2) * (W0_FW + 3) + CO * 16) * sizeof(float);  \
         static bool cfg = false;                                                                                 \
         if (!cfg) { int rc = opt_in_smem(conv0_wgrad_kernel<CO, X3>, smem); if (rc) return rc; cfg = true; }    \
-        conv0_wgrad_kernel<CO, X3><<<grid, 256, smem, s>>>(x0, gz, gw, B, T, F, tiles);                          \
+        SEDK_CUDA(pdl_launch(conv0_wgrad_kernel<CO, X3>, dim3(grid), dim3(256), (size_t)(smem), s, x0, gz, gw, B, T, F, tiles));                          \
     }
     if (cout == 16) { if (precision) SEDK_W0(16, true) else SEDK_W0(16, false) }
     else if (cout == 32) { if (precision) SEDK_W0(32, true) else SEDK_W0(32, false) }
@@ -636,10 +639,10 @@ static int run_conv(const float* in, const float* wp, const float* bias, float* 
     static bool cfg0 = false, cfg1 = false;
     if (precision) {
         if (!cfg1) { int rc = opt_in_smem(conv3x3_kernel<CIN, NT, TT, TF, true>, Cfg::SMEM); if (rc) return rc; cfg1 = true; }
-        conv3x3_kernel<CIN, NT, TT, TF, true><<<grid, 256, Cfg::SMEM, s>>>(in, wp, bias, out, stats, T, F, cout);
+        SEDK_CUDA(pdl_launch(conv3x3_kernel<CIN, NT, TT, TF, true>, dim3(grid), dim3(256), (size_t)(Cfg::SMEM), s, in, wp, bias, out, stats, T, F, cout));
     } else {
         if (!cfg0) { int rc = opt_in_smem(conv3x3_kernel<CIN, NT, TT, TF, false>, Cfg::SMEM); if (rc) return rc; cfg0 = true; }
-        conv3x3_kernel<CIN, NT, TT, TF, false><<<grid, 256, Cfg::SMEM, s>>>(in, wp, bias, out, stats, T, F, cout);
+        SEDK_CUDA(pdl_launch(conv3x3_kernel<CIN, NT, TT, TF, false>, dim3(grid), dim3(256), (size_t)(Cfg::SMEM), s, in, wp, bias, out, stats, T, F, cout));
     }
     SEDK_LAUNCH_CHECK("conv3x3_kernel");
     return SEDK_OK;

@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const float* __restrict__ bias, float* __restrict__ out, double* __restrict__ stats, int T, int F,
                    int cmod) {
+    pdl_enter();
     // cmod: number of REAL output channels behind the COUT MMA columns (COUT, or COUT / 2 in the paired-pixel mode where
     // column (h, co) is channel co of the pixel with parity h): bias and BatchNorm statistics are indexed modulo cmod
     static_assert(TT * TF == 128, "tile must hold 128 pixels");
@@ -176,6 +177,7 @@ template <int CIN, int TT, int TF, int NDX = 3>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_tc5_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
                       float* __restrict__ gwp, int T, int F, int total_tiles) {
+    pdl_enter();
     static_assert(TT * TF == WG_KPIX, "K tile must hold 32 pixels");
     constexpr int COUT = 128;
     constexpr int NCH = CIN / 32;                                   // 32-channel chunks of x
@@ -302,7 +304,7 @@ int run_tc5(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, f
         cfg = true;
     }
     dim3 grid(B * cdiv(T, TT) * cdiv(F, TF));
-    kern<<<grid, TC_THREADS, TC_SMEM, s>>>(tmA, tmB, bias, out, stats, T, F, cmod);
+    SEDK_CUDA(pdl_launch(kern, dim3(grid), dim3(TC_THREADS), (size_t)(TC_SMEM), s, tmA, tmB, bias, out, stats, T, F, cmod));
     SEDK_LAUNCH_CHECK("conv3x3_tc5_kernel");
     return SEDK_OK;
 }
@@ -360,7 +362,7 @@ int run_wgrad_tc5(const CUtensorMap& tmG, const CUtensorMap& tmX, float* gwp, in
     int gx = num_sms() / NDX;
     if (gx > tiles) gx = tiles;
     dim3 grid(gx, NDX);
-    kern<<<grid, WG_THREADS, smem, s>>>(tmG, tmX, gwp, T, F, tiles);
+    SEDK_CUDA(pdl_launch(kern, dim3(grid), dim3(WG_THREADS), (size_t)(smem), s, tmG, tmX, gwp, T, F, tiles));
     SEDK_LAUNCH_CHECK("conv_wgrad_tc5_kernel");
     return SEDK_OK;
 }

@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                 float* __restrict__ ema, int64_t n, int do_adam, float step_size, float beta1, float beta2, float eps,
                 float inv_sqrt_bc2, float ema_alpha, float grad_scale, const float* __restrict__ hyper) {
+    pdl_enter();
     if (hyper != nullptr) {
         step_size = hyper[0];
         inv_sqrt_bc2 = hyper[1];
@@ -490,8 +491,8 @@ extern "C" int sedk_adam_ema(float* p, const float* g, float* m, float* v, float
         step_size = (float)((double)lr / bc1);
         inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     }
-    adam_ema_kernel<<<grid1(n, 1), EW_THREADS, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, n, do_adam, step_size, beta1,
-                                                                        beta2, eps, inv_sqrt_bc2, ema_alpha, grad_scale, nullptr);
+    SEDK_CUDA(pdl_launch(adam_ema_kernel, dim3(grid1(n, 1)), dim3(EW_THREADS), (size_t)(0), (cudaStream_t)stream, p, g, m, v, ema, n, do_adam, step_size, beta1,
+                                                                        beta2, eps, inv_sqrt_bc2, ema_alpha, grad_scale, nullptr));
     SEDK_LAUNCH_CHECK("adam_ema_kernel");
     return SEDK_OK;
 }
@@ -503,8 +504,8 @@ extern "C" int sedk_adam_ema_dev(float* p, const float* g, float* m, float* v, f
     SEDK_PROF("adam_ema", (cudaStream_t)stream);
     SEDK_REQUIRE(p && hyper && n > 0, "sedk_adam_ema_dev: bad arguments");
     SEDK_REQUIRE(!do_adam || (g && m && v), "sedk_adam_ema_dev: Adam needs g, m, v");
-    adam_ema_kernel<<<grid1(n, 1), EW_THREADS, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, n, do_adam, 0.f, beta1, beta2,
-                                                                        eps, 1.f, 0.f, 1.f, hyper);
+    SEDK_CUDA(pdl_launch(adam_ema_kernel, dim3(grid1(n, 1)), dim3(EW_THREADS), (size_t)(0), (cudaStream_t)stream, p, g, m, v, ema, n, do_adam, 0.f, beta1, beta2,
+                                                                        eps, 1.f, 0.f, 1.f, hyper));
     SEDK_LAUNCH_CHECK("adam_ema_kernel");
     return SEDK_OK;
 }

@@ -35,6 +35,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, float* __restrict__ C0,
                 float* __restrict__ C1, const float* __restrict__ bias0, const float* __restrict__ bias1, int M, int N, int K,
                 int ldc) {
+    pdl_enter();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* aligned = smem_raw + (base - smem_u32(smem_raw));
@@ -203,7 +204,7 @@ int launch_gemm_tc5_nt2(const float* A, const float* const B[2], const float* co
     rc = opt_in_once(kern, cfg);
     if (rc) return rc;
     dim3 grid(cdiv(M, 128), cdiv(N, 128), 2);
-    kern<<<grid, GM_THREADS, GM_SMEM, s>>>(ta, tb0, ta, tb1, C[0], C[1], bias[0], bias[1], M, N, K, N);
+    SEDK_CUDA(pdl_launch(kern, dim3(grid), dim3(GM_THREADS), (size_t)(GM_SMEM), s, ta, tb0, ta, tb1, C[0], C[1], bias[0], bias[1], M, N, K, N));
     SEDK_LAUNCH_CHECK("gemm_tc5_kernel<NT>");
     return SEDK_OK;
 }
@@ -225,7 +226,7 @@ int launch_gemm_tc5_nt1(const float* A, const float* B, const float* bias, float
     rc = opt_in_once(kern, cfg);
     if (rc) return rc;
     dim3 grid(cdiv(M, 128), cdiv(N, 128), 1);
-    kern<<<grid, GM_THREADS, GM_SMEM, s>>>(ta, tb, ta, tb, C, C, bias, bias, M, N, K, N);
+    SEDK_CUDA(pdl_launch(kern, dim3(grid), dim3(GM_THREADS), (size_t)(GM_SMEM), s, ta, tb, ta, tb, C, C, bias, bias, M, N, K, N));
     SEDK_LAUNCH_CHECK("gemm_tc5_kernel<NT1>");
     return SEDK_OK;
 }
@@ -251,7 +252,7 @@ int launch_gemm_tc5_nn_pair(const float* const A[2], const float* const B[2], fl
     rc = opt_in_once(kern, cfg);
     if (rc) return rc;
     dim3 grid(cdiv(M, 128), cdiv(N, 128), 1);
-    kern<<<grid, GM_THREADS, GM_SMEM, s>>>(ta0, tb0, ta1, tb1, C, C, nullptr, nullptr, M, N, K, N);
+    SEDK_CUDA(pdl_launch(kern, dim3(grid), dim3(GM_THREADS), (size_t)(GM_SMEM), s, ta0, tb0, ta1, tb1, C, C, nullptr, nullptr, M, N, K, N));
     SEDK_LAUNCH_CHECK("gemm_tc5_kernel<NN>");
     return SEDK_OK;
 }

@@ -59,6 +59,7 @@ gru_fwd_v3_kernel(const float* __restrict__ gi0, const float* __restrict__ gi1, 
                   const float* __restrict__ whh1, const float* __restrict__ bhh0, const float* __restrict__ bhh1,
                   float* __restrict__ out, float* __restrict__ gates0, float* __restrict__ gates1,
                   float* __restrict__ hprev0, float* __restrict__ hprev1, int T, int save) {
+    pdl_enter();
     constexpr int H = H3, NT = 128 / UPO * 8, R = 3 * UPO;
     constexpr int LPU = 8 / UPO;                                  // lanes that end up with the sums of one unit
     __shared__ __align__(16) float h_s[2 * HPAD3];
@@ -198,6 +199,7 @@ gru_bwd_v3_kernel(const float* __restrict__ gout, const float* __restrict__ whh0
                   const float* __restrict__ hprev1, float* __restrict__ dgi0, float* __restrict__ dgi1,
                   float* __restrict__ dghn0, float* __restrict__ dghn1, float* __restrict__ gbih0,
                   float* __restrict__ gbih1, float* __restrict__ gbhh0, float* __restrict__ gbhh1, int T) {
+    pdl_enter();
     constexpr int H = H3, NT = 128 / UPW * 32;
     constexpr int LPU = 32 / UPW;                                 // lanes that end up with d h_prev of one unit (4 or 2)
     __shared__ __align__(16) float dgh_s[2 * 3 * H];
@@ -665,8 +667,8 @@ int launch_cluster3(Kern kern, int B, cudaStream_t s, Args... args) {
 template <int UPO>
 int run_fwd_v3(const float* const gi[2], const float* const w_hh[2], const float* const b_hh[2], float* out,
                float* const gates[2], float* const hprev[2], int B, int T, int save, cudaStream_t s) {
-    gru_fwd_v3_kernel<UPO><<<dim3(B, 2), 128 / UPO * 8, 0, s>>>(gi[0], gi[1], w_hh[0], w_hh[1], b_hh[0], b_hh[1], out,
-                                                               gates[0], gates[1], hprev[0], hprev[1], T, save);
+    SEDK_CUDA(pdl_launch(gru_fwd_v3_kernel<UPO>, dim3(dim3(B, 2)), dim3(128 / UPO * 8), (size_t)(0), s, gi[0], gi[1], w_hh[0], w_hh[1], b_hh[0], b_hh[1], out,
+                                                               gates[0], gates[1], hprev[0], hprev[1], T, save));
     SEDK_LAUNCH_CHECK("gru_fwd_v3_kernel");
     return SEDK_OK;
 }
@@ -679,9 +681,9 @@ int run_bwd_v3(const float* gout, const float* const w_hh[2], const float* const
         SEDK_CUDA(cudaMemsetAsync(gb_ih[d], 0, (size_t)3 * H3 * sizeof(float), s));
         SEDK_CUDA(cudaMemsetAsync(gb_hh[d], 0, (size_t)3 * H3 * sizeof(float), s));
     }
-    gru_bwd_v3_kernel<UPW><<<dim3(B, 2), 128 / UPW * 32, 0, s>>>(gout, w_hh[0], w_hh[1], gates[0], gates[1], hprev[0],
+    SEDK_CUDA(pdl_launch(gru_bwd_v3_kernel<UPW>, dim3(dim3(B, 2)), dim3(128 / UPW * 32), (size_t)(0), s, gout, w_hh[0], w_hh[1], gates[0], gates[1], hprev[0],
                                                                 hprev[1], dgi[0], dgi[1], dghn[0], dghn[1], gb_ih[0],
-                                                                gb_ih[1], gb_hh[0], gb_hh[1], T);
+                                                                gb_ih[1], gb_hh[0], gb_hh[1], T));
     SEDK_LAUNCH_CHECK("gru_bwd_v3_kernel");
     return SEDK_OK;
 }

@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256)
 heads_fwd_kernel(const float* __restrict__ x, const float* __restrict__ dw, const float* __restrict__ db,
                  const float* __restrict__ sw, const float* __restrict__ sb, const uint8_t* __restrict__ cmask,
                  float* __restrict__ strong, float* __restrict__ hsum, float* __restrict__ sof, int T, int D, int C) {
+    pdl_enter();
     extern __shared__ float smem[];
     const int DS = D + 1;
     float* Wd = smem;                    // [C][DS]
@@ -101,6 +102,7 @@ heads_fwd_kernel(const float* __restrict__ x, const float* __restrict__ dw, cons
 
 __global__ void heads_weak_kernel(const float* __restrict__ hsum, const uint8_t* __restrict__ cmask,
                                   float* __restrict__ weak, int B, int C) {
+    pdl_enter();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * C) return;
     int b = i / C, c = i - b * C;
@@ -115,6 +117,7 @@ heads_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dw, cons
                  const float* __restrict__ sof, const float* __restrict__ gstrong, const float* __restrict__ gweak,
                  float* __restrict__ gx, float* __restrict__ gdw, float* __restrict__ gdb, float* __restrict__ gsw,
                  float* __restrict__ gsb, int T, int D, int C) {
+    pdl_enter();
     __shared__ float gl[HT][2 * HC_MAX];
     extern __shared__ float wst[];                       // [2 * HC_MAX][256]: this thread's weight-gradient sums, by class
     const int b = blockIdx.y, tid = threadIdx.x;
@@ -228,6 +231,7 @@ heads_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dw, cons
 __global__ void __launch_bounds__(256)
 dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, uint32_t thresh, float inv_keep,
                uint64_t seed, const uint64_t* __restrict__ seed_dev, uint64_t stream_id) {
+    pdl_enter();
     const Philox ph(seed + (seed_dev ? *seed_dev : 0ull));
     const int64_t n4 = (n + 3) / 4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -254,6 +258,7 @@ sed_loss_kernel(const float* __restrict__ strong, const float* __restrict__ weak
                 int C, int T, int n_strong, int n_weak, int cons_row0, int cons_bce, float cw,
                 const float* __restrict__ cw_dev, float* __restrict__ sums, float* __restrict__ gstrong,
                 float* __restrict__ gweak) {
+    pdl_enter();
     if (cw_dev != nullptr) cw = *cw_dev;
     const int64_t ns = (int64_t)B * C * T, nw = (int64_t)B * C;
     const float inv_bs = n_strong > 0 ? 1.f / (float)((int64_t)n_strong * C * T) : 0.f;
@@ -316,6 +321,7 @@ sed_loss_kernel(const float* __restrict__ strong, const float* __restrict__ weak
 
 __global__ void sed_loss_finalize(float* losses, const float* sums, int B, int C, int T, int n_strong, int n_weak,
                                   int cons_row0, float cw, const float* cw_dev) {
+    pdl_enter();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (cw_dev != nullptr) cw = *cw_dev;
     const float bs = n_strong > 0 ? sums[0] / (float)((int64_t)n_strong * C * T) : 0.f;
@@ -434,9 +440,9 @@ int launch_heads_fwd(const float* x, const float* dw, const float* db, const flo
     }
     SEDK_CUDA(cudaMemsetAsync(hsum, 0, (size_t)B * 2 * C * sizeof(float), s));
     dim3 grid(cdiv(T, HT), B);
-    heads_fwd_kernel<<<grid, 256, smem, s>>>(x, dw, db, sw, sb, cmask, strong, hsum, sof, T, D, C);
+    SEDK_CUDA(pdl_launch(heads_fwd_kernel, dim3(grid), dim3(256), (size_t)(smem), s, x, dw, db, sw, sb, cmask, strong, hsum, sof, T, D, C));
     SEDK_LAUNCH_CHECK("heads_fwd_kernel");
-    heads_weak_kernel<<<cdiv(B * C, 128), 128, 0, s>>>(hsum, cmask, weak, B, C);
+    SEDK_CUDA(pdl_launch(heads_weak_kernel, dim3(cdiv(B * C, 128)), dim3(128), (size_t)(0), s, hsum, cmask, weak, B, C));
     SEDK_LAUNCH_CHECK("heads_weak_kernel");
     return SEDK_OK;
 }
@@ -454,8 +460,8 @@ int launch_heads_bwd(const float* x, const float* dw, const float* sw, const uin
         if (rc) return rc;
         configured = true;
     }
-    heads_bwd_kernel<<<grid, 256, smem, s>>>(x, dw, sw, cmask, strong, hsum, sof, gstrong, gweak, gx, gdw, gdb, gsw, gsb, T,
-                                             D, C);
+    SEDK_CUDA(pdl_launch(heads_bwd_kernel, dim3(grid), dim3(256), (size_t)(smem), s, x, dw, sw, cmask, strong, hsum, sof, gstrong, gweak, gx, gdw, gdb, gsw, gsb, T,
+                                             D, C));
     SEDK_LAUNCH_CHECK("heads_bwd_kernel");
     return SEDK_OK;
 }
@@ -469,7 +475,7 @@ int launch_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, 
     int64_t cap = (int64_t)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    dropout_kernel<<<(int)blocks, 256, 0, s>>>(x, y, n, thresh, inv_keep, seed, seed_dev, stream_id);
+    SEDK_CUDA(pdl_launch(dropout_kernel, dim3((int)blocks), dim3(256), (size_t)(0), s, x, y, n, thresh, inv_keep, seed, seed_dev, stream_id));
     SEDK_LAUNCH_CHECK("dropout_kernel");
     return SEDK_OK;
 }
@@ -521,10 +527,10 @@ static int sed_loss_impl(const float* strong, const float* weak, const float* t_
     const int64_t n = (int64_t)B * C * T + (int64_t)B * C;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
-    sed_loss_kernel<<<blocks, 256, 0, s>>>(strong, weak, t_strong, t_weak, labels, labels_weak, B, C, T, n_strong, n_weak,
-                                           cons_row0, cons_kind, cons_weight, cw_dev, losses + 8, gstrong, gweak);
+    SEDK_CUDA(pdl_launch(sed_loss_kernel, dim3(blocks), dim3(256), (size_t)(0), s, strong, weak, t_strong, t_weak, labels, labels_weak, B, C, T, n_strong, n_weak,
+                                           cons_row0, cons_kind, cons_weight, cw_dev, losses + 8, gstrong, gweak));
     SEDK_LAUNCH_CHECK("sed_loss_kernel");
-    sed_loss_finalize<<<1, 32, 0, s>>>(losses, losses + 8, B, C, T, n_strong, n_weak, cons_row0, cons_weight, cw_dev);
+    SEDK_CUDA(pdl_launch(sed_loss_finalize, dim3(1), dim3(32), (size_t)(0), s, losses, losses + 8, B, C, T, n_strong, n_weak, cons_row0, cons_weight, cw_dev));
     SEDK_LAUNCH_CHECK("sed_loss_finalize");
     return SEDK_OK;
 }

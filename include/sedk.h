@@ -51,6 +51,10 @@ SEDK_API int sedk_set_gru_cluster(int cs);
  *   "gru_v3"      1 (default): H = 128 recurrence, third generation (csrc/gru3.cu): 8 warps, every W_hh weight in registers,
  *                 octet-per-4-units layout (4 LDS.128 of h per thread and step, transposing-butterfly reductions); 2: the
  *                 16-warp variant of the same layout; 0: fall through to "gru_v2"
+ *   "pdl"         1 (default): the kernels on the step's dependency chain are launched with programmatic stream
+ *                 serialisation (programmatic dependent launch: kernel k + 1 is scheduled while kernel k drains and blocks in
+ *                 griddepcontrol.wait until k has completed); 0: plain stream order
+ *   "logmel_v2"   1 (default): second-generation front end (csrc/logmel2.cu); 0: first generation (csrc/logmel.cu)
  *   "gru_v2"      1 (default): H = 128 recurrence with the quad-per-unit layout (shuffle reductions, one barrier per
  *                 step); 0: first-generation kernel (row x k-segment layout, partial sums through shared memory)
  *   "bnglu_small" 1 (default): register-resident warp-autonomous BN+GLU+pool kernels for 16 / 32 channels; 0: tiled kernel
