@@ -51,9 +51,10 @@ SEDK_API int sedk_set_gru_cluster(int cs);
  *   "gru_v3"      1 (default): H = 128 recurrence, third generation (csrc/gru3.cu): 8 warps, every W_hh weight in registers,
  *                 octet-per-4-units layout (4 LDS.128 of h per thread and step, transposing-butterfly reductions); 2: the
  *                 16-warp variant of the same layout; 0: fall through to "gru_v2"
- *   "pdl"         1 (default): the kernels on the step's dependency chain are launched with programmatic stream
- *                 serialisation (programmatic dependent launch: kernel k + 1 is scheduled while kernel k drains and blocks in
- *                 griddepcontrol.wait until k has completed); 0: plain stream order
+ *   "pdl"         0 (default): plain stream order; 1: the kernels on the step's dependency chain are launched with
+ *                 programmatic stream serialisation (programmatic dependent launch: kernel k + 1 is scheduled while kernel k
+ *                 drains and blocks in griddepcontrol.wait until k has completed).  Parity-tested; measured slower on B200
+ *                 (2.205 vs 2.188 ms per supervised step: the waiting CTAs take SM slots from the parallel graph branches)
  *   "logmel_v2"   1 (default): second-generation front end (csrc/logmel2.cu); 0: first generation (csrc/logmel.cu)
  *   "gru_v2"      1 (default): H = 128 recurrence with the quad-per-unit layout (shuffle reductions, one barrier per
  *                 step); 0: first-generation kernel (row x k-segment layout, partial sums through shared memory)

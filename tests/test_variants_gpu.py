@@ -46,7 +46,7 @@ def _compare(a, b, tol_out, tol_grad):
 @pytest.mark.parametrize("precision,tol_out,tol_grad", [(1, 2e-5, 2e-3), (0, 5e-4, 3e-2)])
 def test_kernel_generations_agree(dev, feats, option, precision, tol_out, tol_grad):
     from desed_task_b200._lib import lib
-    default = 0 if option == "conv_pair" else 1         # library defaults (include/sedk.h)
+    default = 0 if option in ("conv_pair", "pdl") else 1         # library defaults (include/sedk.h)
     res = {}
     for on in (1, 0):
         lib().sedk_set_option(option.encode(), on)
