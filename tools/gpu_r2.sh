@@ -38,6 +38,12 @@ if has bench; then
     timeout 600 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err
     stamp "bench full exit $?"
 fi
+for wl in mean_teacher inference; do
+    if has full_$wl; then
+        timeout 600 python bench.py --workload $wl --steps 20 --warmup 5 > $OUT/${TAG}_bench_${wl}.json 2> $OUT/${TAG}_bench_${wl}.err
+        stamp "bench $wl (full) exit $? : $(cut -c1-150 $OUT/${TAG}_bench_${wl}.json)"
+    fi
+done
 if has ref; then
     timeout 400 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err
     stamp "reference arm exit $?"
@@ -48,8 +54,8 @@ if has launches; then
     stamp "ncu launch list exit $?"
 fi
 if has hot; then
-    timeout 500 ncu --profile-from-start off --set full --clock-control none --import-source on \
-        -k regex:"gru_fwd_v3|gru_bwd_v3|logmel|conv_wgrad_kernel|bnglu_small" -c 24 \
+    timeout 800 ncu --profile-from-start off --set full --clock-control none --import-source on \
+        -c 140 \
         -f -o /tmp/${TAG}_hot python tools/profile_step.py supervised > $OUT/${TAG}_ncu_hot.log 2>&1
     stamp "ncu hot capture exit $?"
     ncu -i /tmp/${TAG}_hot.ncu-rep --page raw --csv > $OUT/${TAG}_hot_raw.csv 2>/dev/null
