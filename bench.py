@@ -198,6 +198,17 @@ def kernel_work(name, B, net=NET_2023):
     if name == "conv0_wgrad":
         g = geo[0]
         return 2.0 * 9 * g["cout"] * g["pix"], 4.0 * g["pix"] * (1 + g["cout"])
+    # store-free first block (csrc/layer0.cu): the convolution output never reaches HBM; algorithmic bytes are the
+    # one-channel input + the pooled output (forward) / its gradient (backward)
+    if name == "l0_prep":
+        g = geo[0]
+        return 2.0 * 2 * 9 * g["cout"] * g["pix"], 4.0 * g["pix"] * 2
+    if name == "l0_fwd":
+        g = geo[0]
+        return 2.0 * (9 + g["cout"]) * g["cout"] * g["pix"], 4.0 * g["pix"] * (1 + g["cout"] / 4.0)
+    if name == "l0_bwd":
+        g = geo[0]
+        return 2.0 * (2 * 9 + 3 * g["cout"]) * g["cout"] * g["pix"], 4.0 * g["pix"] * (1 + g["cout"] / 4.0)
     if name == "logmel":
         return 626 * 70e3 * B, 960512.0 * B
     if name.startswith("gru_seq"):
@@ -212,6 +223,7 @@ def kernel_work(name, B, net=NET_2023):
 FAMILIES = [
     ("front end (logmel)", r"^logmel$"),
     ("conv0 (1->16, CUDA cores)", r"^conv0_"),
+    ("first block, store-free (stencil + BN + GLU + pool recomputed)", r"^l0_"),
     ("conv3x3 tcgen05 fwd/dgrad", r"^conv3x3_tc5"),
     ("conv3x3 mma.sync fwd/dgrad", r"^conv3x3_\d"),
     ("conv wgrad tcgen05", r"^conv_wgrad_tc5"),

@@ -59,7 +59,7 @@ class CrnnPlan(C.Structure):
                 ("gdense_w", vp), ("gdense_b", vp), ("gsoft_w", vp), ("gsoft_b", vp),
                 ("classes_mask", vp), ("rnn_drop", vp), ("grnn_drop", vp), ("strong", vp), ("weak", vp), ("sof", vp), ("hsum", vp),
                 ("gstrong", vp), ("gweak", vp),
-                ("zero_fwd", vp), ("zero_fwd_bytes", i64), ("zero_bwd", vp), ("zero_bwd_bytes", i64)]
+                ("zero_fwd", vp), ("zero_fwd_bytes", i64), ("zero_bwd", vp), ("zero_bwd_bytes", i64), ("l0_sums", vp)]
 
 
 _SIGS = {

@@ -216,6 +216,11 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
     return r;
 }
+// Operand rounding for mma.sync TF32 without the three-instruction sequence cvt.rna.tf32 compiles to on sm_100a (FSETP against
+// inf + conditional add + mask): the MMA unit ignores the 13 low mantissa bits of an fp32 operand, so adding half a TF32
+// ulp to the magnitude IS round-to-nearest-ties-away for every finite value (inf / nan do not occur in these operands).
+// ONLY for values that go straight into mma_tf32; anything stored for another consumer keeps to_tf32 (clean low bits).
+__device__ __forceinline__ uint32_t to_tf32_mma(float x) { return __float_as_uint(x) + 0x1000u; }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile(
         "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"

@@ -74,6 +74,13 @@ bool use_glu_tc5(const sedk_crnn_plan* p, const sedk_conv_layer& L) {
     return p->activation == 0 && L.glu_pack != nullptr && L.lin != nullptr && bnglu_tc5_supports(L.T, L.F, L.cout, L.pt, L.pf, p->precision);
 }
 
+// store-free first block (layer0.cu): shipped geometry, GLU, and the caller gave the sums workspace
+bool use_l0_fused(const sedk_crnn_plan* p) {
+    const sedk_conv_layer& L = p->conv[0];
+    return p->l0_sums != nullptr && p->x0 != nullptr && p->activation == 0 && L.cin == 1 &&
+           l0_fused_supports(p->B, L.T, L.F, L.cout, L.pt, L.pf);
+}
+
 template <class... P>
 bool all_aligned16(P... ptrs) {
     return ((((reinterpret_cast<uintptr_t>(ptrs)) & 15) == 0) && ...);
@@ -108,6 +115,12 @@ int validate(const sedk_crnn_plan* p, bool backward) {
     }
     const sedk_conv_layer& last = p->conv[p->n_conv - 1];
     SEDK_REQUIRE(last.F / last.pf == 1, "crnn: the CNN must pool the mel axis down to 1 (got %d)", last.F / last.pf);
+    if (p->l0_sums != nullptr && p->zero_fwd != nullptr && p->zero_fwd_bytes > 0) {
+        const char* lo = (const char*)p->zero_fwd;
+        const char* q = (const char*)p->l0_sums;
+        SEDK_REQUIRE(q >= lo && q + SEDK_L0_SUMS * sizeof(double) <= lo + p->zero_fwd_bytes,
+                     "crnn: l0_sums must lie inside zero_fwd when zero_fwd is used");
+    }
     if (backward) {
         SEDK_REQUIRE(p->training, "crnn backward: the forward pass must have run with training=1");
         SEDK_REQUIRE(p->x0, "crnn backward: x0 workspace missing");
@@ -153,6 +166,19 @@ extern "C" int sedk_crnn_forward(const sedk_crnn_plan* p, void* stream) {
         const int C = L.cout;
         if (p->training && !zf) SEDK_CUDA(cudaMemsetAsync(L.stats, 0, 4 * C * sizeof(double), s));
         double* st = bn_train ? L.stats : nullptr;
+        if (i == 0 && use_l0_fused(p)) {
+            if (bn_train && !zf) SEDK_CUDA(cudaMemsetAsync(p->l0_sums, 0, SEDK_L0_SUMS * sizeof(double), s));
+            rc = launch_l0_prep(p->x, p->x_sb, p->x_sm, p->x_st, p->minmax, p->scaler_eps,
+                                p->training ? p->specaug : nullptr, L.w, L.b, p->x0, st, p->l0_sums, B, L.T, L.F, s);
+            if (rc) return rc;
+            rc = launch_bn_finalize(L.stats, L.gamma, L.beta, L.running_mean, L.running_var, L.num_batches, L.bn,
+                                    (double)B * L.T * L.F, p->bn_eps, p->bn_momentum, bn_train, C, s);
+            if (rc) return rc;
+            rc = launch_l0_fwd(p->x0, L.w, L.b, L.bn, L.glu_w, L.glu_b, L.out, B, L.T, L.F, pdrop, p->seed, p->seed_dev,
+                               (uint64_t)0, p->precision, s);
+            if (rc) return rc;
+            continue;
+        }
         if (i == 0) {
             rc = launch_conv0_fwd(p->x, p->x_sb, p->x_sm, p->x_st, p->minmax, p->scaler_eps,
                                   p->training ? p->specaug : nullptr, L.w, L.b, p->training ? p->x0 : nullptr, L.z, st, B,
@@ -374,6 +400,18 @@ static int crnn_backward_impl(const sedk_crnn_plan* p, int phases, void* stream)
         const int64_t npix = (int64_t)B * L.T * L.F;
         if (!zs) SEDK_CUDA(cudaMemsetAsync(L.stats + 2 * Cc, 0, 2 * Cc * sizeof(double), s));
         if (!zb && L.gglu_b) SEDK_CUDA(cudaMemsetAsync(L.gglu_b, 0, (size_t)Cc * sizeof(float), s));
+        if (i == 0 && use_l0_fused(p)) {
+            if (!zb) {
+                SEDK_CUDA(cudaMemsetAsync(L.gglu_w, 0, (size_t)Cc * Cc * sizeof(float), s));
+                SEDK_CUDA(cudaMemsetAsync(L.gw, 0, (size_t)9 * Cc * sizeof(float), s));
+            }
+            // the GX block of l0_sums is still zero from the forward's clear (only this kernel adds to it)
+            rc = launch_l0_bwd(p->x0, L.w, L.b, L.bn, L.glu_w, L.glu_b, L.gout, L.gglu_w, L.gglu_b, L.stats, p->l0_sums,
+                               L.gw, L.gb, L.ggamma, L.gbeta, B, L.T, L.F, p->bn_eval ? 1 : 0, pdrop, p->seed,
+                               p->seed_dev, (uint64_t)0, p->precision, s);
+            if (rc) return rc;
+            continue;
+        }
         if (use_glu_tc5(p, L)) {
             rc = launch_bnglu_tc5_bwd(L.z, L.bn, L.glu_pack, L.gout, L.lin, L.gy, L.gglu_b, L.stats, B, L.T, L.F, Cc, L.pt,
                                       L.pf, pdrop, p->seed, p->seed_dev, (uint64_t)i, s);

@@ -93,6 +93,24 @@ int launch_glu_wgrad_tc5(const float* z, const float* g_lin, const float* bn, fl
 int launch_bn_bwd_apply(float* gy, const float* z, const float* bn, const double* stats, float* ggamma, float* gbeta,
                         float* gb, double count, int64_t n_pix, int C, int frozen, cudaStream_t s);
 
+// ---- layer0.cu ---------------------------------------------------------------------------------------------
+// First block (1 -> 16 filters, GLU, pooling (2, 2)) with the conv output never written to HBM: see the file header.
+// sums = sedk_crnn_plan.l0_sums (304 doubles: GX [16][9], ZX [16][9], SX [16]), zero before a training forward.
+bool l0_fused_supports(int B, int T, int F, int cout, int pt, int pf);
+// x (strided log-mel) -> x0 [B,T,F] (scaler + SpecAugment); stats != NULL: also sum z / sum z^2 into stats[0..32) and
+// ZX / SX into sums (batch-statistics forward)
+int launch_l0_prep(const float* x, int64_t sb, int64_t sm, int64_t st, const uint32_t* minmax, float scaler_eps,
+                   const int32_t* specaug, const float* w, const float* bias, float* x0, double* stats, double* sums,
+                   int B, int T, int F, cudaStream_t s);
+int launch_l0_fwd(const float* x0, const float* w, const float* bias, const float* bn, const float* glu_w,
+                  const float* glu_b, float* out, int B, int T, int F, float drop_p, uint64_t seed,
+                  const uint64_t* seed_dev, uint64_t drop_stream, int precision, cudaStream_t s);
+// accumulates gglu_w / gglu_b / stats[32..64) / sums.GX, then writes gw (+=), gb, ggamma, gbeta in closed form
+int launch_l0_bwd(const float* x0, const float* w, const float* bias, const float* bn, const float* glu_w,
+                  const float* glu_b, const float* gout, float* gglu_w, float* gglu_b, double* stats, double* sums,
+                  float* gw, float* gb, float* ggamma, float* gbeta, int B, int T, int F, int frozen, float drop_p,
+                  uint64_t seed, const uint64_t* seed_dev, uint64_t drop_stream, int precision, cudaStream_t s);
+
 // ---- gemm.cu ------------------------------------------------------------------------------------------------
 int launch_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
                 int ldb, float beta, float* C, int ldc, const float* bias, int precision, cudaStream_t s);

@@ -67,7 +67,9 @@ class _Workspace:
         self.gflat = self.zero_bwd[:n_grad]
         self.g_offs = g_offs
         gw_off = [n_grad + sum(gw_sizes[:i]) for i in range(n_conv)]
-        self.zero_fwd = new(sum(4 * c for c in cnn.nb_filters), dtype=torch.float64, zero=True)
+        # + the 304 sums of the store-free first block (sedk_crnn_plan.l0_sums), cleared by the same memset
+        n_stats = sum(4 * c for c in cnn.nb_filters)
+        self.zero_fwd = new(n_stats + 304, dtype=torch.float64, zero=True)
         st_off = [sum(4 * c for c in cnn.nb_filters[:i]) for i in range(n_conv)]
         self.gviews = {}
         for (n, p), sz, off in zip(params, sizes, g_offs):
@@ -78,6 +80,7 @@ class _Workspace:
         plan.n_conv = n_conv
         plan.zero_bwd, plan.zero_bwd_bytes = _vp(self.zero_bwd), self.zero_bwd.numel() * 4
         plan.zero_fwd, plan.zero_fwd_bytes = _vp(self.zero_fwd), self.zero_fwd.numel() * 8
+        plan.l0_sums = _vp(self.zero_fwd[n_stats:])
         plan.n_gru = model.rnn.num_layers
         plan.nclass = model.nclass
         plan.bn_eps, plan.bn_momentum = 1e-3, 0.99

@@ -325,7 +325,15 @@ typedef struct {
     int64_t zero_fwd_bytes;
     void* zero_bwd;
     int64_t zero_bwd_bytes;
+    /* Optional: 304 doubles (SEDK_L0_SUMS).  When given, and the first block is 1 -> 16 filters / "glu" / pooling (2, 2)
+     * (the shipped configs; CNN.py:66-98 with i = 0), that block runs with its convolution output recomputed from the
+     * one-channel input instead of stored: conv[0].z and conv[0].gy are not touched, and the BatchNorm backward + conv
+     * weight gradient are evaluated in closed form from sums accumulated here (csrc/layer0.cu).  Must be zero before a
+     * training forward: place it inside zero_fwd when zero_fwd is used (checked), else the forward clears it itself.
+     * NULL: the convolution output goes through HBM (conv0 + BN/GLU kernels). */
+    double* l0_sums;
 } sedk_crnn_plan;
+#define SEDK_L0_SUMS 304
 
 SEDK_API int sedk_crnn_forward(const sedk_crnn_plan* plan, void* stream);
 SEDK_API int sedk_crnn_backward(const sedk_crnn_plan* plan, void* stream);

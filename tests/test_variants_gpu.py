@@ -42,7 +42,7 @@ def _compare(a, b, tol_out, tol_grad):
     assert worst[1] < tol_grad, worst
 
 
-@pytest.mark.parametrize("option", ["gru_v2", "bnglu_small", "bnglu_tc5", "gemm_tc5", "side_stream", "conv_pair", "pdl"])
+@pytest.mark.parametrize("option", ["gru_v2", "bnglu_small", "bnglu_tc5", "gemm_tc5", "side_stream", "conv_pair", "pdl", "l0_fused"])
 @pytest.mark.parametrize("precision,tol_out,tol_grad", [(1, 2e-5, 2e-3), (0, 5e-4, 3e-2)])
 def test_kernel_generations_agree(dev, feats, option, precision, tol_out, tol_grad):
     from desed_task_b200._lib import lib
