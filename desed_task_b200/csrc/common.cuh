@@ -350,6 +350,23 @@ __device__ __forceinline__ bool dropout_keep(const Philox& ph, uint64_t e, uint6
     uint32_t bits = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
     return bits >= thresh;
 }
+// ---------------------------------------------------------------------------------------------
+// One element of the fused EMA + Adam update (include/sedk.h: sedk_adam_ema).  Written with explicit roundings so that
+// every kernel that applies it (elementwise.cu adam_ema_kernel, nvls.cu allreduce_adam_kernel) produces the same bits -
+// left to the compiler, FMA contraction differed between the two.
+__device__ __forceinline__ float ema_elem(float ema, float p, float ema_alpha) {
+    return __fmaf_rn(ema, ema_alpha, __fmul_rn(p, 1.0f - ema_alpha));
+}
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float step_size, float beta1, float beta2,
+                                          float eps, float inv_sqrt_bc2, float grad_scale) {
+    const float gi = __fmul_rn(g, grad_scale);
+    const float mi = __fmaf_rn(__fsub_rn(gi, m), 1.0f - beta1, m);                  // torch: exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = __fmaf_rn(v, beta2, __fmul_rn(__fmul_rn(1.0f - beta2, gi), gi));
+    m = mi;
+    v = vi;
+    const float denom = __fmaf_rn(sqrtf(vi), inv_sqrt_bc2, eps);
+    p = __fmaf_rn(-step_size, __fdiv_rn(mi, denom), p);
+}
 #endif  // __CUDACC__
 
 }  // namespace sedk

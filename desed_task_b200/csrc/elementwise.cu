@@ -194,15 +194,13 @@ adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
     }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float pi = p[i];
-        if (ema) ema[i] = ema[i] * ema_alpha + pi * (1.0f - ema_alpha);
+        if (ema) ema[i] = ema_elem(ema[i], pi, ema_alpha);
         if (do_adam) {
-            float gi = g[i] * grad_scale;
-            float mi = m[i] + (gi - m[i]) * (1.0f - beta1);        // torch: exp_avg.lerp_(grad, 1 - beta1)
-            float vi = v[i] * beta2 + (1.0f - beta2) * gi * gi;
+            float mi = m[i], vi = v[i];
+            adam_elem(pi, g[i], mi, vi, step_size, beta1, beta2, eps, inv_sqrt_bc2, grad_scale);
             m[i] = mi;
             v[i] = vi;
-            float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-            p[i] = pi - step_size * (mi / denom);
+            p[i] = pi;
         }
     }
 }

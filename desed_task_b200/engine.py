@@ -9,6 +9,7 @@ alpha, gradient scale) live in device memory so that a replay sees fresh values.
 reference's order: `random.random()` (mixup yes/no), then for the weak and the strong sub-batch `np.random.beta` +
 `torch.randperm` (data_augm.py:33-35).
 """
+import os
 import random
 
 import numpy as np
@@ -73,10 +74,25 @@ class TrainEngine:
         # (sedk_crnn_backward_phase); "single": one in-graph all-reduce after the backward.  Measured on 2 x B200
         # (profiles/r2_allreduce_modes.txt): eager +24 us per step over N = 1, split +42 us, single +48 us - NCCL kernels
         # captured into the graph cost more than they hide on a 2.2 ms step, so the overlapped schedules stay optional.
+        # "nvls": no NCCL on the step - the flat gradient lives in NVLink-symmetric memory and ONE kernel of this library
+        # (csrc/nvls.cu) reduces it through the switch (multimem.ld_reduce / multimem.st) and applies EMA + Adam, inside the
+        # same CUDA graph as forward / backward, as at N = 1.  Falls back to "eager" where symmetric memory is unavailable.
         import os
         self.ar_mode = os.environ.get("SEDK_AR_MODE", "eager")
-        if self.ar_mode not in ("eager", "split", "single"):
-            raise ValueError("SEDK_AR_MODE must be eager, split or single")
+        if self.ar_mode not in ("eager", "split", "single", "nvls"):
+            raise ValueError("SEDK_AR_MODE must be nvls, eager, split or single")
+        self.nvls = None
+        if self.world > 1 and self.ar_mode == "nvls":
+            from . import nvls
+            self.nvls = nvls.try_create(process_group, next(student.parameters()).device)
+            if self.nvls is None:
+                self.ar_mode = "eager"
+            else:
+                student.grad_alloc = self.nvls.alloc
+                if os.environ.get("SEDK_NVLS_ALLOC_ONLY", "0") == "1":       # diagnostic: symmetric gradient region, NCCL reduce
+                    self.nvls, self.ar_mode = None, "eager"
+        elif self.ar_mode == "nvls":
+            self.ar_mode = "eager"
         if self.world > 1 and self.ar_mode == "eager":
             self.graph_optimizer = False
         self.grad_clip = grad_clip
@@ -260,7 +276,20 @@ class TrainEngine:
 
     def _optimizer_part(self):
         ws = self.ws
-        if self.world > 1 and not getattr(self, "_reduced", False):
+        if self.nvls is not None:
+            if not self.nvls.connected:
+                if ws.zero_bwd.data_ptr() != self.nvls.buf.data_ptr():
+                    raise RuntimeError("the student's gradient region is not the symmetric allocation")
+                # measured on 2 x B200 (profiles/r2_nvls_check.txt): with two ranks plain peer loads / stores beat the
+                # multicast round trip through the switch (29.6 vs 32.2 us); from 4 ranks on P2P traffic grows with the world
+                mc = os.environ.get("SEDK_NVLS_MULTICAST", "auto")
+                self.nvls.connect(use_multicast=(self.world > 2) if mc == "auto" else mc != "0")
+            clip = bool(self.grad_clip and self.grad_clip > 0)
+            # the whole flat gradient in one launch; with clipping the update follows the norm (all-reduce only here)
+            self.nvls.step(self.opt, ws.gflat.numel(), self.t_flat, self.hyper, do_adam=not clip)
+            if not clip:
+                return
+        elif self.world > 1 and not getattr(self, "_reduced", False):
             ddp.allreduce_sum_(ws.gflat, self.pg)
         if self.grad_clip and self.grad_clip > 0:
             # 2024 recipe: gradient_clip 5.0 (pretrained.yaml:17) - norm of the (averaged) gradient, on device

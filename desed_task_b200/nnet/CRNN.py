@@ -63,7 +63,13 @@ class _Workspace:
         gw_sizes = [0] + [9 * chans[i + 1] * chans[i] for i in range(1, n_conv)]
         from ..optim import flat_layout
         g_offs, n_grad = flat_layout(sizes)       # the same 16-byte-aligned layout as the flat parameter buffer
-        self.zero_bwd = new(n_grad + sum(gw_sizes), zero=True)
+        # data parallel: the engine may supply the region from NVLink-symmetric memory (desed_task_b200/nvls.py)
+        galloc = getattr(model, "grad_alloc", None)
+        if galloc is not None:
+            self.zero_bwd = galloc(n_grad + sum(gw_sizes))
+            self.bufs.append(self.zero_bwd)
+        else:
+            self.zero_bwd = new(n_grad + sum(gw_sizes), zero=True)
         self.gflat = self.zero_bwd[:n_grad]
         self.g_offs = g_offs
         gw_off = [n_grad + sum(gw_sizes[:i]) for i in range(n_conv)]
@@ -337,6 +343,7 @@ class CRNN(nn.Module):
         # (torch.save(module), Lightning ddp_spawn); they are rebuilt on the first forward
         state = dict(self.__dict__)
         state["_ws"] = {}
+        state.pop("grad_alloc", None)          # process-local symmetric-memory allocator (desed_task_b200/nvls.py)
         return state
 
     # ------------------------------------------------------------------------------------------------------------
@@ -382,6 +389,8 @@ class CRNN(nn.Module):
         memo[id(self)] = new
         import copy
         for k, v in self.__dict__.items():
+            if k == "grad_alloc":
+                continue
             new.__dict__[k] = {} if k == "_ws" else copy.deepcopy(v, memo)
         new._instance = CRNN._next_instance()
         return new

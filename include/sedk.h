@@ -158,6 +158,25 @@ SEDK_API int sedk_adam_ema(float* p, const float* g, float* m, float* v, float* 
  * values: hyper[4] = { lr / (1 - beta1^step), 1 / sqrt(1 - beta2^step), ema_alpha, grad_scale }. */
 SEDK_API int sedk_adam_ema_dev(float* p, const float* g, float* m, float* v, float* ema, int64_t n, int do_adam, float beta1,
                       float beta2, float eps, const float* hyper, void* stream);
+/* Data-parallel step without NCCL: gradient all-reduce (SUM) over NVLink / NVSwitch peer memory fused with the update above
+ * in ONE launch (csrc/nvls.cu).  There is no reference counterpart (train_sed.py:269-276 refuses > 1 GPU); it replaces
+ * `dist.all_reduce(flat_grad)` + sedk_adam_ema_dev of this library's own data-parallel path.
+ *   g_peers[world]    the flat gradient buffer of EVERY rank as mapped into this process (g_peers[rank] is the local one,
+ *                     n floats each, 16-byte aligned) - a symmetric allocation, e.g. torch.distributed._symmetric_memory;
+ *   g_mc              the multicast address covering all of them (NVLS: the switch reduces on multimem.ld_reduce and
+ *                     replicates on multimem.st), or NULL: peers are read / written one by one (P2P);
+ *   flag_peers[world] per-rank flag blocks of sedk_nvls_flag_bytes() bytes, zero before the first call, same mapping rule.
+ * On return (stream order) every rank's gradient buffer holds the sum - each element reduced exactly once, so replicas stay
+ * bit-identical - and, with do_adam = 1, p / m / v / ema have been updated as by sedk_adam_ema_dev (hyper[3] = 1 / world
+ * folds the mean).  do_adam = 0: all-reduce only (gradient clipping needs the global norm first).  Every rank must make
+ * the same sequence of calls; world <= 8 (one NVSwitch domain).  Capturable in a CUDA graph. */
+SEDK_API int64_t sedk_nvls_flag_bytes(void);
+/* diagnostic (option "nvls_debug" = 1): device-clock stamps (ns) of CTA 0 in the last launch - start, after barrier A,
+ * after phase 1, after barrier B, end */
+SEDK_API int sedk_nvls_debug_stamps(uint64_t* out5);
+SEDK_API int sedk_allreduce_adam_nvls(float* p, float* m, float* v, float* ema, int64_t n, int do_adam, float beta1,
+                             float beta2, float eps, const float* hyper, void* g_mc, void* const* g_peers,
+                             void* const* flag_peers, int rank, int world, void* stream);
 /* *counter += inc (one thread); pair with sedk_crnn_plan.seed_dev */
 SEDK_API int sedk_bump_counter(uint64_t* counter, uint64_t inc, void* stream);
 /* SpecAugment / dropstep span draws on the device (CRNN.apply_specaugment, desed_task/nnet/CRNN.py:207-219 and :288-293;
