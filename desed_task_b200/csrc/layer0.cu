@@ -7,9 +7,9 @@
 // cheaper to recompute (9 FMA per element) than to load, and the tail of the backward collapses into reductions because
 // nothing upstream needs a data gradient:
 //
-//   l0_x0     x (strided log-mel) -> x0 [B, T, F] (scaled, masked)
+//   l0_x0     x (strided log-mel) -> x0 [B, T, F] (scaled, masked) (+ border sums that give SX[tap] = sum_pix x0(pix + tap))
 //   l0_stats  (batch-statistics forward only) the sums that depend on x alone:  sum z, sum z^2 (BatchNorm),
-//             SX[tap] = sum_pix x0(pix + tap),  ZX[c][tap] = sum_pix z_c x0(pix + tap)
+//             ZX[c][tap] = sum_pix z_c x0(pix + tap)
 //   l0_fwd    x0 -> stencil -> BN -> gate GEMM -> sigmoid -> dropout -> 2x2 average pool -> out          (no z0 in HBM)
 //   l0_bwd    g_out, x0 -> recompute up to the gate, g_y in registers -> S1 = sum g_y, S2 = sum g_y zhat,
 //             GX[c][tap] = sum_pix g_y,c x0(pix + tap), gate weight / bias gradients                       (no g_y / g_z in HBM)
@@ -40,11 +40,16 @@ constexpr int P_FW = 128;               // pixel columns per CTA
 constexpr int P_HS = 129;               // tile row stride (odd: conflict-free transposing store)
 
 // ---------------------------------------------------------------------------------------------------------------------
+// sums != NULL: also the nine sums from which SX[tap] = sum over output pixels of x0(pix + tap) follows in closed form
+// (l0_finish: the shifted window covers everything except one border row and / or column): total, first / last row,
+// first / last column, four corners - accumulated over the batch in sums[L0_SX ..].
 __global__ void __launch_bounds__(256)
 l0_x0_kernel(const float* __restrict__ x, int64_t sb, int64_t sm, int64_t st, const uint32_t* __restrict__ minmax,
-             float scaler_eps, const int32_t* __restrict__ specaug, float* __restrict__ x0, int T, int F) {
+             float scaler_eps, const int32_t* __restrict__ specaug, float* __restrict__ x0, double* __restrict__ sums, int T,
+             int F) {
     pdl_enter();
     __shared__ float til[32 * P_HS];
+    __shared__ float s_b[9];
     const int tid = threadIdx.x;
     const int nTf = (F + P_FW - 1) / P_FW;
     const int nTt = (T + 31) / 32;
@@ -77,11 +82,31 @@ l0_x0_kernel(const float* __restrict__ x, int64_t sb, int64_t sm, int64_t st, co
         }
         til[hr * P_HS + hc] = y;
     }
+    if (tid < 9) s_b[tid] = 0.f;
     __syncthreads();
+    float tot = 0.f, r0 = 0.f, rl = 0.f, c0 = 0.f, cl = 0.f;
     for (int idx = tid; idx < 32 * P_FW; idx += 256) {
         const int r = idx / P_FW, c = idx - r * P_FW;
-        if (t0 + r < T && f0 + c < F) x0[((size_t)b * T + t0 + r) * F + f0 + c] = til[r * P_HS + c];
+        const int t = t0 + r, f = f0 + c;
+        if (t < T && f < F) {
+            const float y = til[r * P_HS + c];
+            x0[((size_t)b * T + t) * F + f] = y;
+            tot += y;
+            if (t == 0) r0 += y;
+            if (t == T - 1) rl += y;
+            if (f == 0) c0 += y;
+            if (f == F - 1) cl += y;
+            if (sums != nullptr && (t == 0 || t == T - 1) && (f == 0 || f == F - 1))
+                atomicAdd(&s_b[5 + (t == 0 ? 0 : 2) + (f == 0 ? 0 : 1)], y);
+        }
     }
+    if (sums == nullptr) return;
+    tot = warp_sum(tot); r0 = warp_sum(r0); rl = warp_sum(rl); c0 = warp_sum(c0); cl = warp_sum(cl);
+    if ((tid & 31) == 0) {
+        atomicAdd(&s_b[0], tot); atomicAdd(&s_b[1], r0); atomicAdd(&s_b[2], rl); atomicAdd(&s_b[3], c0); atomicAdd(&s_b[4], cl);
+    }
+    __syncthreads();
+    if (tid < 9 && s_b[tid] != 0.f) atomicAdd(&sums[L0_SX + tid], (double)s_b[tid]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -93,11 +118,11 @@ struct Strips {
 
 struct Walk {
     int col, b, fg, trow, trow1;
-    const float *pl, *pc, *pr;     // x0 + (b T + 0) F + 8 fg + g + {-1, 0, +1}: the lane's three columns at row 0; a
-    float ml, mr;                  // neighbour column outside the image aliases the centre one and gets mask 0
+    const float* prow;     // x0 + (b T + 0) F + (8 fg - 1 + min(lane, 9)), clamped into the row: lanes 0..9 fetch the ten
+    float mcol;            // columns under the warp's 8 pixels (+ halo), one load per row; 0 for a column outside the image
 };
 
-__device__ __forceinline__ Walk walk_begin(const Strips& sp, int item, const float* __restrict__ x0, int g) {
+__device__ __forceinline__ Walk walk_begin(const Strips& sp, int item, const float* __restrict__ x0, int lane) {
     Walk w;
     w.col = item / sp.cpc;
     const int ch = item - w.col * sp.cpc;
@@ -105,35 +130,30 @@ __device__ __forceinline__ Walk walk_begin(const Strips& sp, int item, const flo
     w.fg = w.col - w.b * sp.gpr;
     w.trow = ch * sp.L;
     w.trow1 = min(sp.To, w.trow + sp.L);
-    const int f = 8 * w.fg + g;
-    w.pc = x0 + (size_t)w.b * sp.T * sp.F + f;
-    const bool okl = f > 0, okr = f + 1 < sp.F;
-    w.pl = w.pc - (okl ? 1 : 0); w.ml = okl ? 1.f : 0.f;
-    w.pr = w.pc + (okr ? 1 : 0); w.mr = okr ? 1.f : 0.f;
+    const int f = 8 * w.fg - 1 + min(lane, 9);
+    w.prow = x0 + (size_t)w.b * sp.T * sp.F + min(max(f, 0), sp.F - 1);
+    w.mcol = (f >= 0 && f < sp.F) ? 1.f : 0.f;
     return w;
 }
 
 typedef float2 Row[3];     // one input row under the lane (3 columns), each value in both halves of a packed pair
 
-// zero outside the image; branch-free: clamped addresses, 0 / 1 masks (the first version's predicated loads compiled to
-// three divergence regions per row)
-// A row is fetched one step ahead as raw values (fetch_row: the three loads + the row mask, nothing that waits for the
-// data) and turned into masked packed pairs only after the current step's arithmetic (finish_row): the first version
-// multiplied by the masks right behind the loads and stalled every step for the full L2 latency.
+// A row is fetched one step ahead as a raw value (fetch_row: ONE load per row for the whole warp + the mask, nothing that
+// waits for the data) and turned into the lane's three masked packed pairs only after the current step's arithmetic
+// (finish_row: the mask multiply and three shuffles from lanes g, g + 1, g + 2): the first version loaded 3 values per
+// lane and multiplied by the masks right behind the loads, stalling every step for the full L2 latency.
 // Zero outside the image, branch-free: clamped addresses, 0 / 1 masks.  LOW: t may be negative (first row of a column).
 struct RawRow {
-    float l, c, r, mt;
+    float v, m;
 };
 template <bool LOW>
 __device__ __forceinline__ void fetch_row(RawRow& q, const Walk& w, const Strips& sp, int t) {
-    q.mt = ((!LOW || t >= 0) && t < sp.T) ? 1.f : 0.f;
-    const int off = min(LOW ? max(t, 0) : t, sp.T - 1) * sp.F;           // < 2^31: make_strips bounds B T F
-    q.l = __ldg(w.pl + off);
-    q.c = __ldg(w.pc + off);
-    q.r = __ldg(w.pr + off);
+    q.m = ((!LOW || t >= 0) && t < sp.T) ? w.mcol : 0.f;
+    q.v = __ldg(w.prow + min(LOW ? max(t, 0) : t, sp.T - 1) * sp.F);       // offset < 2^31: make_strips bounds B T F
 }
-__device__ __forceinline__ void finish_row(Row& r, const RawRow& q, const Walk& w) {
-    const float l = q.l * (w.ml * q.mt), c = q.c * q.mt, rr = q.r * (w.mr * q.mt);
+__device__ __forceinline__ void finish_row(Row& r, const RawRow& q, int g) {
+    const float v = q.v * q.m;
+    const float l = __shfl_sync(0xffffffffu, v, g), c = __shfl_sync(0xffffffffu, v, g + 1), rr = __shfl_sync(0xffffffffu, v, g + 2);
     r[0] = make_float2(l, l);
     r[1] = make_float2(c, c);
     r[2] = make_float2(rr, rr);
@@ -142,7 +162,7 @@ __device__ __forceinline__ void finish_row(Row& r, const RawRow& q, const Walk& 
 // Walk the item's steps with a ring of six rows: step(ra, rb, rc, rd, trow) sees the four rows 2 trow - 1 .. 2 trow + 2
 // while the two rows of the next step are in flight; three inlined copies of the body rotate the ring without moves.
 template <class Step>
-__device__ __forceinline__ void walk_rows(const Walk& w, const Strips& sp, Step&& step) {
+__device__ __forceinline__ void walk_rows(const Walk& w, const Strips& sp, int g, Step&& step) {
     Row r0, r1, r2, r3, r4, r5;
     RawRow qa, qb;
     {
@@ -151,21 +171,21 @@ __device__ __forceinline__ void walk_rows(const Walk& w, const Strips& sp, Step&
         fetch_row<true>(q1, w, sp, 2 * w.trow);
         fetch_row<true>(qa, w, sp, 2 * w.trow + 1);
         fetch_row<true>(qb, w, sp, 2 * w.trow + 2);
-        finish_row(r0, q0, w); finish_row(r1, q1, w); finish_row(r2, qa, w); finish_row(r3, qb, w);
+        finish_row(r0, q0, g); finish_row(r1, q1, g); finish_row(r2, qa, g); finish_row(r3, qb, g);
     }
     int trow = w.trow;
     while (true) {
         fetch_row<false>(qa, w, sp, 2 * trow + 3); fetch_row<false>(qb, w, sp, 2 * trow + 4);
         step(r0, r1, r2, r3, trow);
-        finish_row(r4, qa, w); finish_row(r5, qb, w);
+        finish_row(r4, qa, g); finish_row(r5, qb, g);
         if (++trow >= w.trow1) break;
         fetch_row<false>(qa, w, sp, 2 * trow + 3); fetch_row<false>(qb, w, sp, 2 * trow + 4);
         step(r2, r3, r4, r5, trow);
-        finish_row(r0, qa, w); finish_row(r1, qb, w);
+        finish_row(r0, qa, g); finish_row(r1, qb, g);
         if (++trow >= w.trow1) break;
         fetch_row<false>(qa, w, sp, 2 * trow + 3); fetch_row<false>(qb, w, sp, 2 * trow + 4);
         step(r4, r5, r0, r1, trow);
-        finish_row(r2, qa, w); finish_row(r3, qb, w);
+        finish_row(r2, qa, g); finish_row(r3, qb, g);
         if (++trow >= w.trow1) break;
     }
 }
@@ -249,9 +269,9 @@ l0_stats_kernel(const float* __restrict__ x0, const float* __restrict__ w, const
                 double* __restrict__ stats, double* __restrict__ sums, Strips sp) {
     pdl_enter();
     constexpr int C = L0C;
-    __shared__ float red[2 * C + C * 9 + 16];                 // sum z, sum z^2, ZX, SX
+    __shared__ float red[2 * C + C * 9];                      // sum z, sum z^2, ZX
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
-    for (int i = tid; i < 2 * C + C * 9 + 16; i += 128) red[i] = 0.f;
+    for (int i = tid; i < 2 * C + C * 9; i += 128) red[i] = 0.f;
     L0Weights W;
     W.load(w, bias, t4);
     const float2 zero2 = make_float2(0.f, 0.f);
@@ -260,14 +280,12 @@ l0_stats_kernel(const float* __restrict__ x0, const float* __restrict__ w, const
     for (int ep = 0; ep < 2; ep++)
 #pragma unroll
         for (int k = 0; k < 9; k++) zx[ep][k] = zero2;
-    // SX: the four lanes of a pixel column share its 9 taps: lane t4 sums taps t4, t4 + 4 (and 8 when t4 == 0)
-    float sx[3] = {0.f, 0.f, 0.f};
     __syncthreads();
 
     const int nwarps = gridDim.x * 4;
     for (int item = blockIdx.x * 4 + warp; item < sp.items; item += nwarps) {
-        const Walk wk = walk_begin(sp, item, x0, g);
-        walk_rows(wk, sp, [&](const Row& ra, const Row& rb, const Row& rc, const Row& rd, int) {
+        const Walk wk = walk_begin(sp, item, x0, lane);
+        walk_rows(wk, sp, g, [&](const Row& ra, const Row& rb, const Row& rc, const Row& rd, int) {
             float2 z[2][2];
             stencil_row(z[0], ra, rb, rc, W);
             stencil_row(z[1], rb, rc, rd, W);
@@ -280,14 +298,6 @@ l0_stats_kernel(const float* __restrict__ x0, const float* __restrict__ w, const
                 }
             tap_sums(zx, z[0], ra, rb, rc);
             tap_sums(zx, z[1], rb, rc, rd);
-            // x0(pix + tap) of pixel row 0 = (ra, rb, rc)[tap / 3][tap % 3], of pixel row 1 = (rb, rc, rd)[..]
-            const float a0 = t4 == 0 ? ra[0].x : t4 == 1 ? ra[1].x : t4 == 2 ? ra[2].x : rb[0].x;
-            const float a1 = t4 == 0 ? rb[1].x : t4 == 1 ? rb[2].x : t4 == 2 ? rc[0].x : rc[1].x;
-            const float c0 = t4 == 0 ? rb[0].x : t4 == 1 ? rb[1].x : t4 == 2 ? rb[2].x : rc[0].x;
-            const float c1 = t4 == 0 ? rc[1].x : t4 == 1 ? rc[2].x : t4 == 2 ? rd[0].x : rd[1].x;
-            sx[0] += a0 + c0;
-            sx[1] += a1 + c1;
-            sx[2] += rc[2].x + rd[2].x;
         });
     }
     // reduce over the 8 mel bins g of the warp (lanes with equal t4), then the CTA (shared atomics), then fp64 atomics
@@ -303,8 +313,6 @@ l0_stats_kernel(const float* __restrict__ x0, const float* __restrict__ w, const
 #pragma unroll
         for (int k = 0; k < 9; k++) { zx[ep][k].x = over_g(zx[ep][k].x); zx[ep][k].y = over_g(zx[ep][k].y); }
     }
-#pragma unroll
-    for (int k = 0; k < 3; k++) sx[k] = over_g(sx[k]);
     if (g == 0) {
 #pragma unroll
         for (int ep = 0; ep < 2; ep++) {
@@ -317,14 +325,10 @@ l0_stats_kernel(const float* __restrict__ x0, const float* __restrict__ w, const
                 atomicAdd(&red[2 * C + (ch + 1) * 9 + k], zx[ep][k].y);
             }
         }
-        atomicAdd(&red[2 * C + C * 9 + t4], sx[0]);
-        atomicAdd(&red[2 * C + C * 9 + t4 + 4], sx[1]);
-        if (t4 == 0) atomicAdd(&red[2 * C + C * 9 + 8], sx[2]);
     }
     __syncthreads();
     if (tid < 2 * C) atomicAdd(&stats[tid], (double)red[tid]);
     for (int i = tid; i < C * 9; i += 128) atomicAdd(&sums[L0_ZX + i], (double)red[2 * C + i]);
-    if (tid < 9) atomicAdd(&sums[L0_SX + tid], (double)red[2 * C + C * 9 + tid]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -357,12 +361,12 @@ l0_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ w, const f
 
     const int nwarps = gridDim.x * 8;
     for (int item = blockIdx.x * 8 + warp; item < sp.items; item += nwarps) {
-        Walk wk = walk_begin(sp, item, x0, g);
+        Walk wk = walk_begin(sp, item, x0, lane);
         DropBits<NB> db;
         if (drop) db.begin(ph, wk, lane, dstream);
         // pooled output pixel of this lane pair: [b, trow, 4 fg + g / 2], channels 4 t4 ..
         float* op = out + (((size_t)wk.b * sp.To + wk.trow) * Fo + 4 * wk.fg + (g >> 1)) * C + 4 * t4;
-        walk_rows(wk, sp, [&](const Row& ra, const Row& rb, const Row& rc, const Row& rd, int trow) {
+        walk_rows(wk, sp, g, [&](const Row& ra, const Row& rb, const Row& rc, const Row& rd, int trow) {
             float2 z[2][2];
             stencil_row(z[0], ra, rb, rc, W);
             stencil_row(z[1], rb, rc, rd, W);
@@ -460,12 +464,12 @@ l0_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ w, const f
 
     const int nwarps = gridDim.x * 8;
     for (int item = blockIdx.x * 8 + warp; item < sp.items; item += nwarps) {
-        Walk wk = walk_begin(sp, item, x0, g);
+        Walk wk = walk_begin(sp, item, x0, lane);
         DropBits<NB> db;
         if (drop) db.begin(ph, wk, lane, dstream);
         const float* gp = gout + (((size_t)wk.b * sp.To + wk.trow) * Fo + 4 * wk.fg + (g >> 1)) * C + 4 * t4;
         float4 gon = __ldg(reinterpret_cast<const float4*>(gp));
-        walk_rows(wk, sp, [&](const Row& ra, const Row& rb, const Row& rc, const Row& rd, int trow) {
+        walk_rows(wk, sp, g, [&](const Row& ra, const Row& rb, const Row& rc, const Row& rd, int trow) {
             const float4 go = gon;
             gp += (size_t)Fo * C;
             if (trow + 1 < wk.trow1) gon = __ldg(reinterpret_cast<const float4*>(gp));
@@ -629,7 +633,19 @@ __global__ void l0_finish_kernel(const double* __restrict__ stats, const double*
         if (frozen) {
             v = scale * GX;
         } else {
-            const double SX = sums[L0_SX + tap], ZX = sums[L0_ZX + i];
+            // the window of tap (dy, dx) misses the last row (dy = 0) / first row (dy = 2) and the last / first column
+            const double* b = sums + L0_SX;          // total, row 0, row T-1, column 0, column F-1, corners 00 0L L0 LL
+            const int dy = tap / 3, dx = tap - 3 * dy;
+            double SX = b[0];
+            if (dy == 0) SX -= b[2];
+            if (dy == 2) SX -= b[1];
+            if (dx == 0) SX -= b[4];
+            if (dx == 2) SX -= b[3];
+            if (dy == 0 && dx == 0) SX += b[8];
+            if (dy == 0 && dx == 2) SX += b[7];
+            if (dy == 2 && dx == 0) SX += b[6];
+            if (dy == 2 && dx == 2) SX += b[5];
+            const double ZX = sums[L0_ZX + i];
             v = scale * (GX - S1 * inv_count * SX - S2 * inv_count * invstd * (ZX - mean * SX));
         }
         gw[i] += (float)v;
@@ -689,7 +705,7 @@ int launch_l0_prep(const float* x, int64_t sb, int64_t sm, int64_t st, const uin
         SEDK_PROF("l0_x0", s);
         const int grid = B * cdiv(T, 32) * cdiv(F, P_FW);
         SEDK_CUDA(pdl_launch(l0_x0_kernel, dim3(grid), dim3(256), (size_t)(0), s, x, sb, sm, st, minmax, scaler_eps, specaug,
-                             x0, T, F));
+                             x0, stats != nullptr ? sums : nullptr, T, F));
         SEDK_LAUNCH_CHECK("l0_x0_kernel");
     }
     if (stats != nullptr) {
