@@ -506,11 +506,16 @@ def run_ours(args):
                              "heads, losses, optimizer fp32",
                 "l2": "inputs rotate over %d distinct batches (%.0f MB > L2); per-step activations ~0.6 GB"
                       % (NBUF, NBUF * B * L_SAMPLES * 4 / 1e6),
-                "cuda_graph": "forward + loss + backward (+ fused EMA/Adam at N = 1): one graph replay per step; at N > 1 the "
-                              "NCCL all-reduce and the optimizer kernel follow the graph as eager launches",
+                "cuda_graph": "forward + loss + backward (+ fused EMA/Adam at N = 1): one graph replay per step; at N > 1 "
+                              + ("the gradient all-reduce is this library's own NVLink kernel fused with EMA + Adam "
+                                 "(csrc/nvls.cu, multimem.ld_reduce / multimem.st over symmetric memory), inside the same graph"
+                                 if getattr(eng, "ar_mode", "") == "nvls" else
+                                 "the NCCL all-reduce and the optimizer kernel follow the graph as eager launches"),
+                "first_block": "store-free (csrc/layer0.cu): conv0 output recomputed from the one-channel input, BN backward + "
+                               "conv0 weight gradient in closed form" if L.sedk_get_option(b"l0_fused", 1) else "conv0 output through HBM",
                 "embeddings": ("pre-pooled bf16 [768, 156]" if args.emb_pooled else "fp32 [768, 496]") if is_2024 else None,
                 "audio_input": "int16 PCM (x / 32768 in the front end)" if args.pcm16 else "fp32 waveform",
-                "settle_steps": args.settle, "allreduce": os.environ.get("SEDK_AR_MODE", "eager"),
+                "settle_steps": args.settle, "allreduce": getattr(eng, "ar_mode", None) if world > 1 else None,
                 "overlap": "front end of step k+1 runs on its own stream concurrently with step k's graph (ping-pong "
                            "log-mel buffers); weight-gradient GEMMs on a side branch of the graph"}
         out = {

@@ -89,6 +89,7 @@ _SIGS = {
     "sedk_adam_ema_dev": (i32, [vp, vp, vp, vp, vp, i64, i32, f32, f32, f32, vp, vp]),
     "sedk_nvls_flag_bytes": (i64, []),
     "sedk_nvls_debug_stamps": (i32, [vp]),
+    "sedk_nvls_fault": (i32, []),
     "sedk_allreduce_adam_nvls": (i32, [vp, vp, vp, vp, i64, i32, f32, f32, f32, vp, vp, vp, vp, i32, i32, vp]),
     "sedk_bump_counter": (i32, [vp, u64, vp]),
     "sedk_sumsq": (i32, [vp, i64, vp, vp]),

@@ -28,6 +28,8 @@ namespace {
 
 constexpr int NV_MAX_WORLD = 8;
 constexpr int NV_GRID = 256;               // flag slots per barrier; the launch uses option "nvls_grid" (<= NV_GRID, default 128) CTAs
+__device__ unsigned int nv_fault;           // set when a barrier wait exceeded NV_TIMEOUT_NS (a peer is gone): no endless spin
+constexpr unsigned long long NV_TIMEOUT_NS = 10ull * 1000 * 1000 * 1000;
 __device__ unsigned long long nv_dbg[8];   // globaltimer stamps of CTA 0 (option "nvls_debug"): start, barrier A, phase 1, barrier B, end
 constexpr int NV_THREADS = 512;
 
@@ -59,7 +61,15 @@ __device__ __forceinline__ void cross_barrier(const NvArgs& a, int slot, uint32_
         const int peer = threadIdx.x;
         st_release_sys(a.fpeer[peer] + (size_t)slot * NV_MAX_WORLD + a.rank, epoch);
         const uint32_t* local = a.fpeer[a.rank] + (size_t)slot * NV_MAX_WORLD + peer;
-        while ((int32_t)(ld_acquire_sys(local) - epoch) < 0) { }
+        unsigned long long t0 = 0;
+        for (uint32_t spins = 1; (int32_t)(ld_acquire_sys(local) - epoch) < 0; spins++) {
+            if ((spins & 0xfffu) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > NV_TIMEOUT_NS) { nv_fault = 1u; break; }
+            }
+        }
     }
     __syncthreads();
 }
@@ -267,4 +277,12 @@ extern "C" int sedk_nvls_debug_stamps(uint64_t* out5) {
     SEDK_CUDA(cudaMemcpyFromSymbol(h, nv_dbg, sizeof(h)));
     for (int i = 0; i < 5; i++) out5[i] = h[i];
     return SEDK_OK;
+}
+
+// 1 if a barrier of sedk_allreduce_adam_nvls timed out since the last call (then the buffers of this process are invalid); clears it
+extern "C" int sedk_nvls_fault(void) {
+    unsigned int h = 0, z = 0;
+    if (cudaMemcpyFromSymbol(&h, nv_fault, sizeof(h)) != cudaSuccess) return -1;
+    if (h != 0) cudaMemcpyToSymbol(nv_fault, &z, sizeof(z));
+    return (int)h;
 }

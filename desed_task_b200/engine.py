@@ -68,30 +68,21 @@ class TrainEngine:
             self.world = torch.distributed.get_world_size(process_group)
         # the gradient all-reduce and the fused EMA + Adam kernel are captured in the same CUDA graph as forward / backward
         self.graph_optimizer = bool(graph_optimizer) and use_graph
-        # data-parallel all-reduce schedule (env SEDK_AR_MODE).  "eager" (default): the graph ends with the backward, one NCCL
+        # data-parallel all-reduce schedule (env SEDK_AR_MODE).  "eager": the graph ends with the backward, one NCCL
         # all-reduce of the flat gradient and the fused EMA + Adam kernel follow as eager launches (issued while the graph
         # still runs).  "split": three slices reduced inside the graph underneath the rest of the backward
         # (sedk_crnn_backward_phase); "single": one in-graph all-reduce after the backward.  Measured on 2 x B200
         # (profiles/r2_allreduce_modes.txt): eager +24 us per step over N = 1, split +42 us, single +48 us - NCCL kernels
         # captured into the graph cost more than they hide on a 2.2 ms step, so the overlapped schedules stay optional.
-        # "nvls": no NCCL on the step - the flat gradient lives in NVLink-symmetric memory and ONE kernel of this library
+        # "nvls" (default): no NCCL on the step - the flat gradient lives in NVLink-symmetric memory and ONE kernel of this library
         # (csrc/nvls.cu) reduces it through the switch (multimem.ld_reduce / multimem.st) and applies EMA + Adam, inside the
         # same CUDA graph as forward / backward, as at N = 1.  Falls back to "eager" where symmetric memory is unavailable.
         import os
-        self.ar_mode = os.environ.get("SEDK_AR_MODE", "eager")
+        self.ar_mode = os.environ.get("SEDK_AR_MODE", "nvls")
         if self.ar_mode not in ("eager", "split", "single", "nvls"):
             raise ValueError("SEDK_AR_MODE must be nvls, eager, split or single")
         self.nvls = None
-        if self.world > 1 and self.ar_mode == "nvls":
-            from . import nvls
-            self.nvls = nvls.try_create(process_group, next(student.parameters()).device)
-            if self.nvls is None:
-                self.ar_mode = "eager"
-            else:
-                student.grad_alloc = self.nvls.alloc
-                if os.environ.get("SEDK_NVLS_ALLOC_ONLY", "0") == "1":       # diagnostic: symmetric gradient region, NCCL reduce
-                    self.nvls, self.ar_mode = None, "eager"
-        elif self.ar_mode == "nvls":
+        if self.ar_mode == "nvls" and self.world <= 1:
             self.ar_mode = "eager"
         if self.world > 1 and self.ar_mode == "eager":
             self.graph_optimizer = False
@@ -160,6 +151,39 @@ class TrainEngine:
         if teacher is not None:
             teacher.seed_dev = self.seed_ctr
         self.ws = None
+        if self.world > 1 and self.ar_mode == "nvls":
+            self._setup_nvls(process_group)
+
+    def _setup_nvls(self, process_group):
+        """Collective: allocate the student's gradient region in NVLink-symmetric memory, exchange the handles, agree over the
+        group that every rank succeeded - otherwise every rank falls back to the NCCL schedule ("eager")."""
+        from . import nvls
+        student, dev = self.student, self.dev
+        obj = nvls.try_create(process_group, dev)
+        ok, why = obj is not None, ""
+        if ok:
+            try:
+                student.grad_alloc = obj.alloc
+                ws = student._workspace(self.B, self.mel_spec.n_mels, self.T, dev,
+                                        tuple(self.emb_shape) if self.emb_shape else None)
+                if ws.zero_bwd.data_ptr() != obj.buf.data_ptr():
+                    raise RuntimeError("the student's gradient region is not the symmetric allocation")
+                # measured (profiles/r2_nvls_check.txt): with two ranks plain peer loads / stores beat the multicast round
+                # trip through the switch (29.8 vs 31.8 us); at eight the switch reduction wins (37.0 vs 44.0 us)
+                mc = os.environ.get("SEDK_NVLS_MULTICAST", "auto")
+                obj.connect(use_multicast=(self.world > 2) if mc == "auto" else mc != "0")
+            except Exception as e:      # noqa: BLE001 - any failure means "use the NCCL path"
+                ok, why = False, "%s: %s" % (type(e).__name__, e)
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=process_group)
+        if int(flag.item()) == 1:
+            self.nvls = obj
+            return
+        if why:
+            import sys
+            print("[desed_task_b200] fused NVLink all-reduce unavailable (%s); using NCCL" % why, file=sys.stderr)
+        self.nvls, self.ar_mode, self.graph_optimizer = None, "eager", False
+        student.grad_alloc = None
 
     def _host_views(self, r):
         NP = self.NP
@@ -277,13 +301,6 @@ class TrainEngine:
     def _optimizer_part(self):
         ws = self.ws
         if self.nvls is not None:
-            if not self.nvls.connected:
-                if ws.zero_bwd.data_ptr() != self.nvls.buf.data_ptr():
-                    raise RuntimeError("the student's gradient region is not the symmetric allocation")
-                # measured on 2 x B200 (profiles/r2_nvls_check.txt): with two ranks plain peer loads / stores beat the
-                # multicast round trip through the switch (29.6 vs 32.2 us); from 4 ranks on P2P traffic grows with the world
-                mc = os.environ.get("SEDK_NVLS_MULTICAST", "auto")
-                self.nvls.connect(use_multicast=(self.world > 2) if mc == "auto" else mc != "0")
             clip = bool(self.grad_clip and self.grad_clip > 0)
             # the whole flat gradient in one launch; with clipping the update follows the norm (all-reduce only here)
             self.nvls.step(self.opt, ws.gflat.numel(), self.t_flat, self.hyper, do_adam=not clip)
@@ -489,7 +506,15 @@ class TrainEngine:
         for b, c in snap:
             b.copy_(c)
 
+    def _check_nvls(self):
+        # the query synchronises the device: every 64th read is enough to turn a lost peer into an error instead of garbage
+        self._nvls_reads = getattr(self, "_nvls_reads", 0) + 1
+        if self.nvls is not None and self._nvls_reads % 64 == 1 and lib().sedk_nvls_fault() != 0:
+            raise RuntimeError("fused NVLink all-reduce: a peer did not reach the barrier within 10 s (rank lost?); the "
+                               "optimizer state of this process is no longer valid")
+
     def read_losses(self, r=None):
+        self._check_nvls()
         """Losses of ring slot r (default: last step): {total, bce_strong, bce_weak, mse_strong, mse_weak, ...}."""
         if r is None:
             r = (self.step_idx - 1) % self.ring

@@ -35,7 +35,8 @@ class NvlsGradient:
         if self.buf is not None:
             if self.buf.numel() == numel:
                 return self.buf
-            raise RuntimeError("one symmetric gradient region per engine (a second workspace shape was requested)")
+            # another batch shape of the same module (e.g. validation): ordinary memory, that workspace is not reduced here
+            return torch.zeros(int(numel), dtype=torch.float32, device=self.device)
         self.buf = self.symm.empty(int(numel), dtype=torch.float32, device=self.device)
         self.buf.zero_()
         return self.buf

@@ -171,6 +171,9 @@ SEDK_API int sedk_adam_ema_dev(float* p, const float* g, float* m, float* v, flo
  * folds the mean).  do_adam = 0: all-reduce only (gradient clipping needs the global norm first).  Every rank must make
  * the same sequence of calls; world <= 8 (one NVSwitch domain).  Capturable in a CUDA graph. */
 SEDK_API int64_t sedk_nvls_flag_bytes(void);
+/* A barrier wait inside sedk_allreduce_adam_nvls gives up after 10 s (a peer process died): returns 1 once if that happened
+ * since the last call (synchronises the device), 0 otherwise.  After a fault the buffers of this process are invalid. */
+SEDK_API int sedk_nvls_fault(void);
 /* diagnostic (option "nvls_debug" = 1): device-clock stamps (ns) of CTA 0 in the last launch - start, after barrier A,
  * after phase 1, after barrier B, end */
 SEDK_API int sedk_nvls_debug_stamps(uint64_t* out5);

@@ -99,6 +99,9 @@ def family(name):
         return "bnglu_pool_fwd_c" + c
     if "bnglu_small_bwd" in n or "bnglu_bwd" in n:
         return "bnglu_pool_bwd_c" + c
+    for k in ("l0_x0", "l0_stats", "l0_fwd", "l0_bwd", "l0_finish"):
+        if k + "_kernel" in n:
+            return k
     if "conv0_fwd" in n:
         return "conv0_fwd"
     if "conv0_wgrad" in n:
