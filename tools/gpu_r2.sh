@@ -55,7 +55,7 @@ if has launches; then
 fi
 if has hot; then
     timeout 800 ncu --profile-from-start off --set full --clock-control none --import-source on \
-        -c 140 \
+        -c 105 \
         -f -o /tmp/${TAG}_hot python tools/profile_step.py supervised > $OUT/${TAG}_ncu_hot.log 2>&1
     stamp "ncu hot capture exit $?"
     ncu -i /tmp/${TAG}_hot.ncu-rep --page raw --csv > $OUT/${TAG}_hot_raw.csv 2>/dev/null

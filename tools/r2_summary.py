@@ -46,12 +46,19 @@ def main():
             wl, d["value"], d["ms_per_step"], d["e2e"]["value"], d["repeats"]["ms_per_step_min"],
             d["repeats"]["ms_per_step_median"], lib.get("best", "-"), d.get("vs_gpu_library", "-"),
             ("%s clips/s (%s, %s threads)" % (cpu.get("value"), cpu.get("kind"), cpu.get("cores"))) if cpu else "-"))
-    for f, label in (("r2i_bench_n2.json", "supervised N=2"), ("r2m_bench_supervised_n8.json", "supervised N=8"),
-                     ("r2m_bench_mean_teacher_n8.json", "mean_teacher N=8 (48 clips/GPU)"),
-                     ("r2m_bench_inference_n8.json", "inference N=8 (64 clips/GPU)")):
+    multi = (("r2N_bench_n2_supervised.json", "r2_bench_n2.json", "supervised N=2 (fused NVLink all-reduce + Adam)"),
+             ("r2N_bench_n2_mean_teacher.json", "r2_bench_mean_teacher_n2.json", "mean_teacher N=2 (48 clips/GPU, nvls)"),
+             ("r2N_bench_n2_dcase2024.json", "r2_bench_dcase2024_n2.json", "dcase2024 N=2 (nvls all-reduce, clip, Adam)"),
+             ("r2M_bench_n8_nvls.json", "r2_bench_supervised_n8.json", "supervised N=8 (fused NVLink all-reduce + Adam)"),
+             ("r2M_bench_n8_eager.json", "r2_bench_supervised_n8_nccl.json", "supervised N=8 (SEDK_AR_MODE=eager: NCCL)"),
+             ("r2m_bench_mean_teacher_n8.json", "r2_bench_mean_teacher_n8.json",
+              "mean_teacher N=8 (48 clips/GPU; NCCL schedule, before the store-free first block)"),
+             ("r2m_bench_inference_n8.json", "r2_bench_inference_n8.json",
+              "inference N=8 (64 clips/GPU; before the store-free first block)"))
+    for f, dst, label in multi:
         d = jl(os.path.join(OUT, f))
         if d is not None:
-            shutil.copy(os.path.join(OUT, f), os.path.join(PROF, "r2_" + f.split("_", 1)[1]))
+            shutil.copy(os.path.join(OUT, f), os.path.join(PROF, dst))
             md.append("| %s | %s | %s | %s | %s / %s | | | |" % (label, d["value"], d["ms_per_step"], d["e2e"]["value"],
                                                              d["repeats"]["ms_per_step_min"], d["repeats"]["ms_per_step_median"]))
     ref = jl(os.path.join(OUT, "%s_bench_ref.json" % tag))
