@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "desed_task_b200", "lib", "libsedk.so")
-OPS = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UBLKCP", "SYNCS", "UTCBAR", "HMMA", "FFMA2", "FADD2", "FMUL2",
+OPS = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UBLKCP", "SYNCS", "UTCBAR", "LDGMC", "HMMA", "FFMA2", "FADD2", "FMUL2",
        "FFMA", "MUFU", "SHFL", "LDS", "STS", "LDG", "STG", "RED", "ATOM", "UCGABAR", "MAPA", "BAR"]
 
 
@@ -49,6 +49,8 @@ def main():
     print("# kernels on legacy mma.sync (HMMA):", ", ".join(uses("HMMA")))
     print("# kernels using packed fp32 (FFMA2/FADD2/FMUL2):", ", ".join(sorted(set(uses("FFMA2")) | set(uses("FADD2")) | set(uses("FMUL2")))))
     print("# kernels with cluster barriers / DSMEM (UCGABAR / MAPA):", ", ".join(sorted(set(uses("UCGABAR")) | set(uses("MAPA")))))
+    print("# kernels reducing through the NVSwitch (LDGMC = multimem.ld_reduce; multimem.st is an STG to the multicast address):",
+          ", ".join(uses("LDGMC")))
 
 
 if __name__ == "__main__":
