@@ -77,5 +77,31 @@ def build(force=False, verbose=False):
     return LIB
 
 
+IO_SRC = os.path.join(HERE, "csrc_io", "sedkio.c")
+IO_LIB = os.path.join(LIBDIR, "libsedkio.so")
+
+
+def build_io(force=False):
+    """The host-side input library (include/sedk_io.h: PCM16 WAV decode + int16 shards): plain C, gcc, no CUDA."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    stamp = os.path.join(LIBDIR, "libsedkio.sha256")
+    h = hashlib.sha256()
+    for f in (IO_SRC, os.path.join(ROOT, "include", "sedk_io.h")):
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    dig = h.hexdigest()
+    if not force and os.path.exists(IO_LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return IO_LIB
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=c11", "-Wall", "-Wextra", "-fPIC", "-shared", "-fvisibility=hidden",
+           "-pthread", IO_SRC, "-o", IO_LIB]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("gcc failed for %s:\n%s\n%s" % (IO_SRC, r.stdout, r.stderr))
+    with open(stamp, "w") as f:
+        f.write(dig)
+    return IO_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_io(force="--force" in sys.argv))
