@@ -101,6 +101,12 @@ def main():
                      ("r2b_ubench.txt", "r2_ubench.txt"), ("r2a_library_bar.json", "r2_library_bar_first_pass.json")):
         if os.path.exists(os.path.join(OUT, src)):
             shutil.copy(os.path.join(OUT, src), os.path.join(PROF, dst))
+    for title, f in (("Store-free first block: A/B against the kernels it replaces (tools/diag_l0.py, tools/bench_ab.py)", "r2_layer0_ab.txt"),
+                     ("Fused NVLink all-reduce + Adam: check and timing at 2 and 8 ranks (tools/nvls_check.py)", "r2_nvls_check.txt"),
+                     ("Host-side input path on the build container's CPU (tools/bench_io.py)", "r2_io_cpu.txt")):
+        fp = os.path.join(PROF, f)
+        if os.path.exists(fp):
+            md += ["", "## " + title, "", "```", open(fp).read().rstrip(), "```"]
     open(os.path.join(PROF, "r2_summary.md"), "w").write("\n".join(md) + "\n")
     print("\n".join(md)[:3000])
 
